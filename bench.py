@@ -1,0 +1,275 @@
+#!/usr/bin/env python
+"""
+bench.py -- SGLD voxel-steps/s of the B200-native registration step (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # own arm (under torchrun for N > 1)
+    python bench.py --impl reference --steps K --warmup W     # the reference's CPU path (oracle port) on the host cores
+
+One "step" = one SGLD transition (reference Trainer._SGLD_transition) of every chain resident on the GPU.
+Workload (N = 1): BASELINE.json configs[1] -- 128^3 synthetic brain-MRI-shaped pair, LCC + 4-component GMM data term,
+virtual decimation, uniform jitter, Sobolev s=3, RegLoss_LogNormal, 12 SVF steps, ONE chain.  N > 1: every rank runs
+the same number of chains on its own GPU (weak scaling), no per-iteration collective; the Welford moments are merged
+with NCCL once after the timed region (reported, not part of the metric).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BYTES_PER_VOXEL_STEP_LCC = 895.0  # 175 + 60 * n_svf
+BYTES_PER_VOXEL_STEP_SSD = 875.0
+SVF_BWD_BYTES_PER_VOXEL = 36.0    # read g_{k+1} 12 + u_k 12, write g_k 12
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.isfile(path):
+        with open(path) as f:
+            return float(json.load(f)['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+class ClockSampler:
+    """samples nvidia-smi clocks / throttle reasons during the timed region"""
+    Q = 'clocks.sm,clocks.max.sm,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,' \
+        'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,' \
+        'clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(index), f'--query-gpu={self.Q}',
+                                          '--format=csv,noheader,nounits', '-lms', '100'], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.thread.join(timeout=2)
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = sorted({n for r in self.rows if len(r) >= 7 for n, v in zip(names, r[3:7]) if v == 'Active'})
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': mx[0] if mx else None, 'reasons': reasons,
+                'samples': len(sm)}
+
+
+def oracle_transition_rate(n, steps, warmup, chains=1, data='lcc'):
+    """times the oracle port of Trainer._SGLD_transition on the host cores; returns (voxel-steps/s, ms/step, threads)"""
+    import torch
+    from oracle import sgld_oracle as O
+    from irsgmcmc_b200.data_loader.synthetic import make_pair
+    torch.set_num_threads(os.cpu_count() or 1)
+    torch.manual_seed(123)
+    fixed, moving, vp = make_pair(n)
+    cfg = O.Config(data=data, K=4 if data == 'lcc' else 1, reg='lognormal' if data == 'lcc' else 'l2',
+                   w_reg=1.6 if data == 'lcc' else 1.4)
+    sigma = torch.exp(0.5 * vp['log_var']).expand(chains, -1, -1, -1, -1)
+    v0 = vp['mu'] + sigma * torch.randn(chains, 3, n, n, n) + 0.1 * torch.randn(1)
+    st = O.State(cfg, v0, sigma, (n, n, n))
+    O.gmm_init(st, fixed, moving, v0[:1], warm_up=5)
+    for _ in range(warmup):
+        O.sgld_transition(st, fixed, moving)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        O.sgld_transition(st, fixed, moving)
+    dt = time.perf_counter() - t0
+    return chains * n ** 3 * steps / dt, 1e3 * dt / max(steps, 1), torch.get_num_threads()
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path = the oracle port (the reference is Python on
+    PyTorch; /root/reference does not travel to the GPU box), all host threads, rank 0 only."""
+    if int(os.environ.get('RANK', '0')) != 0:
+        return
+    n = args.size
+    # bounded sample: keep (steps + warmup) transitions within a few minutes; voxel-steps/s is volume-normalised
+    rate64, ms64, threads = oracle_transition_rate(64, 1, 1, 1, args.data)
+    budget_s = 150.0
+    est = (ms64 / 1e3) * (n / 64.0) ** 3 * (args.steps + args.warmup)
+    n_run = n if est <= budget_s else 64
+    value, ms, threads = oracle_transition_rate(n_run, args.steps, args.warmup, 1, args.data)
+    sample = f'{args.steps} timed + {args.warmup} warm-up oracle transitions at {n_run}^3, 1 chain, fp32, {threads} threads'
+    line = {'impl': 'reference', 'metric': 'SGLD voxel-steps/s', 'value': value, 'unit': 'voxel-steps/s',
+            'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': workload_config(args, 1, n_run),
+            'cpu_baseline': {'value': value, 'unit': 'voxel-steps/s', 'cores': threads, 'kind': 'port', 'sample': sample},
+            'e2e': {'value': value, 'unit': 'voxel-steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, chains, n):
+    return {'workload': f'{n}^3 synthetic brain-MRI-shaped pair, {"LCC+GMM(K=4,s=2)" if args.data == "lcc" else "SSD(K=1)"} '
+                        f'data term, virtual decimation, uniform jitter 0.1, Sobolev s=3, '
+                        f'{"RegLoss_LogNormal w=1.6 learnable" if args.data == "lcc" else "RegLoss_L2 w=1.4"}, SVF 12 steps, '
+                        f'tau 0.4, VI-shaped init; {chains} SGLD chain(s) per GPU (BASELINE.json configs[1])',
+            'volume': [n, n, n], 'chains_per_gpu': chains, 'parallelism': 'independent chains sharded by rank',
+            'l2_policy': 'working set per transition (SVF history 288 MiB/chain at 128^3 + 20 field-sized buffers) '
+                         'exceeds the 126 MB L2; no explicit flush'}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=200)
+    ap.add_argument('--warmup', type=int, default=10)
+    ap.add_argument('--impl', default='own', choices=['own', 'reference'])
+    ap.add_argument('--size', type=int, default=128)
+    ap.add_argument('--chains', type=int, default=1, help='chains per GPU')
+    ap.add_argument('--data', default='lcc', choices=['lcc', 'ssd'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-graph', action='store_true')
+    ap.add_argument('--e2e-steps', type=int, default=0, help='default: min(steps, 50)')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        return run_reference(args)
+    if args.warmup < 3:
+        args.warmup = 3
+
+    import torch
+    import torch.distributed as dist
+    from irsgmcmc_b200.sampler import SGLDSampler, SGLDConfig
+    from irsgmcmc_b200.data_loader.synthetic import make_pair
+    from irsgmcmc_b200 import parallel
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise RuntimeError('bench.py needs a CUDA device: there is no CPU path (use --impl reference for the CPU baseline)')
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=dev)
+
+    n, C = args.size, args.chains
+    V = n ** 3
+    fixed, moving, vp = make_pair(n)
+    reg = 'RegLoss_LogNormal' if args.data == 'lcc' else 'RegLoss_L2'
+    cfg = SGLDConfig(data_loss=args.data, reg_loss=reg, w_reg=1.6 if args.data == 'lcc' else 1.4,
+                     reg_learnable=args.data == 'lcc')
+    sampler = SGLDSampler(fixed, moving, C, cfg, device=dev, chain_offset=rank * C)
+    gen = torch.Generator(device=dev).manual_seed(123 + rank)
+    sampler.init_chains('VI', vp, generator=gen)
+    sampler.init_gmm()
+    use_graph = not args.no_graph
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput ----
+    sampler.step(args.warmup, use_graph=use_graph)
+    barrier()
+    clocks = ClockSampler(local_rank) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    sampler.step(args.steps, use_graph=use_graph)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clock_info = clocks.stop() if clocks else None
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * C * V * args.steps / (ms_max * 1e-3)
+
+    # ---- end to end through the public API with host buffers ----
+    e2e_steps = args.e2e_steps or min(args.steps, 50)
+    pin = lambda x: x.contiguous().pin_memory()
+    h_fixed, h_moving, h_mask = pin(fixed['im']), pin(moving['im']), pin(fixed['mask'].view(torch.uint8))
+    h_stats = torch.empty(C, 8, dtype=torch.float64).pin_memory()
+    h2d = h_fixed.numel() * 4 + h_moving.numel() * 4 + h_mask.numel()
+    d2h = h_stats.numel() * 8
+
+    def e2e_step():
+        sampler.load_images(h_fixed, h_moving, h_mask)   # pinned host -> device, fixed-side LCC terms recomputed
+        sampler.step(1, use_graph=use_graph)
+        h_stats.copy_(sampler.stats, non_blocking=True)  # loss terms / alpha / energy of every chain
+        torch.cuda.current_stream().synchronize()         # the caller reads the result
+
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    e0.record()
+    for _ in range(e2e_steps):
+        e2e_step()
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * C * V * e2e_steps / (float(t.item()) * 1e-3)
+
+    # ---- dominant kernel: one SVF adjoint step (svf_step_bwd_kernel), CUDA events around the 12-step adjoint ----
+    peak, peak_src = measured_peaks()
+    stage_ms = {k: 0.0 for k in sampler.STAGES}
+    n_prof = 5
+    for _ in range(n_prof):
+        for k, v in sampler.profile_stages().items():
+            stage_ms[k] += v / n_prof
+    svf_steps = cfg.svf_steps
+    kernel_ms = stage_ms['svf_adjoint'] / svf_steps
+    achieved = SVF_BWD_BYTES_PER_VOXEL * C * V / (kernel_ms * 1e-3) / 1e9
+    bytes_step = BYTES_PER_VOXEL_STEP_LCC if args.data == 'lcc' else BYTES_PER_VOXEL_STEP_SSD
+    step_gbs = bytes_step * (value / world) / 1e9
+
+    # ---- posterior moments: Welford update + NCCL merge (once per run; outside the metric) ----
+    sampler.accumulate()
+    barrier()
+    e0.record()
+    mom = sampler.posterior_moments()
+    e1.record()
+    barrier()
+    merge_ms = e0.elapsed_time(e1)
+
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        n_cpu = n if n <= 128 else 128
+        v_cpu, ms_cpu, threads = oracle_transition_rate(n_cpu, 2, 0, 1, args.data)
+        cpu = {'value': v_cpu, 'unit': 'voxel-steps/s', 'cores': threads, 'kind': 'port',
+               'sample': f'2 oracle transitions (oracle/sgld_oracle.py, torch CPU fp32, {threads} threads) at {n_cpu}^3, '
+                         f'1 chain, {ms_cpu:.0f} ms each'}
+
+    if rank == 0:
+        line = {'metric': 'SGLD voxel-steps/s', 'value': value, 'unit': 'voxel-steps/s', 'n_gpus': world,
+                'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_max / args.steps,
+                'iterations_per_s': args.steps / (ms_max * 1e-3), 'higher_is_better': True, 'scaling': 'weak',
+                'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': workload_config(args, C, n),
+                'e2e': {'value': e2e_value, 'unit': 'voxel-steps/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+                        'steps': e2e_steps},
+                'gpu_launches': sampler.launches_per_step() * args.steps,
+                'roofline': {'bound': 'hbm', 'kernel': 'svf_step_bwd_kernel', 'achieved': achieved, 'peak': peak,
+                             'unit': 'GB/s', 'frac': achieved / peak, 'traffic': None, 'peak_source': peak_src,
+                             'algorithmic_bytes_per_launch': SVF_BWD_BYTES_PER_VOXEL * C * V, 'kernel_ms': kernel_ms},
+                'step_roofline': {'bytes_per_voxel_step': bytes_step, 'achieved_gbs_per_gpu': step_gbs,
+                                  'frac': step_gbs / peak},
+                'stage_ms': {k: round(v, 4) for k, v in stage_ms.items()},
+                'moments_merge_ms': merge_ms, 'graph': use_graph, 'clocks': clock_info, 'cpu_baseline': cpu}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,442 @@
+// irs_data.cu -- data term: LCC normalisation as separable box filters over shared-memory tiles with halos, its adjoint,
+// the Gaussian-mixture log-density with warp-shuffle reductions, virtual decimation.
+// (reference model/loss.py:87-114, utils/util.py:330-347,446-485, trainer/trainer.py:68-77,316-327)
+#include "irs_kernels.cuh"
+
+namespace {
+
+constexpr int TX = 32, TY = 8, TZ = 8;  // output tile; 256 threads = TX x TY, each marches TZ planes in the last pass
+
+enum { BOX_FWD_MEAN = 0, BOX_FWD_VAR = 1, BOX_BWD_VAR = 2, BOX_BWD_MEAN = 3 };
+
+// weight of input offset o for output position j in the ADJOINT of a replicate-padded box of half width S:
+// the out-of-range window positions of a border voxel were clamped onto it in the forward pass (fold)
+__device__ __forceinline__ float adj_weight(int j, int o, int n, int S) {
+    float w = 1.f;
+    if (j == 0 && o >= 0) w += (float)(S - o);
+    if (j == n - 1 && o <= 0) w += (float)(S + o);
+    return w;
+}
+
+// One 3-D box filter (forward: replicate padding; backward: its adjoint) over a TZ x TY x TX tile with halo S, with a
+// fused pre-operation on the loaded values and a fused epilogue:
+//   FWD_MEAN : in0 = I                       -> out0 = a = I - box(I)/k^3
+//   FWD_VAR  : in0 = a (pre: a^2), in1 = zF  -> out0 = rs = 1/sqrt(box/k^3 + 1e-10), out1 = z = zF - a rs  (zF null: a rs)
+//   BWD_VAR  : in0 = g, in1 = a, in2 = rs (pre: -g a rs^3 / 2) -> out0 = ga = g rs + 2 a adjbox/k^3        (g = sign * in0)
+//   BWD_MEAN : in0 = ga                      -> out0 = ga - adjbox/k^3
+template <int MODE>
+__global__ void __launch_bounds__(256)
+box_tile_kernel(const float* __restrict__ in0, const float* __restrict__ in1, const float* __restrict__ in2,
+                float sign, float* __restrict__ out0, float* __restrict__ out1, int S, IrsDims d) {
+    extern __shared__ float smem[];
+    const int EX = TX + 2 * S, EY = TY + 2 * S, EZ = TZ + 2 * S;
+    float* A = smem;                 // EZ x EY x EX  (input tile; reused for the y-pass result EZ x TY x TX)
+    float* B = smem + EZ * EY * EX;  // EZ x EY x TX  (x-pass result)
+    constexpr bool BWD = (MODE == BOX_BWD_VAR || MODE == BOX_BWD_MEAN);
+
+    const long long V = d.V();
+    const int c = blockIdx.y;
+    const int tiles_x = (d.W + TX - 1) / TX, tiles_y = (d.H + TY - 1) / TY;
+    const int bx = blockIdx.x % tiles_x, by = (blockIdx.x / tiles_x) % tiles_y, bz = blockIdx.x / (tiles_x * tiles_y);
+    const int x0 = bx * TX, y0 = by * TY, z0 = bz * TZ;
+    const size_t off = (size_t)c * V;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    // ---- load tile + halo with the pre-operation ----
+    for (int row = warp; row < EZ * EY; row += 8) {
+        const int tz = row / EY, ty = row % EY;
+        const int gz = z0 - S + tz, gy = y0 - S + ty;
+        for (int tx = lane; tx < EX; tx += 32) {
+            const int gx = x0 - S + tx;
+            float val;
+            if (!BWD) {
+                const long long gi = ((long long)irs_clampi(gz, 0, d.D - 1) * d.H + irs_clampi(gy, 0, d.H - 1)) * d.W +
+                                     irs_clampi(gx, 0, d.W - 1);
+                const float a = __ldg(in0 + off + gi);
+                val = (MODE == BOX_FWD_VAR) ? a * a : a;
+            } else {
+                val = 0.f;
+                if (gz >= 0 && gz < d.D && gy >= 0 && gy < d.H && gx >= 0 && gx < d.W) {
+                    const long long gi = ((long long)gz * d.H + gy) * d.W + gx;
+                    if (MODE == BOX_BWD_VAR) {
+                        const float g = sign * __ldg(in0 + off + gi), a = __ldg(in1 + off + gi), r = __ldg(in2 + off + gi);
+                        val = -0.5f * g * a * r * r * r;
+                    } else {
+                        val = __ldg(in0 + off + gi);
+                    }
+                }
+            }
+            A[(tz * EY + ty) * EX + tx] = val;
+        }
+    }
+    __syncthreads();
+
+    // ---- x pass: B[tz][ty][x] = sum_o w A[tz][ty][x + S + o] ----
+    {
+        const int gx = x0 + lane;
+        for (int row = warp; row < EZ * EY; row += 8) {
+            const float* a = A + row * EX + lane + S;
+            float acc = 0.f;
+            for (int o = -S; o <= S; ++o) acc += (BWD ? adj_weight(gx, o, d.W, S) : 1.f) * a[o];
+            B[row * TX + lane] = acc;
+        }
+    }
+    __syncthreads();
+
+    // ---- y pass: A[tz][y][x] = sum_o w B[tz][y + S + o][x]   (A reused as EZ x TY x TX) ----
+    for (int row = warp; row < EZ * TY; row += 8) {
+        const int tz = row / TY, ty = row % TY;
+        const int gy = y0 + ty;
+        const float* b = B + (tz * EY + ty + S) * TX + lane;
+        float acc = 0.f;
+        for (int o = -S; o <= S; ++o) acc += (BWD ? adj_weight(gy, o, d.H, S) : 1.f) * b[o * TX];
+        A[row * TX + lane] = acc;
+    }
+    __syncthreads();
+
+    // ---- z pass + epilogue: thread (warp = y, lane = x) walks the TZ output planes ----
+    const int gx = x0 + lane, gy = y0 + warp;
+    if (gx >= d.W || gy >= d.H) return;
+    const float inv_k3 = 1.0f / (float)((2 * S + 1) * (2 * S + 1) * (2 * S + 1));
+    for (int tz = 0; tz < TZ; ++tz) {
+        const int gz = z0 + tz;
+        if (gz >= d.D) break;
+        const float* a = A + ((tz + S) * TY + warp) * TX + lane;
+        float acc = 0.f;
+        for (int o = -S; o <= S; ++o) acc += (BWD ? adj_weight(gz, o, d.D, S) : 1.f) * a[o * TY * TX];
+        const float box = acc * inv_k3;
+        const size_t gi = off + ((size_t)gz * d.H + gy) * d.W + gx;
+        if (MODE == BOX_FWD_MEAN) {
+            out0[gi] = in0[gi] - box;
+        } else if (MODE == BOX_FWD_VAR) {
+            const float rs = 1.0f / sqrtf(box + 1e-10f);
+            const float zn = in0[gi] * rs;
+            if (out0 != nullptr) out0[gi] = rs;
+            if (out1 != nullptr) out1[gi] = in1 != nullptr ? in1[gi - off] - zn : zn;
+        } else if (MODE == BOX_BWD_VAR) {
+            out0[gi] = sign * in0[gi] * in2[gi] + 2.0f * in1[gi] * box;
+        } else {
+            out0[gi] = in0[gi] - box;
+        }
+    }
+}
+
+template <int MODE>
+int launch_box(const float* in0, const float* in1, const float* in2, float sign, float* out0, float* out1, int S, int C,
+               IrsDims d, cudaStream_t st) {
+    const int EX = TX + 2 * S, EY = TY + 2 * S, EZ = TZ + 2 * S;
+    const size_t smem = sizeof(float) * ((size_t)EZ * EY * EX + (size_t)EZ * EY * TX);
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(box_tile_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        if (e != cudaSuccess) return (int)e;
+        configured = true;
+    }
+    if (smem > 96 * 1024) return IRS_ERR_UNSUPPORTED;
+    const int tiles = ((d.W + TX - 1) / TX) * ((d.H + TY - 1) / TY) * ((d.D + TZ - 1) / TZ);
+    dim3 grid(tiles, C);
+    box_tile_kernel<MODE><<<grid, 256, smem, st>>>(in0, in1, in2, sign, out0, out1, S, d);
+    return (int)cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// mixture statistics of one chain with the CURRENT parameters, then (last block) virtual decimation factor + Adam step
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float masked_vd_residual(const IrsGmm& g, const float* __restrict__ z,
+                                                    const unsigned char* __restrict__ mask, long long i) {
+    return mask[i] ? irs_gmm_vd_residual(g, __ldg(z + i)) : 0.f;
+}
+
+// mode 0: fused path (parameters from `hyper`, Adam step + table/alpha outputs; alpha_fixed != null reuses a stored
+//         factor instead of recomputing it -- the 25 warm-up steps of trainer.py:544-547)
+// mode 1: op-level VD factor only (mixture passed by value)
+// mode 2: VD factor with the parameters in `hyper`, no Adam step
+template <int MODE>
+__global__ void __launch_bounds__(256)
+gmm_stats_kernel(const float* __restrict__ z, const unsigned char* __restrict__ mask, double* __restrict__ hyper,
+                 IrsGmm table_in, IrsHyperCfg cfg, double* __restrict__ partials, unsigned int* __restrict__ counter,
+                 double* __restrict__ stats_row, float* __restrict__ table_out, double* __restrict__ alpha_out,
+                 const double* __restrict__ alpha_fixed, IrsDims d) {
+    __shared__ IrsGmm g;
+    __shared__ double sh[IRS_SUM_COUNT * 32];
+    __shared__ double total[IRS_SUM_COUNT];
+    if (threadIdx.x == 0) {
+        if (MODE != 1) irs_gmm_table(hyper + IRS_HYPER_LOG_STD, hyper + IRS_HYPER_LOGITS, cfg.K, g);
+        else g = table_in;
+    }
+    __syncthreads();
+    const IrsGmm gl = g;
+    const long long V = d.V();
+    const long long sy = d.W, sz = (long long)d.W * d.H;
+    float acc[IRS_SUM_COUNT];
+#pragma unroll
+    for (int k = 0; k < IRS_SUM_COUNT; ++k) acc[k] = 0.f;
+
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < V; i += (long long)gridDim.x * blockDim.x) {
+        if (!mask[i]) continue;  // off the mask r = 0: no contribution to any sum
+        const int x = (int)(i % d.W), y = (int)((i / d.W) % d.H), zc = (int)(i / sz);
+        const float zi = z[i];
+        float rho[IRS_MAX_K], wp;
+        const float lp = irs_gmm_eval(gl, zi, rho, wp);
+        const float z2 = zi * zi, r = z2 * wp;
+        acc[IRS_SUM_NLL] -= lp;
+        acc[IRS_SUM_RR] += r * r;
+        if (cfg.virtual_decimation) {
+            if (zc < d.D - 1) acc[IRS_SUM_RD] += r * masked_vd_residual(gl, z, mask, i + sz);
+            if (y < d.H - 1) acc[IRS_SUM_RH] += r * masked_vd_residual(gl, z, mask, i + sy);
+            if (x < d.W - 1) acc[IRS_SUM_RW] += r * masked_vd_residual(gl, z, mask, i + 1);
+        }
+#pragma unroll
+        for (int k = 0; k < IRS_MAX_K; ++k) if (k < gl.K) {
+            acc[IRS_SUM_RHO + k] += rho[k];
+            acc[IRS_SUM_Q + k] += rho[k] * z2 * gl.prec[k];
+        }
+    }
+    double blk[IRS_SUM_COUNT];
+    irs_block_sum<IRS_SUM_COUNT>(acc, blk, sh);
+    if (!irs_grid_sum<IRS_SUM_COUNT>(blk, partials, counter, total)) return;
+    if (threadIdx.x != 0) return;
+
+    double n_mask = cfg.n_mask;
+    if (!(n_mask > 0.0)) {  // responsibilities sum to one per masked voxel
+        n_mask = 0.0;
+        for (int k = 0; k < cfg.K; ++k) n_mask += total[IRS_SUM_RHO + k];
+    }
+    double alpha = cfg.virtual_decimation ? irs_vd_alpha(total, n_mask) : 1.0;
+    if (MODE == 1) { *alpha_out = alpha; return; }
+    if (MODE == 2) { stats_row[IRS_STAT_ALPHA] = irs_round_f32(alpha); return; }
+    if (alpha_fixed != nullptr) alpha = *alpha_fixed;
+    const double alpha32 = irs_round_f32(alpha);  // a fp32 scalar in the reference
+    irs_gmm_adam_step(hyper, cfg, total, alpha32);
+    IrsGmm up;
+    irs_gmm_table(hyper + IRS_HYPER_LOG_STD, hyper + IRS_HYPER_LOGITS, cfg.K, up);
+    for (int k = 0; k < IRS_MAX_K; ++k) { table_out[k] = up.lw[k]; table_out[IRS_MAX_K + k] = up.prec[k]; }
+    stats_row[IRS_STAT_ALPHA] = alpha32;
+    stats_row[IRS_STAT_NLL_PRE] = total[IRS_SUM_NLL];
+}
+
+// g_z = alpha_c z sum_k rho_k prec_k on the mask (dL/dz of alpha * NLL with the chain's UPDATED mixture), and the
+// data term alpha_c * NLL_c for logging
+__global__ void __launch_bounds__(256)
+gmm_grad_kernel(const float* __restrict__ z_all, const unsigned char* __restrict__ mask,
+                const float* __restrict__ tables, int K, double* __restrict__ stats, float* __restrict__ g_all,
+                double* __restrict__ partials, unsigned int* __restrict__ counters, IrsDims d) {
+    __shared__ double sh[32];
+    __shared__ double total[1];
+    const int c = blockIdx.y;
+    const long long V = d.V();
+    IrsGmm g;
+    g.K = K;
+#pragma unroll
+    for (int k = 0; k < IRS_MAX_K; ++k) { g.lw[k] = __ldg(tables + c * 16 + k); g.prec[k] = __ldg(tables + c * 16 + 8 + k); }
+    const float alpha = (float)stats[(size_t)c * IRS_STAT_SIZE + IRS_STAT_ALPHA];
+    const float* z = z_all + (size_t)c * V;
+    float* go = g_all + (size_t)c * V;
+    float nll = 0.f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < V; i += (long long)gridDim.x * blockDim.x) {
+        float gz = 0.f;
+        if (mask[i]) {
+            float rho[IRS_MAX_K], wp;
+            const float zi = z[i];
+            nll -= irs_gmm_eval(g, zi, rho, wp);
+            gz = alpha * zi * wp;
+        }
+        go[i] = gz;
+    }
+    double blk[1];
+    irs_block_sum<1>(&nll, blk, sh);
+    if (irs_grid_sum<1>(blk, partials + (size_t)c * gridDim.x, counters + c, total)) {
+        if (threadIdx.x == 0) stats[(size_t)c * IRS_STAT_SIZE + IRS_STAT_DATA] = (double)alpha * total[0];
+    }
+}
+
+// op-level mixture log-density: logp, d logp / dz and weighted parameter gradients
+__global__ void __launch_bounds__(256)
+gmm_log_pdf_kernel(const float* __restrict__ z, long long n, IrsGmm g, float* __restrict__ logp, float* __restrict__ dz,
+                   const float* __restrict__ weights, double* __restrict__ g_params, double* __restrict__ partials,
+                   unsigned int* __restrict__ counter) {
+    __shared__ double sh[2 * IRS_MAX_K * 32];
+    __shared__ double total[2 * IRS_MAX_K];
+    float acc[2 * IRS_MAX_K];
+#pragma unroll
+    for (int k = 0; k < 2 * IRS_MAX_K; ++k) acc[k] = 0.f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        float rho[IRS_MAX_K], wp;
+        const float zi = z[i];
+        const float lp = irs_gmm_eval(g, zi, rho, wp);
+        if (logp != nullptr) logp[i] = lp;
+        if (dz != nullptr) dz[i] = -zi * wp;
+        if (g_params != nullptr) {
+            const float w = weights ? weights[i] : 1.f;
+#pragma unroll
+            for (int k = 0; k < IRS_MAX_K; ++k) if (k < g.K) {
+                acc[k] += w * rho[k] * (zi * zi * g.prec[k] - 1.f);  // d logp / d log_std_k
+                acc[IRS_MAX_K + k] += w * rho[k];                     // -> d logp / d logits_j = rho_j - pi_j (host adds pi)
+            }
+        }
+    }
+    if (g_params == nullptr) return;
+    double blk[2 * IRS_MAX_K];
+    irs_block_sum<2 * IRS_MAX_K>(acc, blk, sh);
+    if (irs_grid_sum<2 * IRS_MAX_K>(blk, partials, counter, total)) {
+        if (threadIdx.x < 2 * IRS_MAX_K) g_params[threadIdx.x] = total[threadIdx.x];
+    }
+}
+
+// sum, sum of squares and count over the mask (mixture initialisation: reference trainer/trainer.py:537-541)
+__global__ void __launch_bounds__(256)
+masked_moments_kernel(const float* __restrict__ z, const unsigned char* __restrict__ mask, long long n,
+                      double* __restrict__ out, double* __restrict__ partials, unsigned int* __restrict__ counter) {
+    __shared__ double sh[3 * 32];
+    __shared__ double total[3];
+    // shifted by the first masked value would be better conditioned; residuals are O(1) so plain sums in double suffice
+    double s = 0.0, s2 = 0.0, cnt = 0.0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        if (mask[i]) { const double v = (double)z[i]; s += v; s2 += v * v; cnt += 1.0; }
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    s = irs_warp_sum(s); s2 = irs_warp_sum(s2); cnt = irs_warp_sum(cnt);
+    if (lane == 0) { sh[warp] = s; sh[32 + warp] = s2; sh[64 + warp] = cnt; }
+    __syncthreads();
+    double blk[3] = {0.0, 0.0, 0.0};
+    if (threadIdx.x == 0) {
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { blk[0] += sh[w]; blk[1] += sh[32 + w]; blk[2] += sh[64 + w]; }
+    }
+    __syncthreads();
+    if (irs_grid_sum<3>(blk, partials, counter, total)) {
+        if (threadIdx.x == 0) {
+            const double m = total[0] / total[2];
+            out[0] = m;
+            out[1] = sqrt(fmax(0.0, (total[1] - total[2] * m * m) / (total[2] - 1.0)));
+            out[2] = total[2];
+        }
+    }
+}
+
+}  // namespace
+
+int irs_data_blocks(IrsDims d) {
+    long long b = (d.V() + 255) / 256;
+    return (int)(b < 1184 ? b : 1184);  // 8 CTAs per SM x 148 SMs
+}
+
+int irs_launch_lcc_fwd(const float* im, const float* zF, int s, float* a, float* rs, float* z, int C, IrsDims d,
+                       cudaStream_t st) {
+    IRS_TRY(launch_box<BOX_FWD_MEAN>(im, nullptr, nullptr, 1.f, a, nullptr, s, C, d, st));
+    return launch_box<BOX_FWD_VAR>(a, zF, nullptr, 1.f, rs, z, s, C, d, st);
+}
+
+int irs_launch_lcc_bwd(const float* g_z, float g_sign, const float* a, const float* rs, int s, float* work, float* g_im,
+                       int C, IrsDims d, cudaStream_t st) {
+    IRS_TRY(launch_box<BOX_BWD_VAR>(g_z, a, rs, g_sign, work, nullptr, s, C, d, st));
+    return launch_box<BOX_BWD_MEAN>(work, nullptr, nullptr, 1.f, g_im, nullptr, s, C, d, st);
+}
+
+int irs_launch_gmm_stats_step(const float* z, const unsigned char* mask, double* hyper, const IrsHyperCfg& cfg,
+                              double* partials, unsigned int* counter, double* stats_row, float* table_out,
+                              const double* alpha_fixed, IrsDims d, cudaStream_t st) {
+    IrsGmm dummy;
+    dummy.K = cfg.K;
+    gmm_stats_kernel<0><<<irs_data_blocks(d), 256, 0, st>>>(z, mask, hyper, dummy, cfg, partials, counter, stats_row,
+                                                           table_out, nullptr, alpha_fixed, d);
+    return (int)cudaGetLastError();
+}
+
+int irs_launch_vd_alpha(const float* z, const unsigned char* mask, double* hyper, const IrsHyperCfg& cfg,
+                        double* partials, unsigned int* counter, double* stats_row, IrsDims d, cudaStream_t st) {
+    IrsGmm dummy;
+    dummy.K = cfg.K;
+    gmm_stats_kernel<2><<<irs_data_blocks(d), 256, 0, st>>>(z, mask, hyper, dummy, cfg, partials, counter, stats_row,
+                                                           nullptr, nullptr, nullptr, d);
+    return (int)cudaGetLastError();
+}
+
+// log_std <- linspace(log(sigma/100), log(5 sigma), K), sigma = moments[1]      (reference model/loss.py:61-65)
+__global__ void gmm_init_params_kernel(double* hyper, const double* moments, int K) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const double sigma = moments[1];
+    const double lo = log(sigma / 100.0), hi = log(sigma * 5.0);
+    for (int k = 0; k < K; ++k) {
+        // torch.linspace in fp32
+        const double t = K > 1 ? lo + (hi - lo) * (double)k / (double)(K - 1) : lo;
+        hyper[IRS_HYPER_LOG_STD + k] = irs_round_f32(t);
+    }
+}
+
+int irs_launch_gmm_init_params(double* hyper, const double* moments, int K, cudaStream_t st) {
+    gmm_init_params_kernel<<<1, 32, 0, st>>>(hyper, moments, K);
+    return (int)cudaGetLastError();
+}
+
+int irs_launch_gmm_grad(const float* z, const unsigned char* mask, const float* tables, int K, double* stats, float* g,
+                        double* partials, unsigned int* counters, int C, IrsDims d, cudaStream_t st) {
+    dim3 grid(irs_data_blocks(d), C);
+    gmm_grad_kernel<<<grid, 256, 0, st>>>(z, mask, tables, K, stats, g, partials, counters, d);
+    return (int)cudaGetLastError();
+}
+
+static int table_from_host(const float* gmm_host, int K, IrsGmm& g) {
+    if (!gmm_host || K < 1 || K > IRS_MAX_K) return IRS_ERR_BAD_ARG;
+    double ls[IRS_MAX_K], lg[IRS_MAX_K];
+    for (int k = 0; k < K; ++k) { ls[k] = gmm_host[k]; lg[k] = gmm_host[K + k]; }
+    irs_gmm_table(ls, lg, K, g);
+    return IRS_OK;
+}
+
+extern "C" int irs_lcc_normalise(const float* im, int s, float* a, float* rs, float* zn, int C, int D, int H, int W,
+                                 void* stream) {
+    IRS_CHECK_DIMS(C, D, H, W);
+    if (!im || !a || s < 1 || s > 3) return IRS_ERR_BAD_ARG;
+    return irs_launch_lcc_fwd(im, nullptr, s, a, rs, zn, C, IrsDims{D, H, W}, (cudaStream_t)stream);
+}
+
+extern "C" int irs_lcc_normalise_bwd(const float* g_zn, const float* a, const float* rs, int s, float* work,
+                                     float* g_im, int C, int D, int H, int W, void* stream) {
+    IRS_CHECK_DIMS(C, D, H, W);
+    if (!g_zn || !a || !rs || !work || !g_im || s < 1 || s > 3) return IRS_ERR_BAD_ARG;
+    return irs_launch_lcc_bwd(g_zn, 1.f, a, rs, s, work, g_im, C, IrsDims{D, H, W}, (cudaStream_t)stream);
+}
+
+extern "C" int irs_gmm_log_pdf(const float* z, long long n, const float* gmm_host, int K, float* logp, float* dz,
+                               const float* weights, double* g_params, double* partials, unsigned int* counter,
+                               void* stream) {
+    if (!z || n < 1) return IRS_ERR_BAD_ARG;
+    if (g_params && (!partials || !counter)) return IRS_ERR_BAD_ARG;
+    IrsGmm g;
+    IRS_TRY(table_from_host(gmm_host, K, g));
+    long long b = (n + 255) / 256;
+    const int blocks = (int)(b < 1184 ? b : 1184);
+    gmm_log_pdf_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(z, n, g, logp, dz, weights, g_params, partials, counter);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int irs_vd_factor(const float* z, const unsigned char* mask, const float* gmm_host, int K, double* alpha,
+                             double* partials, unsigned int* counter, int D, int H, int W, void* stream) {
+    IRS_CHECK_DIMS(1, D, H, W);
+    if (!z || !mask || !alpha || !partials || !counter) return IRS_ERR_BAD_ARG;
+    IrsGmm g;
+    IRS_TRY(table_from_host(gmm_host, K, g));
+    IrsHyperCfg cfg = {};
+    cfg.K = K;
+    cfg.virtual_decimation = 1;
+    IrsDims d{D, H, W};
+    // n_mask is not known on the host: the kernel recovers it as sum_k sum rho_k (responsibilities sum to 1 per voxel)
+    cfg.n_mask = -1.0;
+    gmm_stats_kernel<1><<<irs_data_blocks(d), 256, 0, (cudaStream_t)stream>>>(z, mask, nullptr, g, cfg, partials, counter,
+                                                                             nullptr, nullptr, alpha, nullptr, d);
+    return (int)cudaGetLastError();
+}
+
+int irs_launch_masked_moments(const float* z, const unsigned char* mask, long long n, double* out, double* partials,
+                              unsigned int* counter, cudaStream_t st) {
+    long long b = (n + 255) / 256;
+    const int blocks = (int)(b < 1184 ? b : 1184);
+    masked_moments_kernel<<<blocks, 256, 0, st>>>(z, mask, n, out, partials, counter);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int irs_masked_mean_std(const float* z, const unsigned char* mask, long long n, double* out,
+                                   double* partials, unsigned int* counter, void* stream) {
+    if (!z || !mask || !out || !partials || !counter || n < 2) return IRS_ERR_BAD_ARG;
+    return irs_launch_masked_moments(z, mask, n, out, partials, counter, (cudaStream_t)stream);
+}

@@ -1,0 +1,309 @@
+// irs_sampler.cu -- the fused SGLD transition (reference trainer/trainer.py:291-356), posterior moments
+// (utils/util.py:114-120) and the small ABI helpers.
+//
+// One call enqueues the whole iteration for all chains of this GPU on one stream; every scalar (virtual decimation
+// factors, mixture / regulariser hyper-parameters and their Adam state, the Philox offset) stays in device memory, so
+// the sequence has no host synchronisation and can be captured in a CUDA graph and replayed.
+#include "irs_kernels.cuh"
+
+namespace {
+
+__global__ void __launch_bounds__(256)
+ssd_residual_kernel(const float* __restrict__ fixed, const float* __restrict__ warped, float* __restrict__ z,
+                    long long V) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= V) return;
+    const size_t o = (size_t)blockIdx.y * V + i;
+    z[o] = fixed[i] - warped[o];
+}
+
+// regulariser loss / coefficient / Adam step for all chains, then advance the Philox offset
+__global__ void reg_hyper_kernel(double* hyper, IrsHyperCfg cfg, int C, double* stats) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    irs_reg_hyper_step(hyper, cfg, C, stats);
+    hyper[IRS_HYPER_ITER] += 1.0;
+}
+
+// running mean / M2 over samples (Welford); `count` = number of samples already folded in
+__global__ void __launch_bounds__(256)
+welford_kernel(const float* __restrict__ sample, int n_new, long long n, double count, float* __restrict__ mean,
+               float* __restrict__ m2) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float m = mean[i], s = m2[i];
+    float cnt = (float)count;
+    for (int j = 0; j < n_new; ++j) {
+        const float x = sample[(size_t)j * n + i];
+        cnt += 1.f;
+        const float dlt = x - m;
+        m += dlt / cnt;
+        s += dlt * (x - m);
+    }
+    mean[i] = m;
+    m2[i] = s;
+}
+
+__global__ void __launch_bounds__(256)
+welford_std_kernel(const float* __restrict__ m2, double count, float* __restrict__ out, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    out[i] = sqrtf(m2[i] / (float)(count - 1.0));
+}
+
+IrsHyperCfg hyper_cfg(const irs_sgld_config* c) {
+    IrsHyperCfg h;
+    h.K = c->K; h.virtual_decimation = c->virtual_decimation; h.reg_type = c->reg_type; h.reg_learnable = c->reg_learnable;
+    h.lr_log_std = c->lr_log_std; h.lr_logits = c->lr_logits; h.lr_reg0 = c->lr_reg0; h.lr_reg1 = c->lr_reg1;
+    h.lr_decay = c->lr_decay; h.beta1 = c->beta1; h.beta2 = c->beta2; h.eps = c->adam_eps;
+    h.gmm_prior_loc = c->gmm_scale_prior_loc; h.gmm_prior_scale = c->gmm_scale_prior_scale;
+    h.dirichlet_alpha = c->dirichlet_alpha;
+    h.reg_prior_loc = c->reg_scale_prior_loc; h.reg_prior_scale = c->reg_scale_prior_scale;
+    h.w_reg = c->w_reg; h.dof = c->dof;
+    h.w_reg_prior_shape = c->w_reg_prior_shape; h.w_reg_prior_rate = c->w_reg_prior_rate;
+    h.n_mask = c->n_mask;
+    return h;
+}
+
+int check_config(const irs_sgld_config* c) {
+    if (!c) return IRS_ERR_BAD_ARG;
+    IRS_CHECK_DIMS(c->C, c->D, c->H, c->W);
+    if (c->K < 1 || c->K > IRS_MAX_K) return IRS_ERR_BAD_ARG;
+    if (c->data_term != IRS_DATA_LCC && c->data_term != IRS_DATA_SSD) return IRS_ERR_BAD_ARG;
+    if (c->data_term == IRS_DATA_LCC && (c->lcc_s < 1 || c->lcc_s > 3)) return IRS_ERR_BAD_ARG;
+    if (c->reg_type != IRS_REG_L2 && c->reg_type != IRS_REG_LOGNORMAL) return IRS_ERR_BAD_ARG;
+    if (c->n_taps < 0 || c->n_taps > IRS_MAX_TAPS || (c->n_taps > 0 && c->n_taps % 2 == 0)) return IRS_ERR_BAD_ARG;
+    if (c->svf_steps < 1 || c->svf_steps > IRS_MAX_SVF_STEPS) return IRS_ERR_BAD_ARG;
+    if (!(c->n_mask >= 2.0) || !(c->tau >= 0.0) || c->gather_radius_max < 0) return IRS_ERR_BAD_ARG;
+    return IRS_OK;
+}
+
+}  // namespace
+
+extern "C" size_t irs_sgld_partials_doubles(const irs_sgld_config* cfg) {
+    if (!cfg) return 0;
+    IrsDims d{cfg->D, cfg->H, cfg->W};
+    const size_t per_chain = (size_t)irs_data_blocks(d) * IRS_SUM_COUNT;
+    return (size_t)cfg->C * per_chain;
+}
+
+extern "C" int irs_sgld_launches_per_step(const irs_sgld_config* c) {
+    if (check_config(c) != IRS_OK) return -1;
+    int n = 1;                                   // langevin
+    n += c->n_taps > 0 ? 3 : 0;                  // Sobolev z, y, x
+    n += 1;                                      // regulariser energy
+    n += c->svf_steps;                           // scaling and squaring
+    n += 1;                                      // warp
+    n += c->data_term == IRS_DATA_LCC ? 2 : 1;   // LCC boxes / SSD residual
+    n += c->C;                                   // per-chain mixture statistics + Adam
+    n += 1;                                      // dL/dz
+    n += c->data_term == IRS_DATA_LCC ? 2 : 0;   // LCC adjoint boxes
+    n += 1;                                      // warp grid gradient
+    n += 1;                                      // regulariser hyper step
+    n += 2 * c->svf_steps;                       // SVF adjoint (gather + large-displacement scatter)
+    n += 1;                                      // regulariser gradient + SGD update
+    return n;
+}
+
+namespace {
+struct StageTimer {
+    cudaEvent_t ev[IRS_N_STAGES + 1];
+    int n;
+};
+inline void mark(StageTimer* t, cudaStream_t st) {
+    if (t != nullptr && t->n <= IRS_N_STAGES) cudaEventRecord(t->ev[t->n++], st);
+}
+}  // namespace
+
+static int sgld_step_impl(const irs_sgld_config* cfg, const irs_sgld_buffers* b, void* stream, StageTimer* tm) {
+    IRS_TRY(check_config(cfg));
+    if (!b || !b->v || !b->fixed || !b->moving || !b->mask || !b->css || !b->hist || !b->im_warped || !b->z ||
+        !b->scratch1 || !b->field_a || !b->field_b || !b->grad_v || !b->maxabs || !b->hyper || !b->stats ||
+        !b->gmm_table || !b->partials || !b->counters)
+        return IRS_ERR_BAD_ARG;
+    if (cfg->data_term == IRS_DATA_LCC && (!b->lcc_a || !b->lcc_rs || !b->scratch2)) return IRS_ERR_BAD_ARG;
+
+    cudaStream_t st = (cudaStream_t)stream;
+    const int C = cfg->C;
+    const IrsDims d{cfg->D, cfg->H, cfg->W};
+    const long long V = d.V();
+    const size_t F = (size_t)C * 3 * V;
+    const IrsHyperCfg hc = hyper_cfg(cfg);
+    const double* iter_ptr = b->hyper + IRS_HYPER_ITER;
+
+    mark(tm, st);
+    // (1) Langevin proposal + Sobolev smoothing                                   trainer.py:292-293
+    IrsRng rng_l{b->eps, cfg->seed, iter_ptr, 0ull, cfg->chain_offset};
+    const float coef = (float)sqrt(2.0 * cfg->tau);
+    if (cfg->n_taps > 0) {
+        IrsTaps taps;
+        taps.n = cfg->n_taps;
+        for (int t = 0; t < cfg->n_taps; ++t) taps.w[t] = cfg->taps[t];
+        IRS_TRY(irs_launch_langevin(b->v, b->sigma, b->sigma_chain_stride, coef, rng_l, b->field_a, C, d, st));
+        IRS_TRY(irs_launch_smooth3(b->field_a, b->field_a, b->css, taps, C, d, st));
+    } else {
+        IRS_TRY(irs_launch_langevin(b->v, b->sigma, b->sigma_chain_stride, coef, rng_l, b->css, C, d, st));
+    }
+
+    mark(tm, st);
+    // (2) regulariser energy y_c                                                  trainer.py:311
+    IRS_TRY(irs_launch_reg_energy(b->css, b->stats + IRS_STAT_ENERGY, IRS_STAT_SIZE, b->partials, b->counters, C, d, st));
+
+    mark(tm, st);
+    // (3) scaling and squaring                                                    trainer.py:294
+    IRS_TRY(irs_launch_svf_fwd(b->css, b->hist, b->maxabs, cfg->svf_steps, C, d, st));
+    const float* disp = b->hist + (size_t)(cfg->svf_steps - 1) * F;
+
+    mark(tm, st);
+    // (4) warp the moving image at T (+ jitter)                                   trainer.py:296-300
+    IrsRng rng_j{b->jitter_unit, cfg->seed, iter_ptr, 0ull, cfg->chain_offset};
+    const float alpha = (float)cfg->jitter_alpha;
+    IRS_TRY(irs_launch_warp_vox_fwd(b->moving, disp, rng_j, alpha, cfg->use_jitter, b->im_warped, C, d, st));
+
+    mark(tm, st);
+    // (5) residual map                                                            trainer.py:307
+    if (cfg->data_term == IRS_DATA_LCC) {
+        IRS_TRY(irs_launch_lcc_fwd(b->im_warped, b->fixed, cfg->lcc_s, b->lcc_a, b->lcc_rs, b->z, C, d, st));
+    } else {
+        dim3 grid((unsigned)((V + 255) / 256), C);
+        ssd_residual_kernel<<<grid, 256, 0, st>>>(b->fixed, b->im_warped, b->z, V);
+        IRS_LAUNCH_CHECK();
+    }
+
+    mark(tm, st);
+    // (6) per chain, in order: VD factor, Adam step on the shared mixture          trainer.py:316-318
+    const size_t per_chain = (size_t)irs_data_blocks(d) * IRS_SUM_COUNT;
+    for (int c = 0; c < C; ++c) {
+        IRS_TRY(irs_launch_gmm_stats_step(b->z + (size_t)c * V, b->mask, b->hyper, hc, b->partials + c * per_chain,
+                                          b->counters + c, b->stats + (size_t)c * IRS_STAT_SIZE,
+                                          b->gmm_table + (size_t)c * 16, nullptr, d, st));
+    }
+
+    mark(tm, st);
+    // (7) dL/dz with each chain's updated mixture + the logged data term          trainer.py:320
+    IRS_TRY(irs_launch_gmm_grad(b->z, b->mask, b->gmm_table, cfg->K, b->stats, b->scratch1, b->partials, b->counters, C,
+                                d, st));
+
+    mark(tm, st);
+    // (8) back through the residual map and the warp -> dL/du_n
+    if (cfg->data_term == IRS_DATA_LCC) {
+        IRS_TRY(irs_launch_lcc_bwd(b->scratch1, -1.f, b->lcc_a, b->lcc_rs, cfg->lcc_s, b->scratch2, b->scratch1, C, d, st));
+        IRS_TRY(irs_launch_warp_vox_bwd(b->moving, disp, rng_j, alpha, cfg->use_jitter, b->scratch1, 1.f, b->field_a, C,
+                                        d, st));
+    } else {
+        IRS_TRY(irs_launch_warp_vox_bwd(b->moving, disp, rng_j, alpha, cfg->use_jitter, b->scratch1, -1.f, b->field_a, C,
+                                        d, st));
+    }
+
+    mark(tm, st);
+    // (9) regulariser loss, coefficient and hyper-parameter Adam step              trainer.py:311,334-339,353-354
+    reg_hyper_kernel<<<1, 32, 0, st>>>(b->hyper, hc, C, b->stats);
+    IRS_LAUNCH_CHECK();
+
+    mark(tm, st);
+    // (10) SVF adjoint -> dL/dcss (data part)                                      trainer.py:349
+    IRS_TRY(irs_launch_svf_bwd(b->css, b->hist, b->maxabs, b->field_a, b->field_b, b->grad_v, cfg->svf_steps,
+                               cfg->gather_radius_max, C, d, st));
+
+    mark(tm, st);
+    // (11) + regulariser gradient, sigma^2 preconditioning, SGD step               utils/functions.py:82-84, trainer.py:351
+    IRS_TRY(irs_launch_sgd_update(b->v, b->sigma, b->sigma_chain_stride, b->css, b->grad_v, b->stats + IRS_STAT_REG_COEF,
+                                  IRS_STAT_SIZE, (float)cfg->tau, b->grad_v, C, d, st));
+    mark(tm, st);
+    return IRS_OK;
+}
+
+extern "C" int irs_sgld_step(const irs_sgld_config* cfg, const irs_sgld_buffers* b, void* stream) {
+    return sgld_step_impl(cfg, b, stream, nullptr);
+}
+
+// Profiling aid (not for graph capture; synchronises): runs one transition eagerly with a CUDA event between the
+// stages and writes the IRS_N_STAGES stage durations in milliseconds to ms_host.
+extern "C" int irs_sgld_step_profile(const irs_sgld_config* cfg, const irs_sgld_buffers* b, void* stream,
+                                     float* ms_host) {
+    if (!ms_host) return IRS_ERR_BAD_ARG;
+    StageTimer tm;
+    tm.n = 0;
+    for (int i = 0; i <= IRS_N_STAGES; ++i) {
+        cudaError_t e = cudaEventCreate(&tm.ev[i]);
+        if (e != cudaSuccess) return (int)e;
+    }
+    int r = sgld_step_impl(cfg, b, stream, &tm);
+    cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
+    if (r == IRS_OK && e != cudaSuccess) r = (int)e;
+    if (r == IRS_OK) {
+        for (int i = 0; i < IRS_N_STAGES; ++i) {
+            ms_host[i] = 0.f;
+            if (i + 1 < tm.n) cudaEventElapsedTime(&ms_host[i], tm.ev[i], tm.ev[i + 1]);
+        }
+    }
+    for (int i = 0; i <= IRS_N_STAGES; ++i) cudaEventDestroy(tm.ev[i]);
+    return r;
+}
+
+// Mixture initialisation (reference trainer/trainer.py:529-547): smooth the given velocity sample (no Langevin noise),
+// integrate, warp (no jitter), residual map, sigma_hat = std over the mask, log_std = linspace(log sigma_hat/100,
+// log 5 sigma_hat, K), VD factor once, then n_warmup Adam steps on the mixture with that factor.
+// Uses the chain-0 slices of the step buffers; v_sample is (1,3,D,H,W).
+extern "C" int irs_sgld_gmm_init(const irs_sgld_config* cfg, const irs_sgld_buffers* b, const float* v_sample,
+                                 int n_warmup, void* stream) {
+    IRS_TRY(check_config(cfg));
+    if (!b || !v_sample || n_warmup < 0) return IRS_ERR_BAD_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    const IrsDims d{cfg->D, cfg->H, cfg->W};
+    const long long V = d.V();
+    const IrsHyperCfg hc = hyper_cfg(cfg);
+    IrsRng none{nullptr, 0ull, nullptr, 0ull, 0};
+    if (cfg->n_taps > 0) {
+        IrsTaps taps;
+        taps.n = cfg->n_taps;
+        for (int t = 0; t < cfg->n_taps; ++t) taps.w[t] = cfg->taps[t];
+        IRS_TRY(irs_launch_langevin(v_sample, nullptr, 0, 0.f, none, b->field_a, 1, d, st));
+        IRS_TRY(irs_launch_smooth3(b->field_a, b->field_a, b->css, taps, 1, d, st));
+    } else {
+        IRS_TRY(irs_launch_langevin(v_sample, nullptr, 0, 0.f, none, b->css, 1, d, st));
+    }
+    // hist of a single chain is laid out with stride 3V per step when C = 1
+    IRS_TRY(irs_launch_svf_fwd(b->css, b->hist, b->maxabs, cfg->svf_steps, 1, d, st));
+    const float* disp = b->hist + (size_t)(cfg->svf_steps - 1) * 3 * V;
+    IRS_TRY(irs_launch_warp_vox_fwd(b->moving, disp, none, 0.f, 0, b->im_warped, 1, d, st));
+    if (cfg->data_term == IRS_DATA_LCC) {
+        IRS_TRY(irs_launch_lcc_fwd(b->im_warped, b->fixed, cfg->lcc_s, b->lcc_a, b->lcc_rs, b->z, 1, d, st));
+    } else {
+        dim3 grid((unsigned)((V + 255) / 256), 1);
+        ssd_residual_kernel<<<grid, 256, 0, st>>>(b->fixed, b->im_warped, b->z, V);
+        IRS_LAUNCH_CHECK();
+    }
+    double* moments = b->stats + IRS_STAT_SIZE - 3;  // last three slots of chain 0's row, overwritten by the next step
+    IRS_TRY(irs_launch_masked_moments(b->z, b->mask, V, moments, b->partials, b->counters, st));
+    IRS_TRY(irs_launch_gmm_init_params(b->hyper, moments, cfg->K, st));
+    IRS_TRY(irs_launch_vd_alpha(b->z, b->mask, b->hyper, hc, b->partials, b->counters, b->stats, d, st));
+    for (int it = 0; it < n_warmup; ++it)
+        IRS_TRY(irs_launch_gmm_stats_step(b->z, b->mask, b->hyper, hc, b->partials, b->counters, b->stats, b->gmm_table,
+                                          b->stats + IRS_STAT_ALPHA, d, st));
+    return IRS_OK;
+}
+
+extern "C" int irs_welford_update(const float* sample, int n_new, long long n, double count_before, float* mean,
+                                  float* m2, void* stream) {
+    if (!sample || !mean || !m2 || n_new < 1 || n < 1 || count_before < 0) return IRS_ERR_BAD_ARG;
+    welford_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(sample, n_new, n, count_before, mean, m2);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int irs_welford_std(const float* m2, double count, float* std_out, long long n, void* stream) {
+    if (!m2 || !std_out || n < 1 || count < 2) return IRS_ERR_BAD_ARG;
+    welford_std_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(m2, count, std_out, n);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int irs_abi_version(void) { return IRS_ABI_VERSION; }
+
+extern "C" const char* irs_error_string(int code) {
+    switch (code) {
+        case IRS_OK: return "ok";
+        case IRS_ERR_BAD_ARG: return "irsgmcmc: bad argument (null pointer, size or option out of range)";
+        case IRS_ERR_UNSUPPORTED: return "irsgmcmc: unsupported shape or option";
+        case IRS_ERR_WORKSPACE: return "irsgmcmc: workspace too small";
+        default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "irsgmcmc: unknown error";
+    }
+}

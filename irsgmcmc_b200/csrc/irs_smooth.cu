@@ -1,0 +1,303 @@
+// irs_smooth.cu -- Langevin proposal, Sobolev smoothing, diffusion regulariser, preconditioned SGD update
+// (reference utils/functions.py:76-109, utils/util.py:48-58,394-404, utils/diff_op.py:78-96, model/loss.py:152-161,
+//  trainer/trainer.py:351)
+#include "irs_kernels.cuh"
+
+namespace {
+
+// out = v + coef * sigma * eps   (reference utils/util.py:48-58)
+__global__ void __launch_bounds__(256)
+langevin_kernel(const float* __restrict__ v, const float* __restrict__ sigma, long long sigma_cs, float coef,
+                IrsRng rng, float* __restrict__ out, IrsDims d) {
+    const long long V = d.V();
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= V) return;
+    const int c = blockIdx.y;
+    const float* vc = v + (size_t)c * 3 * V;
+    float* oc = out + (size_t)c * 3 * V;
+    if (coef == 0.f) {
+        oc[i] = vc[i]; oc[V + i] = vc[V + i]; oc[2 * V + i] = vc[2 * V + i];
+        return;
+    }
+    float e[3];
+    if (rng.explicit_values != nullptr) {
+        const float* ec = rng.explicit_values + (size_t)c * 3 * V;
+        e[0] = ec[i]; e[1] = ec[V + i]; e[2] = ec[2 * V + i];
+    } else {
+        const unsigned long long it = rng.iter_ptr ? (unsigned long long)(*rng.iter_ptr) : rng.iter;
+        irs_normal3(rng.seed, (uint32_t)i, (uint32_t)(rng.chain0 + c), it, e);
+    }
+    float s0 = 1.f, s1 = 1.f, s2 = 1.f;
+    if (sigma != nullptr) {
+        const float* sc = sigma + (size_t)c * sigma_cs;
+        s0 = sc[i]; s1 = sc[V + i]; s2 = sc[2 * V + i];
+    }
+    oc[i] = vc[i] + coef * s0 * e[0];
+    oc[V + i] = vc[V + i] + coef * s1 * e[1];
+    oc[2 * V + i] = vc[2 * V + i] + coef * s2 * e[2];
+}
+
+// one axis of the separable smoothing: out(j) = sum_t w_t in(clamp(j + t - s))  (replicate padding).  n_fields = C*3
+template <int AXIS>
+__global__ void __launch_bounds__(256)
+smooth_axis_kernel(const float* __restrict__ in, float* __restrict__ out, IrsTaps taps, IrsDims d) {
+    const long long V = d.V();
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= V) return;
+    const float* f = in + (size_t)blockIdx.y * V;
+    const int x = (int)(i % d.W), y = (int)((i / d.W) % d.H), z = (int)(i / ((long long)d.W * d.H));
+    const int s = (taps.n - 1) / 2;
+    const int n = AXIS == 0 ? d.W : (AXIS == 1 ? d.H : d.D);
+    const int j = AXIS == 0 ? x : (AXIS == 1 ? y : z);
+    const long long stride = AXIS == 0 ? 1 : (AXIS == 1 ? d.W : (long long)d.W * d.H);
+    const long long base = i - (long long)j * stride;
+    float acc = 0.f;
+    for (int t = 0; t < taps.n; ++t) {
+        const int jj = irs_clampi(j + t - s, 0, n - 1);
+        acc += taps.w[t] * __ldg(f + base + (long long)jj * stride);
+    }
+    out[(size_t)blockIdx.y * V + i] = acc;
+}
+
+// energy of one chain: sum over 3 components x 3 axes of squared forward differences (last one counted twice)
+__global__ void __launch_bounds__(256)
+reg_energy_kernel(const float* __restrict__ v, double* __restrict__ energy, long long energy_stride,
+                  double* __restrict__ partials, unsigned int* __restrict__ counters, IrsDims d) {
+    __shared__ double sh[32];
+    __shared__ double total[1];
+    const long long V = d.V();
+    const int c = blockIdx.y;
+    const float* vc = v + (size_t)c * 3 * V;
+    float acc = 0.f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < V; i += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(i % d.W), y = (int)((i / d.W) % d.H), z = (int)(i / ((long long)d.W * d.H));
+        const long long sy = d.W, sz = (long long)d.W * d.H;
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+            const float* f = vc + (size_t)ch * V;
+            const float vj = f[i];
+            const float vx = x < d.W - 1 ? __ldg(f + i + 1) : 0.f;
+            const float vy = y < d.H - 1 ? __ldg(f + i + sy) : 0.f;
+            const float vz = z < d.D - 1 ? __ldg(f + i + sz) : 0.f;
+            acc += irs_diff_energy(vj, vx, x, d.W) + irs_diff_energy(vj, vy, y, d.H) + irs_diff_energy(vj, vz, z, d.D);
+        }
+    }
+    double blk[1];
+    irs_block_sum<1>(&acc, blk, sh);
+    if (irs_grid_sum<1>(blk, partials + (size_t)c * gridDim.x, counters + c, total)) {
+        if (threadIdx.x == 0) energy[(size_t)c * energy_stride] = total[0];
+    }
+}
+
+__global__ void __launch_bounds__(256)
+reg_energy_grad_kernel(const float* __restrict__ v, const double* __restrict__ coef, float* __restrict__ g_v,
+                       IrsDims d) {
+    const long long V = d.V();
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= V) return;
+    const int c = blockIdx.y;
+    const float k = (float)coef[c];
+    const int x = (int)(i % d.W), y = (int)((i / d.W) % d.H), z = (int)(i / ((long long)d.W * d.H));
+    const long long sy = d.W, sz = (long long)d.W * d.H;
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+        const float* f = v + ((size_t)c * 3 + ch) * V;
+        const float vj = f[i];
+        float ge = irs_diff_energy_grad(x > 0 ? __ldg(f + i - 1) : 0.f, vj, x < d.W - 1 ? __ldg(f + i + 1) : 0.f, x, d.W)
+                 + irs_diff_energy_grad(y > 0 ? __ldg(f + i - sy) : 0.f, vj, y < d.H - 1 ? __ldg(f + i + sy) : 0.f, y, d.H)
+                 + irs_diff_energy_grad(z > 0 ? __ldg(f + i - sz) : 0.f, vj, z < d.D - 1 ? __ldg(f + i + sz) : 0.f, z, d.D);
+        g_v[((size_t)c * 3 + ch) * V + i] += k * ge;
+    }
+}
+
+// grad_v = sigma^2 (g_css + coef_c dE/dcss) ;  v <- v - tau grad_v    (reference utils/functions.py:82-84 + plain SGD)
+__global__ void __launch_bounds__(256)
+sgd_update_kernel(float* __restrict__ v, const float* __restrict__ sigma, long long sigma_cs,
+                  const float* __restrict__ css, const float* __restrict__ g_css, const double* __restrict__ coef,
+                  long long coef_stride, float tau, float* __restrict__ grad_v, IrsDims d) {
+    const long long V = d.V();
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= V) return;
+    const int c = blockIdx.y;
+    const float k = (float)coef[(size_t)c * coef_stride];
+    const int x = (int)(i % d.W), y = (int)((i / d.W) % d.H), z = (int)(i / ((long long)d.W * d.H));
+    const long long sy = d.W, sz = (long long)d.W * d.H;
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+        const size_t o = ((size_t)c * 3 + ch) * V + i;
+        const float* f = css + ((size_t)c * 3 + ch) * V;
+        const float vj = f[i];
+        float ge = irs_diff_energy_grad(x > 0 ? __ldg(f + i - 1) : 0.f, vj, x < d.W - 1 ? __ldg(f + i + 1) : 0.f, x, d.W)
+                 + irs_diff_energy_grad(y > 0 ? __ldg(f + i - sy) : 0.f, vj, y < d.H - 1 ? __ldg(f + i + sy) : 0.f, y, d.H)
+                 + irs_diff_energy_grad(z > 0 ? __ldg(f + i - sz) : 0.f, vj, z < d.D - 1 ? __ldg(f + i + sz) : 0.f, z, d.D);
+        const float sg = sigma ? sigma[(size_t)c * sigma_cs + (size_t)ch * V + i] : 1.f;
+        const float g = sg * sg * (g_css[o] + k * ge);
+        if (grad_v != nullptr) grad_v[o] = g;
+        v[o] -= tau * g;
+    }
+}
+
+// nabla (C,3,D,H,W,3): [c, j, voxel, i] = d v_i / d x_j   (reference utils/diff_op.py:78-96)
+__global__ void __launch_bounds__(256)
+diff_fwd_kernel(const float* __restrict__ v, float* __restrict__ nabla, int transformation, IrsDims d) {
+    const long long V = d.V();
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= V) return;
+    const int c = blockIdx.y;
+    const int x = (int)(i % d.W), y = (int)((i / d.W) % d.H), z = (int)(i / ((long long)d.W * d.H));
+    const long long sy = d.W, sz = (long long)d.W * d.H;
+    // replicated last difference: position n-1 repeats the difference of position n-2
+    const long long ix = x < d.W - 1 ? i : i - 1, iy = y < d.H - 1 ? i : i - sy, iz = z < d.D - 1 ? i : i - sz;
+    float sxp = 1.f, syp = 1.f, szp = 1.f;
+    if (transformation) {
+        sxp = (float)(d.W - 1) * 0.5f; syp = (float)(d.H - 1) * 0.5f; szp = (float)(d.D - 1) * 0.5f;
+    }
+    float* o = nabla + (size_t)c * 9 * V;
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+        const float* f = v + ((size_t)c * 3 + ch) * V;
+        o[(0 * V + i) * 3 + ch] = (__ldg(f + ix + 1) - __ldg(f + ix)) * sxp;
+        o[(1 * V + i) * 3 + ch] = (__ldg(f + iy + sy) - __ldg(f + iy)) * syp;
+        o[(2 * V + i) * 3 + ch] = (__ldg(f + iz + sz) - __ldg(f + iz)) * szp;
+    }
+}
+
+// adjoint of diff_fwd: g_v[ch](j) = sum over axes of  [G(j-1) - G(j)] with the replicated last entry folded back
+__global__ void __launch_bounds__(256)
+diff_bwd_kernel(const float* __restrict__ g_nabla, float* __restrict__ g_v, int transformation, IrsDims d) {
+    const long long V = d.V();
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= V) return;
+    const int c = blockIdx.y;
+    const int x = (int)(i % d.W), y = (int)((i / d.W) % d.H), z = (int)(i / ((long long)d.W * d.H));
+    const long long st[3] = {1, d.W, (long long)d.W * d.H};
+    const int pos[3] = {x, y, z}, len[3] = {d.W, d.H, d.D};
+    const float* G = g_nabla + (size_t)c * 9 * V;
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+        float acc = 0.f;
+#pragma unroll
+        for (int ax = 0; ax < 3; ++ax) {
+            const int j = pos[ax], n = len[ax];
+            const float sp = transformation ? (float)(n - 1) * 0.5f : 1.f;
+            const float* Ga = G + (size_t)ax * V * 3;
+            // effective gradient on difference d_m (m = 0..n-2): Ge(m) = G(m) + [m == n-2] G(n-1)
+            float a = 0.f;
+            if (j >= 1) {  // + Ge(j-1)
+                const int m = j - 1;
+                float ge = __ldg(Ga + (i - st[ax]) * 3 + ch);
+                if (m == n - 2) ge += __ldg(Ga + i * 3 + ch);  // here i is position n-1
+                a += ge;
+            }
+            if (j <= n - 2) {  // - Ge(j)
+                float ge = __ldg(Ga + i * 3 + ch);
+                if (j == n - 2) ge += __ldg(Ga + (i + st[ax]) * 3 + ch);
+                a -= ge;
+            }
+            acc += a * sp;
+        }
+        g_v[((size_t)c * 3 + ch) * V + i] = acc;
+    }
+}
+
+}  // namespace
+
+int irs_launch_langevin(const float* v, const float* sigma, long long sigma_cs, float coef, IrsRng rng, float* out,
+                        int C, IrsDims d, cudaStream_t st) {
+    dim3 grid((unsigned)((d.V() + 255) / 256), C);
+    langevin_kernel<<<grid, 256, 0, st>>>(v, sigma, sigma_cs, coef, rng, out, d);
+    return (int)cudaGetLastError();
+}
+
+// in -> (z pass) out -> (y pass) work -> (x pass) out : the reference's order (utils/util.py:402-404)
+int irs_launch_smooth3(const float* in, float* work, float* out, const IrsTaps& taps, int C, IrsDims d,
+                       cudaStream_t st) {
+    dim3 grid((unsigned)((d.V() + 255) / 256), C * 3);
+    smooth_axis_kernel<2><<<grid, 256, 0, st>>>(in, out, taps, d);
+    smooth_axis_kernel<1><<<grid, 256, 0, st>>>(out, work, taps, d);
+    smooth_axis_kernel<0><<<grid, 256, 0, st>>>(work, out, taps, d);
+    return (int)cudaGetLastError();
+}
+
+int irs_reg_energy_blocks(IrsDims d) {
+    long long b = (d.V() + 255) / 256;
+    return (int)(b < 592 ? b : 592);  // 4 CTAs per SM x 148 SMs
+}
+
+int irs_launch_reg_energy(const float* v, double* energy, long long energy_stride, double* partials,
+                          unsigned int* counters, int C, IrsDims d, cudaStream_t st) {
+    dim3 grid(irs_reg_energy_blocks(d), C);
+    reg_energy_kernel<<<grid, 256, 0, st>>>(v, energy, energy_stride, partials, counters, d);
+    return (int)cudaGetLastError();
+}
+
+int irs_launch_sgd_update(float* v, const float* sigma, long long sigma_cs, const float* css, const float* g_css,
+                          const double* coef, long long coef_stride, float tau, float* grad_v, int C, IrsDims d,
+                          cudaStream_t st) {
+    dim3 grid((unsigned)((d.V() + 255) / 256), C);
+    sgd_update_kernel<<<grid, 256, 0, st>>>(v, sigma, sigma_cs, css, g_css, coef, coef_stride, tau, grad_v, d);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int irs_langevin_sobolev(const float* v, const float* sigma, long long sigma_cs, float coef,
+                                    const float* eps, unsigned long long seed, unsigned long long iter, int chain0,
+                                    const float* taps_host, int n_taps, float* work, float* out, int C, int D, int H,
+                                    int W, void* stream) {
+    IRS_CHECK_DIMS(C, D, H, W);
+    if (!v || !out) return IRS_ERR_BAD_ARG;
+    if (n_taps < 0 || n_taps > IRS_MAX_TAPS || (n_taps > 0 && (n_taps % 2 == 0 || !taps_host || !work)))
+        return IRS_ERR_BAD_ARG;
+    IrsDims d{D, H, W};
+    cudaStream_t st = (cudaStream_t)stream;
+    IrsRng rng{eps, seed, nullptr, iter, chain0};
+    if (n_taps == 0) return irs_launch_langevin(v, sigma, sigma_cs, coef, rng, out, C, d, st);
+    IrsTaps taps;
+    taps.n = n_taps;
+    for (int t = 0; t < n_taps; ++t) taps.w[t] = taps_host[t];
+    IRS_TRY(irs_launch_langevin(v, sigma, sigma_cs, coef, rng, work, C, d, st));
+    // z pass reads `work`, so route: work -> out -> work -> out needs a third buffer; instead do work -> out (z),
+    // out -> work (y), work -> out (x)
+    return irs_launch_smooth3(work, work, out, taps, C, d, st);
+}
+
+extern "C" int irs_diff_fwd(const float* v, float* nabla, int transformation, int C, int D, int H, int W,
+                            void* stream) {
+    IRS_CHECK_DIMS(C, D, H, W);
+    if (!v || !nabla) return IRS_ERR_BAD_ARG;
+    IrsDims d{D, H, W};
+    dim3 grid((unsigned)((d.V() + 255) / 256), C);
+    diff_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(v, nabla, transformation, d);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int irs_diff_bwd(const float* g_nabla, float* g_v, int transformation, int C, int D, int H, int W,
+                            void* stream) {
+    IRS_CHECK_DIMS(C, D, H, W);
+    if (!g_nabla || !g_v) return IRS_ERR_BAD_ARG;
+    IrsDims d{D, H, W};
+    dim3 grid((unsigned)((d.V() + 255) / 256), C);
+    diff_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(g_nabla, g_v, transformation, d);
+    return (int)cudaGetLastError();
+}
+
+extern "C" size_t irs_reduce_scratch_doubles(int C, int D, int H, int W) {
+    IrsDims d{D, H, W};
+    return (size_t)C * 592 * 32;
+}
+
+extern "C" int irs_reg_energy(const float* v, double* energy, double* partials, unsigned int* counters, int C, int D,
+                              int H, int W, void* stream) {
+    IRS_CHECK_DIMS(C, D, H, W);
+    if (!v || !energy || !partials || !counters) return IRS_ERR_BAD_ARG;
+    return irs_launch_reg_energy(v, energy, 1, partials, counters, C, IrsDims{D, H, W}, (cudaStream_t)stream);
+}
+
+extern "C" int irs_reg_energy_grad(const float* v, const double* coef, float* g_v, int C, int D, int H, int W,
+                                   void* stream) {
+    IRS_CHECK_DIMS(C, D, H, W);
+    if (!v || !coef || !g_v) return IRS_ERR_BAD_ARG;
+    IrsDims d{D, H, W};
+    dim3 grid((unsigned)((d.V() + 255) / 256), C);
+    reg_energy_grad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(v, coef, g_v, d);
+    return (int)cudaGetLastError();
+}

@@ -1,0 +1,167 @@
+"""GPU parity of the fused SGLD transition (irs_sgld_step through SGLDSampler) against the oracle's restatement of
+Trainer._SGLD_transition (reference trainer/trainer.py:291-356) with injected noise, fp32 and fp64."""
+import math
+
+import pytest
+import torch
+
+from oracle import sgld_oracle as O
+from tests.util import rel, three_numbers
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+
+
+def run_pair(n, C, data, reg, learnable, iters, vd=True, jitter=True, noise=True, seed=123, s=2):
+    from irsgmcmc_b200.sampler import SGLDSampler, SGLDConfig
+    from irsgmcmc_b200.data_loader.synthetic import make_pair
+    torch.manual_seed(seed)
+    fixed, moving, vp = make_pair(n)
+    reg_name = 'RegLoss_LogNormal' if reg == 'lognormal' else 'RegLoss_L2'
+    cfg = SGLDConfig(data_loss=data, reg_loss=reg_name, w_reg=1.6 if reg == 'lognormal' else 1.4, s=s,
+                     reg_learnable=learnable, virtual_decimation=vd, uniform_noise=jitter, tau=0.4 if noise else 0.4)
+    sampler = SGLDSampler(fixed, moving, C, cfg, device=DEV)
+    v0 = 0.8 * torch.randn(C, 3, n, n, n)
+    sigma = torch.exp(0.5 * vp['log_var'])
+    sampler.set_state(v0, sigma)
+    sampler.init_gmm(sigma_hat=0.7)
+
+    K = 4 if data == 'lcc' else 1
+    def oracle_state(dtype):
+        ocfg = O.Config(data=data, K=K, s=s, reg=reg, w_reg=cfg.w_reg, reg_learnable=learnable, virtual_decimation=vd,
+                        jitter_alpha=0.1 if jitter else None, exact_grid=(dtype == torch.float64))
+        st = O.State(ocfg, v0.to(dtype), sigma.to(dtype).expand(C, -1, -1, -1, -1), (n, n, n), dtype)
+        st.init_gmm(0.7)
+        return st
+    st32, st64 = oracle_state(torch.float32), oracle_state(torch.float64)
+    f64 = {k: (v.double() if v.dtype == torch.float32 else v) for k, v in fixed.items()}
+    m64 = {k: (v.double() if v.dtype == torch.float32 else v) for k, v in moving.items()}
+
+    report = []
+    for it in range(iters):
+        eps = torch.randn(C, 3, n, n, n) if noise else torch.zeros(C, 3, n, n, n)
+        ju = torch.rand(C, 3, n, n, n)
+        sampler.set_noise(eps, ju)
+        # restart every implementation from the fp32 oracle's state so that per-iteration errors do not compound
+        sampler.v.copy_(st32.v)
+        st64.v = st32.v.double()
+        sampler.step(1, use_graph=False)
+        torch.cuda.synchronize()
+        lt32, out32, aux32, g32 = O.sgld_transition(st32, fixed, moving, eps, ju)
+        lt64, out64, aux64, g64 = O.sgld_transition(st64, f64, m64, eps.double(), ju.double())
+        terms = sampler.loss_terms()
+        r = {
+            'css': three_numbers(sampler.css, out32['curr_state'], out64['curr_state']),
+            'disp': three_numbers(sampler.displacement, out32['displacement'], out64['displacement']),
+            'T': three_numbers(sampler.transformation(), out32['transformation'], out64['transformation']),
+            'im_w': three_numbers(sampler.im_warped, out32['im_moving_warped'], out64['im_moving_warped']),
+            'z': three_numbers(sampler.z, aux32['residuals'], aux64['residuals']),
+            'alpha': three_numbers(terms['alpha'], torch.stack(aux32['alpha']), torch.stack(aux64['alpha'])),
+            'data': three_numbers(terms['data'], torch.stack(lt32['data']), torch.stack(lt64['data'])),
+            'reg': three_numbers(terms['reg'], torch.stack(lt32['reg']), torch.stack(lt64['reg'])),
+            'energy': three_numbers(terms['reg_energy'], torch.stack(aux32['reg_energy']), torch.stack(aux64['reg_energy'])),
+            'grad_v': three_numbers(sampler.grad_v, g32, g64),
+            'log_std': three_numbers(sampler.gmm_parameters()[0], st32.log_std, st64.log_std),
+            'logits': three_numbers(sampler.gmm_parameters()[1], st32.logits, st64.logits),
+        }
+        if reg == 'lognormal':
+            r['reg_p'] = three_numbers(sampler.reg_parameters(), torch.stack((st32.loc, st32.log_scale)),
+                                       torch.stack((st64.loc, st64.log_scale)))
+        else:
+            r['reg_p'] = three_numbers(sampler.reg_parameters()[:1], st32.log_w_reg.view(1), st64.log_w_reg.view(1))
+        # deterministic step: v_new - v_old = -tau grad_v
+        r['step'] = three_numbers(sampler.v.cpu() - (st32.v + 0.4 * g32), -0.4 * g32, -0.4 * g64)
+        report.append(r)
+        print(f'[{data}/{reg}/learn={learnable}/vd={vd}] it {it}: ' +
+              ' '.join(f'{k}=({v[0]:.1e},{v[1]:.1e})' for k, v in r.items()))
+        # hyper-parameters follow the fp32 oracle from here on (shared mixture state must not drift apart)
+        K_ = st32.log_std.numel()
+        sampler.hyper[1:1 + K_] = st32.log_std.double().to(DEV)
+        sampler.hyper[9:9 + K_] = st32.logits.double().to(DEV)
+        sampler.hyper[17:17 + K_] = st32.adam_gmm.m[0].double().to(DEV)
+        sampler.hyper[25:25 + K_] = st32.adam_gmm.v[0].double().to(DEV)
+        sampler.hyper[33:33 + K_] = st32.adam_gmm.m[1].double().to(DEV)
+        sampler.hyper[41:41 + K_] = st32.adam_gmm.v[1].double().to(DEV)
+        st64.log_std.copy_(st32.log_std.double()); st64.logits.copy_(st32.logits.double())
+        for a, b in zip(st64.adam_gmm.m + st64.adam_gmm.v, st32.adam_gmm.m + st32.adam_gmm.v):
+            a.copy_(b.double())
+    return report
+
+
+FWD_KEYS = ('css', 'disp', 'T', 'im_w', 'energy', 'reg')
+
+
+def check(report):
+    for r in report:
+        for k in FWD_KEYS:
+            assert r[k][0] < 1e-5, (k, r[k])
+        for k in ('z', 'alpha', 'data', 'grad_v', 'step', 'log_std', 'logits', 'reg_p'):
+            e_new, e_ref, _ = r[k]
+            assert e_new <= max(1e-5, 2 * e_ref), (k, r[k])
+
+
+@pytest.mark.parametrize('data,reg,learnable', [('lcc', 'lognormal', True), ('lcc', 'l2', False), ('ssd', 'l2', True),
+                                                ('ssd', 'lognormal', False)])
+def test_transition_parity(built, data, reg, learnable):
+    check(run_pair(16, 2, data, reg, learnable, iters=3))
+
+
+def test_transition_parity_larger_no_vd(built):
+    check(run_pair(32, 3, 'lcc', 'lognormal', True, iters=2, vd=False, jitter=False))
+
+
+def test_transition_deterministic_no_noise(built):
+    check(run_pair(24, 1, 'lcc', 'lognormal', True, iters=2, noise=False, jitter=False, s=1))
+
+
+def test_graph_replay_matches_eager(built):
+    from irsgmcmc_b200.sampler import SGLDSampler, SGLDConfig
+    from irsgmcmc_b200.data_loader.synthetic import make_pair
+    n, C = 16, 2
+    fixed, moving, vp = make_pair(n)
+    outs = []
+    for use_graph in (False, True):
+        torch.manual_seed(0)
+        s = SGLDSampler(fixed, moving, C, SGLDConfig(), device=DEV)
+        s.set_state(0.5 * torch.randn(C, 3, n, n, n), torch.exp(0.5 * vp['log_var']))
+        s.init_gmm(sigma_hat=0.7)
+        s.step(5, use_graph=use_graph)
+        torch.cuda.synchronize()
+        outs.append((s.v.clone(), s.hyper.clone(), s.stats.clone()))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    assert outs[0][1][56] == 5  # Philox offset advanced once per transition
+
+
+def test_gmm_init_matches_oracle(built):
+    from irsgmcmc_b200.sampler import SGLDSampler, SGLDConfig
+    from irsgmcmc_b200.data_loader.synthetic import make_pair
+    n = 20
+    fixed, moving, vp = make_pair(n)
+    torch.manual_seed(1)
+    v_sample = 0.5 * torch.randn(1, 3, n, n, n)
+    s = SGLDSampler(fixed, moving, 1, SGLDConfig(), device=DEV)
+    s.init_gmm(v_sample)
+    st = O.State(O.Config(), v_sample, torch.ones(1, 3, n, n, n), (n, n, n))
+    O.gmm_init(st, fixed, moving, v_sample)
+    ls, lg = s.gmm_parameters()
+    print('gmm init', ls, st.log_std, lg, st.logits)
+    assert rel(ls, st.log_std) < 1e-4 and rel(lg, st.logits) < 1e-3
+
+
+def test_posterior_moments_single_rank(built):
+    from irsgmcmc_b200.sampler import SGLDSampler, SGLDConfig
+    from irsgmcmc_b200.data_loader.synthetic import make_pair
+    n, C = 16, 3
+    fixed, moving, vp = make_pair(n)
+    torch.manual_seed(2)
+    s = SGLDSampler(fixed, moving, C, SGLDConfig(), device=DEV)
+    s.init_chains('VI', vp)
+    s.init_gmm()
+    kept = []
+    for it in range(6):
+        s.step(2)
+        s.accumulate()
+        kept.append(s.displacement.clone())
+    mom = s.posterior_moments()
+    mean, std = O.posterior_statistics(torch.cat(kept).cpu())
+    assert mom['n'] == 18 and rel(mom['displacement_mean'], mean) < 1e-5 and rel(mom['displacement_std'], std) < 1e-4
