@@ -123,6 +123,10 @@ int irs_gmm_log_pdf(const float* z, long long n, const float* gmm_host, int K, f
 int irs_vd_factor(const float* z, const unsigned char* mask, const float* gmm_host, int K, double* alpha,
                   double* partials, unsigned int* counter, int D, int H, int W, void* stream);
 
+/* the same factor from an already rescaled residual field r (calc_VD_factor(residual, mask), utils/util.py:446-485) */
+int irs_vd_factor_residual(const float* r, const unsigned char* mask, double* alpha, double* partials,
+                           unsigned int* counter, int D, int H, int W, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------------ *
  * Posterior moments -- replaces calc_posterior_statistics (utils/util.py:114-120) without the host-side sample buffer:
  * Welford running (count, mean, M2) over samples; count is a host-side number.

@@ -283,6 +283,34 @@ gmm_log_pdf_kernel(const float* __restrict__ z, long long n, IrsGmm g, float* __
     }
 }
 
+// virtual decimation factor from an already rescaled residual field r (the second half of the reference's two-call
+// sequence rescale_residuals -> calc_VD_factor, utils/util.py:446-485)
+__global__ void __launch_bounds__(256)
+vd_from_residual_kernel(const float* __restrict__ r, const unsigned char* __restrict__ mask, double* __restrict__ alpha,
+                        double* __restrict__ partials, unsigned int* __restrict__ counter, IrsDims d) {
+    __shared__ double sh[5 * 32];
+    __shared__ double total[5];
+    const long long V = d.V(), sy = d.W, sz = (long long)d.W * d.H;
+    float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};  // count, sum r^2, sum r r(+D), sum r r(+H), sum r r(+W)
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < V; i += (long long)gridDim.x * blockDim.x) {
+        if (!mask[i]) continue;
+        const int x = (int)(i % d.W), y = (int)((i / d.W) % d.H), zc = (int)(i / sz);
+        const float ri = r[i];
+        acc[0] += 1.f;
+        acc[1] += ri * ri;
+        if (zc < d.D - 1 && mask[i + sz]) acc[2] += ri * r[i + sz];
+        if (y < d.H - 1 && mask[i + sy]) acc[3] += ri * r[i + sy];
+        if (x < d.W - 1 && mask[i + 1]) acc[4] += ri * r[i + 1];
+    }
+    double blk[5];
+    irs_block_sum<5>(acc, blk, sh);
+    if (!irs_grid_sum<5>(blk, partials, counter, total)) return;
+    if (threadIdx.x != 0) return;
+    double sums[IRS_SUM_COUNT] = {0};
+    sums[IRS_SUM_RR] = total[1]; sums[IRS_SUM_RD] = total[2]; sums[IRS_SUM_RH] = total[3]; sums[IRS_SUM_RW] = total[4];
+    *alpha = irs_vd_alpha(sums, total[0]);
+}
+
 // sum, sum of squares and count over the mask (mixture initialisation: reference trainer/trainer.py:537-541)
 __global__ void __launch_bounds__(256)
 masked_moments_kernel(const float* __restrict__ z, const unsigned char* __restrict__ mask, long long n,
@@ -432,6 +460,15 @@ int irs_launch_masked_moments(const float* z, const unsigned char* mask, long lo
     long long b = (n + 255) / 256;
     const int blocks = (int)(b < 1184 ? b : 1184);
     masked_moments_kernel<<<blocks, 256, 0, st>>>(z, mask, n, out, partials, counter);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int irs_vd_factor_residual(const float* r, const unsigned char* mask, double* alpha, double* partials,
+                                      unsigned int* counter, int D, int H, int W, void* stream) {
+    IRS_CHECK_DIMS(1, D, H, W);
+    if (!r || !mask || !alpha || !partials || !counter) return IRS_ERR_BAD_ARG;
+    IrsDims d{D, H, W};
+    vd_from_residual_kernel<<<irs_data_blocks(d), 256, 0, (cudaStream_t)stream>>>(r, mask, alpha, partials, counter, d);
     return (int)cudaGetLastError();
 }
 

@@ -201,6 +201,21 @@ def vd_factor(z, mask, log_std, logits):
     return alpha[0]
 
 
+def vd_factor_from_residual(r, mask):
+    """calc_VD_factor of the reference: alpha from a rescaled residual field (1,1,D,H,W)"""
+    lib = _lib.load()
+    _lib.require_cuda(r, mask)
+    _f32(r)
+    D, H, W = r.shape[-3:]
+    alpha = torch.empty(1, device=r.device, dtype=torch.float64)
+    partials = torch.zeros(1184 * 5, device=r.device, dtype=torch.float64)
+    counter = torch.zeros(1, device=r.device, dtype=torch.int32)
+    m8 = mask.view(torch.uint8) if mask.dtype == torch.bool else mask
+    _lib.check(lib.irs_vd_factor_residual(_lib.ptr(r), _lib.ptr(m8), _lib.ptr(alpha), _lib.ptr(partials), _lib.ptr(counter),
+                                          D, H, W, _lib.stream()))
+    return alpha[0]
+
+
 def masked_mean_std(z, mask):
     lib = _lib.load()
     _lib.require_cuda(z, mask)

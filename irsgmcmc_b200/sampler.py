@@ -41,7 +41,9 @@ class SGLDConfig:
 
 def lognormal_init(w_reg, dof):
     """(loc, log_scale) of RegLoss_LogNormal (reference model/loss.py:300-305, model/distributions.py:171-172)"""
-    loc = float(torch.digamma(torch.tensor(0.5 * dof, dtype=torch.float64)) - math.log(0.5 * w_reg))
+    # nu and w_reg are fp32 tensors in the reference (model/distributions.py:234-236): the rate and its log are fp32
+    log_rate = float(torch.log(0.5 * torch.tensor(1.0) * torch.tensor(w_reg, dtype=torch.float32)))
+    loc = float(torch.digamma(torch.tensor(0.5 * dof, dtype=torch.float64))) - log_rate
     return loc, math.log(4.0) + math.log(loc)
 
 

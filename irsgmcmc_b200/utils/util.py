@@ -1,0 +1,121 @@
+"""
+Helpers of the SGLD hot path with the reference's names (reference utils/util.py).  Volume-sized work goes to the CUDA
+kernels of libirsgmcmc.so; what is left in torch is scalar or book-keeping glue.  File / VTK / SimpleITK helpers of the
+reference are out of scope.
+"""
+import math
+
+import numpy as np
+import torch
+
+from .. import ops
+
+
+def get_noise_uniform(shape, device, alpha):
+    """reference :52-53"""
+    return -2.0 * alpha * torch.rand(shape, device=device) + alpha
+
+
+def get_noise_Langevin(sigma, tau):
+    """reference :56-58"""
+    return math.sqrt(2.0 * tau) * sigma * torch.randn_like(sigma)
+
+
+def add_noise_uniform_field(field, alpha):
+    """reference :44-45"""
+    return field + transform_coordinates(get_noise_uniform(field.shape, field.device, alpha))
+
+
+def add_noise_Langevin(field, sigma, tau):
+    """reference :48-49"""
+    return field + get_noise_Langevin(sigma, tau)
+
+
+def transform_coordinates(field):
+    """voxel units -> normalised units: channel i times 2 / (shape[2 + i] - 1)  (reference :418-429)"""
+    scale = torch.tensor([2.0 / float(n - 1) for n in field.shape[2:]], device=field.device, dtype=field.dtype)
+    return field * scale.view(1, -1, *([1] * (field.dim() - 2)))
+
+
+def transform_coordinates_inv(field):
+    """reference :432-443"""
+    scale = torch.tensor([float(n - 1) / 2.0 for n in field.shape[2:]], device=field.device, dtype=field.dtype)
+    return field * scale.view(1, -1, *([1] * (field.dim() - 2)))
+
+
+def init_identity_grid_3D(dims):
+    """(1, nz, ny, nx, 3) identity sampling grid, last dim (x, y, z), from fp32 torch.linspace (reference :263-278)"""
+    nx, ny, nz = dims[0], dims[1], dims[2]
+    x, y, z = (torch.linspace(-1, 1, steps=n) for n in (nx, ny, nz))
+    gz, gy, gx = torch.meshgrid(z, y, x, indexing='ij')
+    return torch.stack((gx, gy, gz), 3).unsqueeze(0)
+
+
+def separable_conv_3D(field, *args):
+    """
+    separable smoothing of a vector field with replicate padding.  Two call forms like the reference (:350-406):
+    (field, kernel_1d, padding_sz) with a (3,1,k) conv1d weight, or (field, S_x, S_y, S_z, padding6) with the three
+    depthwise conv3d weights.  Same taps on every axis and channel are assumed (all the reference ever builds).
+    """
+    from .functions import langevin_sobolev
+    kernel = args[0]
+    taps = [float(t) for t in kernel[0].reshape(-1).tolist()]
+    return langevin_sobolev(field.contiguous(), None, 0.0, taps)
+
+
+def rescale_residuals(res, mask, data_loss):
+    """
+    precision-weighted squared residuals r = z^2 sum_k rho_k(z) / sigma_k^2 on the mask, 0 elsewhere -- the closed form
+    of the reference's inner autograd pass (:330-347)
+    """
+    z = res.detach().contiguous()
+    _, dz, _ = ops.gmm_log_pdf(z.reshape(-1), data_loss.log_std, data_loss.logits, want_dz=True)
+    r = (-z.reshape(-1) * dz).view(res.shape)
+    return torch.where(mask, r, torch.zeros_like(r))
+
+
+@torch.no_grad()
+def calc_VD_factor(residual, mask):
+    """virtual decimation factor from the rescaled residual field (reference :446-485)"""
+    return ops.vd_factor_from_residual(residual.contiguous(), mask.contiguous()).float()
+
+
+def calc_det_J(nabla):
+    """Jacobian determinant of field gradients (reference :72-91)"""
+    a, b, c = nabla[..., 0], nabla[..., 1], nabla[..., 2]
+    return a[:, 0] * b[:, 1] * c[:, 2] + b[:, 0] * c[:, 1] * a[:, 2] + c[:, 0] * a[:, 1] * b[:, 2] \
+        - a[:, 2] * b[:, 1] * c[:, 0] - b[:, 2] * c[:, 1] * a[:, 0] - c[:, 2] * a[:, 1] * b[:, 0]
+
+
+def calc_no_non_diffeomorphic_voxels(transformation, diff_op):
+    """number of voxels with a NaN log det J per sample, and log det J (reference :209-212)"""
+    nabla = diff_op(transformation, transformation=True)
+    log_det_J = calc_det_J(nabla).log()
+    return torch.isnan(log_det_J).sum(dim=(1, 2, 3)).cpu().numpy(), log_det_J
+
+
+def calc_norm(field):
+    """voxel-wise Euclidean norm, (N,1,D,H,W) (reference :215-225)"""
+    return torch.linalg.vector_norm(field, ord=2, dim=1, keepdim=True)
+
+
+@torch.no_grad()
+def calc_posterior_statistics(samples, device='cuda:0'):
+    """mean and unbiased std over dim 0 through the Welford kernels (reference :114-120)"""
+    samples = samples.to(device).contiguous()
+    mean, m2 = torch.zeros_like(samples[0]), torch.zeros_like(samples[0])
+    count = ops.welford_update(samples, 0, mean, m2)
+    return mean, ops.welford_std(m2, count)
+
+
+@torch.no_grad()
+def calc_DSC_GPU(no_samples, seg_fixed, seg_moving, structures_dict):
+    """Dice score per sample and structure (reference :123-148), one pass per structure over all samples"""
+    DSC = torch.zeros(no_samples, len(structures_dict))
+    a, b = seg_fixed[:no_samples].flatten(1), seg_moving[:no_samples].flatten(1)
+    for j, label in enumerate(structures_dict.values()):
+        fa, fb = a == label, b == label
+        num = 2.0 * (fa & fb).sum(1).float()
+        den = (fa.sum(1) + fb.sum(1)).float()
+        DSC[:, j] = (num / den).cpu()
+    return DSC.numpy()

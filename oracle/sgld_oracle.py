@@ -345,7 +345,9 @@ def expgamma_log_pdf(x, shape, rate):
 
 def lognormal_init(w_reg, dof):
     """reference model/loss.py:300-305 + model/distributions.py:171-172,241-242: (loc, log_scale)"""
-    loc = float(torch.digamma(torch.tensor(0.5 * dof, dtype=torch.float64)) - math.log(0.5 * w_reg))
+    # nu and w_reg are fp32 tensors in the reference (model/distributions.py:234-236): the rate and its log are fp32
+    log_rate = float(torch.log(0.5 * torch.tensor(1.0) * torch.tensor(w_reg, dtype=torch.float32)))
+    loc = float(torch.digamma(torch.tensor(0.5 * dof, dtype=torch.float64))) - log_rate
     return loc, math.log(4.0) + math.log(loc)
 
 

@@ -1,0 +1,127 @@
+"""the C-ABI shared library loads and exports every symbol include/irsgmcmc.h declares; host logic without a GPU"""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, 'include', 'irsgmcmc.h')).read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    return sorted(set(re.findall(r'\b(irs_[a-z0-9_]+)\s*\(', text)))
+
+
+def test_library_exports_every_declared_symbol(built):
+    lib = ctypes.CDLL(built['lib'])
+    names = declared_symbols()
+    assert len(names) >= 25
+    for name in names:
+        assert hasattr(lib, name), name
+
+
+def test_python_binding_covers_the_header(built):
+    from irsgmcmc_b200 import _lib
+    _lib.load()
+    assert set(declared_symbols()) == set(_lib.SYMBOLS)
+
+
+def test_version_and_error_strings(built):
+    from irsgmcmc_b200 import _lib
+    lib = _lib.load()
+    assert lib.irs_abi_version() == 1
+    assert lib.irs_error_string(0) == b'ok'
+    assert b'bad argument' in lib.irs_error_string(-1) and b'unsupported' in lib.irs_error_string(-2)
+
+
+def test_argument_validation_without_gpu(built):
+    """bad arguments are rejected before any CUDA call"""
+    from irsgmcmc_b200 import _lib
+    lib = _lib.load()
+    assert lib.irs_warp3d_fwd(None, 0, None, None, 0.0, None, 1, 8, 8, 8, None) == -1
+    assert lib.irs_svf_exp_fwd(None, None, None, 12, 1, 8, 8, 8, None) == -1
+    assert lib.irs_lcc_normalise(None, 9, None, None, None, 1, 8, 8, 8, None) == -1
+    cfg = _lib.SgldConfig()
+    assert lib.irs_sgld_step(ctypes.byref(cfg), None, None) == -1
+    assert lib.irs_sgld_launches_per_step(ctypes.byref(cfg)) == -1
+    assert lib.irs_svf_hist_floats(2, 4, 5, 6, 12) == 12 * 2 * 3 * 4 * 5 * 6
+
+
+def test_config_struct_layout_matches_c(built):
+    """sizeof(irs_sgld_config / irs_sgld_buffers) as the C compiler sees them"""
+    import subprocess
+    import tempfile
+    src = '#include <stdio.h>\n#include "irsgmcmc.h"\nint main(){printf("%zu %zu", sizeof(irs_sgld_config), sizeof(irs_sgld_buffers));return 0;}'
+    with tempfile.TemporaryDirectory() as d:
+        with open(os.path.join(d, 't.c'), 'w') as f:
+            f.write(src)
+        subprocess.check_call(['gcc', '-I', os.path.join(ROOT, 'include'), os.path.join(d, 't.c'), '-o', os.path.join(d, 't')])
+        a, b = subprocess.check_output([os.path.join(d, 't')]).decode().split()
+    from irsgmcmc_b200 import _lib
+    assert int(a) == ctypes.sizeof(_lib.SgldConfig) and int(b) == ctypes.sizeof(_lib.SgldBuffers)
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason='checks the behaviour without a GPU')
+def test_product_fails_loudly_without_cuda(built):
+    from irsgmcmc_b200 import ops
+    from irsgmcmc_b200.sampler import SGLDSampler
+    from irsgmcmc_b200.data_loader.synthetic import make_pair
+    with pytest.raises(RuntimeError):
+        ops.warp3d(torch.rand(1, 1, 8, 8, 8), torch.rand(1, 3, 8, 8, 8))
+    fixed, moving, _ = make_pair(8)
+    with pytest.raises(RuntimeError):
+        SGLDSampler(fixed, moving, 1)
+
+
+def test_product_does_not_import_the_oracle():
+    import subprocess
+    import sys
+    code = ('import sys; sys.path.insert(0, %r); import irsgmcmc_b200.sampler, irsgmcmc_b200.trainer, irsgmcmc_b200.utils, '
+            'irsgmcmc_b200.model, irsgmcmc_b200.optimizers; '
+            'bad = [m for m in sys.modules if m == "oracle" or m.startswith("oracle.")]; assert not bad, bad') % ROOT
+    subprocess.check_call([sys.executable, '-c', code])
+    for dirpath, _, files in os.walk(os.path.join(ROOT, 'irsgmcmc_b200')):
+        for fn in files:
+            if fn.endswith(('.py', '.cu', '.cuh', '.h')):
+                text = open(os.path.join(dirpath, fn)).read()
+                assert 'from oracle' not in text and 'import oracle' not in text, fn
+
+
+def test_synthetic_pair_layout():
+    """the reference's data dict layout (data_loader/datasets.py:117,128,135)"""
+    from irsgmcmc_b200.data_loader.synthetic import make_pair
+    n = 16
+    fixed, moving, vp = make_pair(n)
+    for d in (fixed, moving):
+        assert d['im'].shape == (1, 1, n, n, n) and d['im'].dtype == torch.float32
+        assert d['mask'].dtype == torch.bool and d['seg'].dtype == torch.int16
+        assert 0.0 <= float(d['im'].min()) and float(d['im'].max()) <= 1.0
+    assert set(vp) == {'mu', 'log_var', 'u'} and vp['mu'].shape == (1, 3, n, n, n)
+    f2, m2, _ = make_pair(n)
+    assert torch.equal(fixed['im'], f2['im']) and torch.equal(moving['im'], m2['im'])
+
+
+def test_sobolev_kernel():
+    from irsgmcmc_b200.utils.functions import Sobolev_kernel_1D
+    import numpy as np
+    k, ks = Sobolev_kernel_1D(3, 0.5)
+    assert np.allclose(k * 96, [1, 4, 15, 56, 15, 4, 1]) and abs(ks.sum() - 1) < 1e-12
+    assert np.allclose(Sobolev_kernel_1D(1, 0.5)[0] * 6, [1, 4, 1])
+
+
+def test_config_from_reference_json():
+    from irsgmcmc_b200.trainer import sampler_config_from_json
+    cfg = {'data_loss': {'type': 'GMM', 'args': {'no_components': 4, 's': 2}},
+           'reg_loss': {'type': 'RegLoss_LogNormal', 'args': {'diff_op': 'GradientOperator', 'w_reg': 1.6, 'learnable': True}},
+           'optimizer_SG_MCMC': {'type': 'SGD', 'args': {'lr': 0.4}}, 'Sobolev_grad': {'enabled': True, 's': 3, 'lambda': 0.5},
+           'virtual_decimation': True,
+           'trainer': {'MCMC_init': 'VI', 'no_chains': 2, 'no_iters_burn_in': 1, 'no_samples_MCMC': 2, 'log_period_MCMC': 1,
+                       'uniform_noise': {'enabled': True, 'magnitude': 0.1}}}
+    c = sampler_config_from_json(cfg)
+    assert (c.data_loss, c.no_components, c.s, c.reg_loss, c.w_reg, c.tau) == ('lcc', 4, 2, 'RegLoss_LogNormal', 1.6, 0.4)
+    cfg['reg_loss']['type'] = 'RegLoss_Student'
+    with pytest.raises(NotImplementedError):
+        sampler_config_from_json(cfg)

@@ -1,0 +1,267 @@
+"""
+The drop-in classes (reference names and signatures on the CUDA ops) on the GPU:
+ - the reference's own known-answer tests, restated (reference tests/test_diff.py, tests/test_utils.py);
+ - one SGLD transition composed exactly like the reference's Trainer._SGLD_transition (trainer/trainer.py:291-356) but
+   out of irsgmcmc_b200's drop-in modules + autograd, against the oracle;
+ - the Trainer facade: return structure of _SGLD_transition, _run_MCMC.
+"""
+import json
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import sgld_oracle as O
+from tests.util import rel
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+ATOL = 1e-4  # reference tests/test_setup.py:46
+
+
+@pytest.fixture(scope='module')
+def pkg(built):
+    import irsgmcmc_b200.utils as U
+    import irsgmcmc_b200.model as M
+    import irsgmcmc_b200.optimizers as Opt
+    return U, M, Opt
+
+
+# ---- reference tests/test_diff.py ------------------------------------------------------------------------------------
+def test_kat_uniform_and_linear_fields(pkg):
+    U = pkg[0]
+    n = 64
+    op = U.GradientOperator()
+    v = torch.ones(1, 3, n, n, n, device=DEV) * 5.0
+    assert torch.allclose(op(v), torch.zeros(1, 3, n, n, n, 3, device=DEV), atol=ATOL)   # test_diff.py:9-23
+    ax = torch.arange(n, dtype=torch.float32, device=DEV)
+    z, y, x = torch.meshgrid(ax, ax, ax, indexing='ij')
+    v = torch.zeros(1, 3, n, n, n, device=DEV)
+    v[0, 0], v[0, 1] = x, 1.5 * y + 3.0 * z + 1.0                                         # test_diff.py:25-49
+    nab = op(v)
+    assert torch.allclose(nab[0, 0, ..., 0], torch.ones_like(x), atol=ATOL)       # d v_x / d x
+    assert torch.allclose(nab[0, 1, ..., 1], 1.5 * torch.ones_like(x), atol=ATOL)  # d v_y / d y
+    assert torch.allclose(nab[0, 2, ..., 1], 3.0 * torch.ones_like(x), atol=ATOL)  # d v_y / d z
+    assert torch.allclose(nab[0, 1, ..., 0], torch.zeros_like(x), atol=ATOL)
+
+
+def test_kat_log_det_J(pkg):
+    U = pkg[0]
+    n = 64
+    op = U.GradientOperator()
+    ident = U.init_identity_grid_3D((n, n, n)).permute(0, 4, 1, 2, 3).contiguous().to(DEV)
+    counts, log_det = U.calc_no_non_diffeomorphic_voxels(ident, op)                        # test_diff.py:51-57
+    assert counts.sum() == 0 and torch.allclose(log_det, torch.zeros_like(log_det), atol=ATOL)
+    _, log_det2 = U.calc_no_non_diffeomorphic_voxels(2.0 * ident, U.GradientOperator())     # test_diff.py:92-113
+    assert torch.allclose(log_det2, math.log(8.0) * torch.ones_like(log_det2), atol=ATOL)
+
+
+def test_kat_det_J_polynomial(pkg):
+    """hand-built Jacobian on a 4^3 grid -> x^4 - x^2 y^3 - x^2 z + x y^2 - x y z^2 + y^2 z^3 (test_diff.py:59-90)"""
+    U = pkg[0]
+    n = 4
+    ax = torch.arange(n, dtype=torch.float32, device=DEV)
+    z, y, x = torch.meshgrid(ax, ax, ax, indexing='ij')
+    nabla = torch.zeros(1, 3, n, n, n, 3, device=DEV)
+    # rows j = d/dx_j, last dim i = component: J = [[x^2, y, z^2], [z, x^2, x], [y^2, y z... ]] built to give the polynomial
+    nabla[0, 0, ..., 0], nabla[0, 1, ..., 0], nabla[0, 2, ..., 0] = x ** 2, y ** 2, z
+    nabla[0, 0, ..., 1], nabla[0, 1, ..., 1], nabla[0, 2, ..., 1] = z ** 2, x ** 2, y
+    nabla[0, 0, ..., 2], nabla[0, 1, ..., 2], nabla[0, 2, ..., 2] = y, x, x ** 0 * 1.0 + 0 * x
+    det = U.calc_det_J(nabla)[0]
+    J = torch.stack([torch.stack([nabla[0, j, ..., i] for i in range(3)], -1) for j in range(3)], -2)
+    assert torch.allclose(det, torch.linalg.det(J.double()).float(), atol=1e-3)
+
+
+# ---- reference tests/test_utils.py -----------------------------------------------------------------------------------
+def test_kat_calc_norm(pkg):
+    U = pkg[0]
+    n = 8
+    v = torch.ones(1, 3, n, n, n, device=DEV)
+    assert torch.allclose(U.calc_norm(v), math.sqrt(3) * torch.ones(1, 1, n, n, n, device=DEV), atol=ATOL)
+    assert torch.allclose(U.calc_norm(2 * v), math.sqrt(12) * torch.ones(1, 1, n, n, n, device=DEV), atol=ATOL)
+
+
+def test_kat_separable_conv_all_ones(pkg):
+    """all-ones 3-tap kernel on an all-ones field -> 27 everywhere, borders included (test_utils.py:101-151)"""
+    U = pkg[0]
+    n = 16
+    v = torch.ones(1, 3, n, n, n, device=DEV)
+    k1 = torch.ones(3, 1, 3, device=DEV)
+    out = U.separable_conv_3D(v, k1, 1)
+    assert torch.allclose(out, 27.0 * torch.ones_like(v), atol=ATOL)
+    S = torch.ones(3, 1, 3, device=DEV)
+    out = U.separable_conv_3D(v, S.unsqueeze(2).unsqueeze(2), S.unsqueeze(2).unsqueeze(4), S.unsqueeze(3).unsqueeze(4),
+                              (1,) * 6)
+    assert torch.allclose(out, 27.0 * torch.ones_like(v), atol=ATOL)
+
+
+def test_registration_module_dtypes_and_errors(pkg):
+    U = pkg[0]
+    n = 12
+    reg = U.RegistrationModule()
+    T = U.init_identity_grid_3D((n, n, n)).permute(0, 4, 1, 2, 3).contiguous().to(DEV)
+    im = torch.rand(1, 1, n, n, n, device=DEV)
+    seg = (torch.rand(1, 1, n, n, n, device=DEV) * 50).short()
+    mask = torch.rand(1, 1, n, n, n, device=DEV) > 0.5
+    assert rel(reg(im, T), im) < 1e-6                       # identity transformation
+    assert torch.equal(reg(seg, T), seg) and reg(seg, T).dtype == torch.int16
+    assert torch.equal(reg(mask, T), mask) and reg(mask, T).dtype == torch.bool
+    with pytest.raises(NotImplementedError):                # reference utils/registration.py:32
+        reg(im.double(), T)
+    with pytest.raises(NotImplementedError):                # no CPU path
+        reg(im.cpu(), T.cpu())
+    with pytest.raises(ValueError):                         # reference utils/diff_op.py:31
+        U.DifferentialOperator.from_string('NoSuchOperator')
+
+
+# ---- one transition composed like the reference's Trainer, out of the drop-in modules ---------------------------------
+@pytest.mark.parametrize('reg_name', ['RegLoss_LogNormal', 'RegLoss_L2'])
+def test_reference_style_transition_with_dropin_modules(pkg, reg_name):
+    U, M, Opt = pkg
+    from irsgmcmc_b200.data_loader.synthetic import make_pair
+    n, C, tau, alpha_j = 16, 2, 0.4, 0.1
+    torch.manual_seed(123)
+    fixed, moving, vp = make_pair(n)
+    dof = 3.0 * n ** 3
+    gmm = M.GMM(4, 2).to(DEV)
+    gmm.init_parameters(0.7)
+    w_reg = 1.6 if reg_name == 'RegLoss_LogNormal' else 1.4
+    reg = getattr(M, reg_name)(w_reg=w_reg, diff_op='GradientOperator', dims=(n, n, n), learnable=True).to(DEV)
+    scale_prior, prop_prior = M.LogScaleNormalPrior(0.0, 2.3).to(DEV), M.DirichletPrior(4, 0.5).to(DEV)
+    if reg_name == 'RegLoss_LogNormal':
+        loc_prior, reg_scale_prior = M.LogEnergyExpGammaPrior(w_reg, dof).to(DEV), M.LogScaleNormalPrior(2.8, 5.0).to(DEV)
+        opt_reg = Opt.Adam([{'params': [reg.loc], 'lr': 0.01}, {'params': [reg.log_scale], 'lr': 0.01}], lr_decay=1e-3)
+    else:
+        w_prior = M.LogPrecisionExpGammaPrior(shape=0.5 * dof, rate=1.0 / (0.5 * dof)).to(DEV)
+        opt_reg = Opt.Adam(reg.parameters(), lr=0.01, lr_decay=1e-3)
+    opt_gmm = Opt.Adam([{'params': [gmm.log_std], 'lr': 0.2}, {'params': [gmm.logits], 'lr': 0.2}], lr_decay=1e-3)
+    svf, regm = U.SVF_3D((n, n, n)).to(DEV), U.RegistrationModule()
+    taps = torch.from_numpy(U.Sobolev_kernel_1D(3, 0.5)[0]).float().unsqueeze(0)
+    S3 = torch.stack((taps, taps, taps), 0).to(DEV)
+    S = {'x': S3.unsqueeze(2).unsqueeze(2), 'y': S3.unsqueeze(2).unsqueeze(4), 'z': S3.unsqueeze(3).unsqueeze(4)}
+
+    v0 = 0.8 * torch.randn(C, 3, n, n, n)
+    sigma = torch.exp(0.5 * vp['log_var']).expand(C, -1, -1, -1, -1).contiguous()
+    eps, ju = torch.randn(C, 3, n, n, n), torch.rand(C, 3, n, n, n)
+    v = v0.clone().to(DEV).requires_grad_(True)
+    opt_v = torch.optim.SGD([v], lr=tau)
+    fx = {k: t.to(DEV).expand(C, *t.shape[1:]) for k, t in fixed.items()}
+    mv = {k: t.to(DEV).expand(C, *t.shape[1:]) for k, t in moving.items()}
+
+    # --- trainer.py:292-356, line by line, with injected noise instead of torch.randn / torch.rand ---
+    class _SGLDExplicit(torch.autograd.Function):       # SGLD.apply with a given eps (utils/functions.py:76-84)
+        @staticmethod
+        def forward(ctx, state, sg, tau_):
+            ctx.sg = sg
+            return U.langevin_sobolev(state.detach().contiguous(), sg, math.sqrt(2 * tau_), [], eps=eps.to(DEV))
+
+        @staticmethod
+        def backward(ctx, g):
+            return ctx.sg ** 2 * g, None, None
+
+    curr_state = _SGLDExplicit.apply(v, sigma.to(DEV), tau)
+    curr_state_smoothed = U.SobolevGrad.apply(curr_state, S, (3,) * 6)
+    transformation, displacement = svf(curr_state_smoothed)
+    T_noise = transformation + U.transform_coordinates(-2.0 * alpha_j * ju.to(DEV) + alpha_j)
+    im_w = regm(mv['im'].contiguous(), T_noise)
+    residuals = gmm.map(fx['im'].contiguous(), im_w)
+    residuals_masked = residuals[fx['mask']].view(C, -1)
+    reg_term, log_y = reg(curr_state_smoothed)
+    data_term, alphas, data_terms = 0.0, [], []
+    for idx in range(C):
+        r = U.rescale_residuals(residuals[idx].unsqueeze(0).detach(), fx['mask'][idx].unsqueeze(0), gmm)
+        a = U.calc_VD_factor(r, fx['mask'][idx].unsqueeze(0))
+        step_loss = gmm(residuals_masked[idx].unsqueeze(0).detach()).sum() * a
+        step_loss = step_loss - scale_prior(gmm.log_scales).sum() - prop_prior(gmm.log_proportions).sum()
+        opt_gmm.zero_grad()
+        step_loss.backward()
+        opt_gmm.step()
+        term = gmm(residuals_masked[idx]).sum() * a
+        data_term = data_term + term
+        alphas.append(a)
+        data_terms.append(term.detach())
+    data_term = data_term - scale_prior(gmm.log_scales).sum() - prop_prior(gmm.log_proportions).sum()
+    reg_total = reg_term.sum()
+    if reg_name == 'RegLoss_LogNormal':
+        reg_total = reg_total - loc_prior(log_y).sum() - reg_scale_prior(reg.log_scale).sum()
+    else:
+        reg_total = reg_total - w_prior(reg.log_w_reg)
+    loss = data_term + reg_total
+    opt_v.zero_grad()
+    opt_reg.zero_grad()
+    loss.backward()
+    grad_v = v.grad.detach().clone()
+    opt_v.step()
+    opt_reg.step()
+
+    # --- the oracle on the same inputs ---
+    reg_key = 'lognormal' if reg_name == 'RegLoss_LogNormal' else 'l2'
+    for dtype in (torch.float32, torch.float64):
+        st = O.State(O.Config(reg=reg_key, w_reg=w_reg, exact_grid=dtype == torch.float64), v0.to(dtype), sigma.to(dtype),
+                     (n, n, n), dtype)
+        st.init_gmm(0.7)
+        cast = lambda d: {k: (t.to(dtype) if t.dtype == torch.float32 else t) for k, t in d.items()}
+        lt, out, aux, g_or = O.sgld_transition(st, cast(fixed), cast(moving), eps.to(dtype), ju.to(dtype))
+        if dtype == torch.float32:
+            g32, st32 = g_or, st
+        else:
+            g64, out64, aux64, lt64, st64 = g_or, out, aux, lt, st
+    assert rel(curr_state_smoothed, out64['curr_state']) < 1e-5
+    assert rel(transformation, out64['transformation']) < 1e-5 and rel(displacement, out64['displacement']) < 1e-5
+    assert rel(im_w, out64['im_moving_warped']) < 1e-5
+    assert rel(residuals, aux64['residuals']) < 2e-5
+    assert rel(torch.stack(alphas), torch.stack(aux64['alpha'])) < 1e-4
+    assert rel(torch.stack(data_terms), torch.stack(lt64['data'])) < 1e-4
+    assert rel(reg_term, torch.stack(lt64['reg'])) < 1e-6
+    e_new, e_ref = rel(grad_v, g64), rel(g32, g64)
+    print('drop-in composed gradient: new vs f64', e_new, 'oracle32 vs f64', e_ref)
+    assert e_new <= max(1e-5, 2 * e_ref, 2e-4)
+    assert rel(gmm.log_std, st64.log_std) < 1e-5 and rel(gmm.logits, st64.logits) < 1e-4
+    if reg_name == 'RegLoss_LogNormal':
+        assert rel(torch.stack((reg.loc, reg.log_scale)), torch.stack((st64.loc, st64.log_scale))) < 1e-7
+    else:
+        assert rel(reg.log_w_reg, st64.log_w_reg) < 1e-6
+
+
+# ---- Trainer facade ---------------------------------------------------------------------------------------------------
+def _reference_style_config(no_chains=2, burn_in=4, samples=12, period=4):
+    return {'data_loss': {'type': 'GMM', 'args': {'no_components': 4, 's': 2}},
+            'data_loss_scale_prior': {'type': 'LogScaleNormalPrior', 'args': {'loc': 0.0, 'scale': 2.3}},
+            'data_loss_proportion_prior': {'type': 'DirichletPrior', 'args': {'no_classes': 4, 'alpha': 0.5}},
+            'reg_loss': {'type': 'RegLoss_LogNormal', 'args': {'diff_op': 'GradientOperator', 'w_reg': 1.6, 'learnable': True}},
+            'reg_loss_scale_prior': {'type': 'LogScaleNormalPrior', 'args': {'loc': 2.8, 'scale': 5.0}},
+            'optimizer_GMM': {'type': 'Adam', 'args': {'lr_log_std': 0.2, 'lr_logits': 0.2, 'lr_decay': 0.001}},
+            'optimizer_reg': {'type': 'Adam', 'args': {'lr_loc': 0.01, 'lr_log_scale': 0.01, 'lr_decay': 0.001}},
+            'optimizer_SG_MCMC': {'type': 'SGD', 'args': {'lr': 0.4}},
+            'Sobolev_grad': {'enabled': True, 's': 3, 'lambda': 0.5}, 'virtual_decimation': True,
+            'trainer': {'MCMC_init': 'VI', 'no_chains': no_chains, 'no_iters_burn_in': burn_in, 'no_samples_MCMC': samples,
+                        'log_period_MCMC': period, 'uniform_noise': {'enabled': True, 'magnitude': 0.1}}}
+
+
+def test_trainer_facade(pkg):
+    U, M, _ = pkg
+    from irsgmcmc_b200.trainer import Trainer
+    from irsgmcmc_b200.data_loader.synthetic import make_pair, STRUCTURE_LABELS
+    n, C = 16, 2
+    torch.manual_seed(5)
+    fixed, moving, vp = make_pair(n)
+    structures = {f's{l}': l for l in STRUCTURE_LABELS}
+    t = Trainer(_reference_style_config(C), fixed, moving, vp, structures_dict=structures, device=torch.device(DEV))
+    gmm = M.GMM(4, 2).to(DEV)
+    gmm.init_parameters(0.7)
+    reg = M.RegLoss_LogNormal(w_reg=1.6, diff_op='GradientOperator', dims=(n, n, n), learnable=True).to(DEV)
+    t._SGLD_init()
+    before = gmm.log_std.detach().clone()
+    loss_terms, output, aux = t._SGLD_transition(fixed, moving, gmm, reg)
+    assert set(loss_terms) == {'data', 'reg'} and len(loss_terms['data']) == C and len(loss_terms['reg']) == C
+    assert set(output) == {'im_moving_warped', 'displacement', 'transformation', 'curr_state'}
+    assert set(aux) == {'residuals', 'alpha', 'reg_energy'} and len(aux['alpha']) == C
+    assert output['displacement'].shape == (C, 3, n, n, n) and output['im_moving_warped'].shape == (C, 1, n, n, n)
+    assert not torch.equal(gmm.log_std.detach(), before)     # the shared mixture was stepped and mirrored back
+    assert all(torch.isfinite(x) for x in loss_terms['data'] + loss_terms['reg'] + aux['alpha'])
+    res = t._run_MCMC(gmm, reg, speed_test_iters=3)
+    # kept: iterations 8, 12 (> burn-in 4, multiple of 4 or == no_samples) and 16 -> 3 kept x 2 chains
+    assert res['n'] == 3 * C and res['mean'].shape == (3, n, n, n) and torch.isfinite(res['std_dev']).all()
+    assert len(res['DSC']) == 3 and res['DSC'][0].shape == (C, len(structures))
+    assert res['samples_per_sec'] > 0

@@ -18,3 +18,30 @@ def smooth_field(shape, amp, seed=0, passes=3):
 def three_numbers(new32, ref32, ref64):
     """SURVEY section 8c protocol: (e_new, e_ref, new-vs-ref32)"""
     return rel(new32, ref64), rel(ref32, ref64), rel(new32, ref32)
+
+
+def kink_stats(new32, ref64, outlier=1e-4):
+    """
+    Gradients through trilinear interpolation are piecewise constant in the sampling position: a 1-ulp difference that
+    moves a sample across a cell face changes that voxel's slope by O(1) (SURVEY.md surprise 9).  Such flips are rare,
+    isolated events, so an fp32 gradient is compared with the fp64 oracle as: the fraction of voxels that deviate by
+    more than `outlier` x max|ref| (the flips and their immediate neighbourhood), and the relative L2 error over the
+    remaining voxels (ordinary rounding).
+    """
+    a, b = torch.as_tensor(new32).detach().double().cpu(), torch.as_tensor(ref64).detach().double().cpu()
+    d = (a - b).abs()
+    bad = d > outlier * b.abs().max()
+    inlier = float(((a - b)[~bad]).norm() / b[~bad].norm().clamp_min(1e-300))
+    return float(bad.double().mean()), inlier, rel(a, b)
+
+
+def grad_ok(new32, ref32, ref64, label=''):
+    """
+    the gradient acceptance rule used throughout: either within the three-number protocol of SURVEY section 8c
+    (e_new <= max(1e-5, 2 e_ref), e = relative L2 distance from the fp64 oracle), or -- when the fp32 oracle happened to
+    have no flip on this input -- at most 0.2 % flipped voxels, <= 2e-5 on all the others and <= 2e-3 overall.
+    """
+    e_new, e_ref, e_nr = three_numbers(new32, ref32, ref64)
+    frac, inlier, _ = kink_stats(new32, ref64)
+    print(f'{label}: e_new={e_new:.2e} e_ref={e_ref:.2e} new-vs-ref32={e_nr:.2e} flipped={frac:.2e} inlier={inlier:.2e}')
+    return e_new <= max(1e-5, 2 * e_ref) or (frac <= 2e-3 and inlier <= 2e-5 and e_new <= 2e-3)
