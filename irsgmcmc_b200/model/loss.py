@@ -56,7 +56,9 @@ class _MixtureLogPdf(torch.autograd.Function):
     def forward(ctx, z, log_std, logits):
         flat = z.reshape(-1).contiguous()
         logp, dz, _ = ops.gmm_log_pdf(flat, log_std, logits, want_dz=True)
-        ctx.save_for_backward(flat, dz, log_std, logits)
+        # snapshots: the shared mixture is stepped in place between a chain's forward pass and the final backward pass
+        # (trainer/trainer.py:316-327 of the reference), and the gradient belongs to the values used in the forward pass
+        ctx.save_for_backward(flat, dz, log_std.detach().clone(), logits.detach().clone())
         ctx.z_shape = z.shape
         return logp.view(1, -1)
 
