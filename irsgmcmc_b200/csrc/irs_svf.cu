@@ -72,149 +72,336 @@ svf_step_bwd_scatter_kernel(const float* __restrict__ in, float in_scale, const 
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// Tiled adjoint step.  A CTA owns a TX x TY column of targets and marches over source planes; the velocity planes
-// s-R..s+R live in a shared-memory ring (halo R in x and y), the incoming gradient plane s in a second buffer.
-// Every source voxel is visited once per (ox, oy) offset and deposits into the 2R+1 register accumulators of the
-// target planes s-R..s+R, so a target voxel costs (2R+1)^2 pruned candidates instead of (2R+1)^3, all from shared
-// memory; the position term gathers the same ring.  Radii 1 and 2 are compiled; larger ones fall back to the global
-// gather below (or to the scatter kernel above gather_radius_max).
+// Tiled kernels.  A CTA owns a TX x TY column of voxels and marches along z.  The velocity planes z-R..z+R live in a
+// shared-memory ring (halo R in x and y, zero outside the volume), so every trilinear corner and every candidate
+// source of the interpolation transpose is a shared-memory load with a compile-time offset.  The next plane is
+// prefetched into registers while the current one is processed.
 // ---------------------------------------------------------------------------------------------------------------------
-constexpr int BT_X = 32, BT_Y = 8;
+constexpr int TILE_X = 32, TILE_Y = 8, TILE_T = TILE_X * TILE_Y;
 
 template <int R>
+struct Tile {
+    static constexpr int EX = TILE_X + 2 * R, EY = TILE_Y + 2 * R, PS = EX * EY, NP = 2 * R + 1;
+    static constexpr int NE = (PS + TILE_T - 1) / TILE_T;  // plane elements per thread
+};
+
+// the plane elements a thread moves from global to shared memory: fixed for the whole march
+template <int R>
+struct PlaneMap {
+    int gofs[Tile<R>::NE];   // offset inside a (H, W) plane, or -1 outside the volume
+    __device__ __forceinline__ void init(int x0t, int y0t, IrsDims d) {
+#pragma unroll
+        for (int k = 0; k < Tile<R>::NE; ++k) {
+            const int e = threadIdx.x + k * TILE_T;
+            const int ey = e / Tile<R>::EX, ex = e - ey * Tile<R>::EX;
+            const int gx = x0t - R + ex, gy = y0t - R + ey;
+            gofs[k] = (e < Tile<R>::PS && gx >= 0 && gx < d.W && gy >= 0 && gy < d.H) ? gy * d.W + gx : -1;
+        }
+    }
+};
+
+template <int R, int NCH>
+__device__ __forceinline__ void plane_fetch(const PlaneMap<R>& m, const float* __restrict__ src, long long V, int pz,
+                                            IrsDims d, float scale, float (&reg)[NCH][Tile<R>::NE]) {
+    const bool zin = pz >= 0 && pz < d.D;
+    const int zofs = pz * d.H * d.W;   // 3 V < 2^31 (IRS_CHECK_DIMS): 32-bit element offsets
+    const int Vi = (int)V;
+#pragma unroll
+    for (int k = 0; k < Tile<R>::NE; ++k) {
+        const bool ok = zin && m.gofs[k] >= 0;
+        const int o = zofs + m.gofs[k];
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch) reg[ch][k] = ok ? __ldg(src + (ch * Vi + o)) * scale : 0.f;
+    }
+}
+
+template <int R, int NCH>
+__device__ __forceinline__ bool plane_nonzero(const float (&reg)[NCH][Tile<R>::NE]) {
+    bool nz = false;
+#pragma unroll
+    for (int k = 0; k < Tile<R>::NE; ++k)
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch) nz = nz || (reg[ch][k] != 0.f);
+    return nz;
+}
+
+template <int R, int NCH>
+__device__ __forceinline__ void plane_store(float* __restrict__ dst, int ch_stride, const float (&reg)[NCH][Tile<R>::NE]) {
+#pragma unroll
+    for (int k = 0; k < Tile<R>::NE; ++k) {
+        const int e = threadIdx.x + k * TILE_T;
+        if (e < Tile<R>::PS) {
+#pragma unroll
+            for (int ch = 0; ch < NCH; ++ch) dst[ch * ch_stride + e] = reg[ch][k];
+        }
+    }
+}
+
+// trilinear cell in the ring: index of the (x0,y0,z0) corner and the z-corner offset; x/y corner offsets are 1 and EX.
+// slot_z = ring slot of plane z (the thread's own plane); the cell's planes lie within z-R .. z+R.
+template <int R>
+__device__ __forceinline__ void ring_cell(float px, float py, float pz, int x0t, int y0t, int z, int slot_z, int& i000,
+                                          int& sz, float& fx, float& fy, float& fz) {
+    const float x0 = floorf(px), y0 = floorf(py), z0 = floorf(pz);
+    fx = px - x0; fy = py - y0; fz = pz - z0;
+    const int ix = (int)x0, iy = (int)y0, iz = (int)z0;
+    int s0 = slot_z + (iz - z);
+    s0 += s0 < 0 ? Tile<R>::NP : 0;
+    s0 -= s0 >= Tile<R>::NP ? Tile<R>::NP : 0;
+    const int s1 = (s0 + 1 == Tile<R>::NP) ? 0 : s0 + 1;
+    i000 = s0 * Tile<R>::PS + (iy - (y0t - R)) * Tile<R>::EX + (ix - (x0t - R));
+    sz = (s1 - s0) * Tile<R>::PS;
+}
+
+template <int EX>
+__device__ __forceinline__ float ring_interp(const float* __restrict__ U, int i, int sz, float fx, float fy, float fz) {
+    const float v000 = U[i], v001 = U[i + 1], v010 = U[i + EX], v011 = U[i + EX + 1];
+    const float* U1 = U + sz;
+    const float v100 = U1[i], v101 = U1[i + 1], v110 = U1[i + EX], v111 = U1[i + EX + 1];
+    const float a00 = v000 + fx * (v001 - v000), a01 = v010 + fx * (v011 - v010);
+    const float a10 = v100 + fx * (v101 - v100), a11 = v110 + fx * (v111 - v110);
+    const float b0 = a00 + fy * (a01 - a00), b1 = a10 + fy * (a11 - a10);
+    return b0 + fz * (b1 - b0);
+}
+
+template <int EX>
+__device__ __forceinline__ void ring_interp_grad(const float* __restrict__ U, int i, int sz, float fx, float fy, float fz,
+                                                 float& gx, float& gy, float& gz) {
+    const float v000 = U[i], v001 = U[i + 1], v010 = U[i + EX], v011 = U[i + EX + 1];
+    const float* U1 = U + sz;
+    const float v100 = U1[i], v101 = U1[i + 1], v110 = U1[i + EX], v111 = U1[i + EX + 1];
+    const float d00 = v001 - v000, d01 = v011 - v010, d10 = v101 - v100, d11 = v111 - v110;
+    const float a00 = v000 + fx * d00, a01 = v010 + fx * d01, a10 = v100 + fx * d10, a11 = v110 + fx * d11;
+    const float e0 = a01 - a00, e1 = a11 - a10;
+    const float b0 = a00 + fy * e0, b1 = a10 + fy * e1;
+    const float dx0 = d00 + fy * (d01 - d00), dx1 = d10 + fy * (d11 - d10);
+    gx = dx0 + fz * (dx1 - dx0);
+    gy = e0 + fz * (e1 - e0);
+    gz = b1 - b0;
+}
+
+// ---- forward step -----------------------------------------------------------------------------------------------------
+// Threads whose displacement stays inside the ring window (|u| < R) gather from shared memory; the others (large
+// deformations) fall back to the global gather, so the kernel is exact for any field.
+template <int R>
+__global__ void __launch_bounds__(TILE_T)
+svf_step_fwd_tile_kernel(const float* __restrict__ in_all, float in_scale, float* __restrict__ out_all,
+                         float* __restrict__ maxabs, int seg_len, IrsDims d) {
+    using T = Tile<R>;
+    extern __shared__ float smem[];
+    float* U = smem;  // [3][NP][PS]
+    const long long V = d.V();
+    const float* in = in_all + (size_t)blockIdx.y * 3 * V;
+    float* out = out_all + (size_t)blockIdx.y * 3 * V;
+    const int tiles_x = (d.W + TILE_X - 1) / TILE_X, tiles_y = (d.H + TILE_Y - 1) / TILE_Y;
+    const int bx = blockIdx.x % tiles_x, by = (blockIdx.x / tiles_x) % tiles_y, bz = blockIdx.x / (tiles_x * tiles_y);
+    const int x0t = bx * TILE_X, y0t = by * TILE_Y, zs = bz * seg_len, ze = min(zs + seg_len, d.D);
+    const int lx = threadIdx.x % TILE_X, ly = threadIdx.x / TILE_X, x = x0t + lx, y = y0t + ly;
+    const bool active = x < d.W && y < d.H;
+    const int lc = (ly + R) * T::EX + lx + R;
+    const float xmax = (float)(d.W - 1), ymax = (float)(d.H - 1), zmax = (float)(d.D - 1);
+
+    PlaneMap<R> map;
+    map.init(x0t, y0t, d);
+    float reg[3][T::NE];
+    for (int pz = zs - R; pz <= zs + R; ++pz) {
+        plane_fetch<R, 3>(map, in, V, pz, d, in_scale, reg);
+        plane_store<R, 3>(U + (((pz % T::NP) + T::NP) % T::NP) * T::PS, T::NP * T::PS, reg);
+    }
+    __syncthreads();
+
+    float m = 0.f;
+    int slot = zs % T::NP;                       // ring slot of plane z
+    int slot_in = (zs + R + 1) % T::NP;          // ring slot the prefetched plane z+R+1 goes to (= slot of plane z-R)
+    int gi = (zs * d.H + y) * d.W + x;
+    const int HW = d.H * d.W, Vi = (int)V;
+    for (int z = zs; z < ze; ++z) {
+        plane_fetch<R, 3>(map, in, V, z + R + 1, d, in_scale, reg);  // in flight while this plane is processed
+        if (active) {
+            const float* Uz = U + slot * T::PS + lc;
+            const float ux = Uz[0], uy = Uz[T::NP * T::PS], uz = Uz[2 * T::NP * T::PS];
+            const float amax = fmaxf(fabsf(ux), fmaxf(fabsf(uy), fabsf(uz)));
+            m = fmaxf(m, amax);
+            if (amax < (float)R) {
+                const float px = irs_clampf((float)x + ux, 0.f, xmax), py = irs_clampf((float)y + uy, 0.f, ymax),
+                            pz = irs_clampf((float)z + uz, 0.f, zmax);
+                int i000, sz;
+                float fx, fy, fz;
+                ring_cell<R>(px, py, pz, x0t, y0t, z, slot, i000, sz, fx, fy, fz);
+                out[gi] = ux + ring_interp<T::EX>(U, i000, sz, fx, fy, fz);
+                out[Vi + gi] = uy + ring_interp<T::EX>(U + T::NP * T::PS, i000, sz, fx, fy, fz);
+                out[2 * Vi + gi] = uz + ring_interp<T::EX>(U + 2 * T::NP * T::PS, i000, sz, fx, fy, fz);
+            } else {
+                irs_body_svf_fwd(in, in_scale, out, V, gi, d);
+            }
+        }
+        __syncthreads();  // plane z-R is no longer needed
+        plane_store<R, 3>(U + slot_in * T::PS, T::NP * T::PS, reg);
+        __syncthreads();
+        slot = slot + 1 == T::NP ? 0 : slot + 1;
+        slot_in = slot_in + 1 == T::NP ? 0 : slot_in + 1;
+        gi += HW;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    __shared__ float sm[TILE_T / 32];
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float mm = sm[0];
+        for (int w = 1; w < TILE_T / 32; ++w) mm = fmaxf(mm, sm[w]);
+        if (mm > 0.f) atomic_max_nonneg(maxabs, mm);
+    }
+}
+
+// ---- adjoint step -------------------------------------------------------------------------------------------------------
+// Every source voxel of plane s is visited once per in-plane offset (ox, oy) and deposits into the 2R+1 register
+// accumulators of the target planes s-R..s+R: (2R+1)^2 candidates per voxel instead of (2R+1)^3, all from shared memory.
+// BORDER = false for tiles whose halo lies strictly inside the volume: positions cannot be clamped there.
+template <int R, bool BORDER>
 __device__ __forceinline__ void svf_bwd_tile_body(const float* __restrict__ u, float in_scale,
                                                   const float* __restrict__ gp, float* __restrict__ g, float out_scale,
                                                   IrsDims d, int x0t, int y0t, int zs, int ze, float* smem) {
-    constexpr int EX = BT_X + 2 * R, EY = BT_Y + 2 * R, PS = EX * EY, NP = 2 * R + 1;
-    float* U = smem;               // [3][NP][EY][EX]  ring of velocity planes, slot = plane mod NP
-    float* G = smem + 3 * NP * PS; // [3][EY][EX]      incoming gradient of the current source plane
+    using T = Tile<R>;
+    constexpr int NP = T::NP, PS = T::PS, EX = T::EX;
+    float* U = smem;                // [3][NP][PS]  velocity ring, slot = plane mod NP (scaled)
+    float* G = smem + 3 * NP * PS;  // [3][PS]      incoming gradient of the current source plane
     const long long V = d.V();
-    const int tid = threadIdx.x, lx = tid % BT_X, ly = tid / BT_X;
-    const int x = x0t + lx, y = y0t + ly;
+    const int Vi = (int)V, HW = d.H * d.W;
+    const int lx = threadIdx.x % TILE_X, ly = threadIdx.x / TILE_X, x = x0t + lx, y = y0t + ly;
     const bool active = x < d.W && y < d.H;
+    const int lc = (ly + R) * EX + lx + R;
+    const float xf = (float)x, yf = (float)y;
     const float xmax = (float)(d.W - 1), ymax = (float)(d.H - 1), zmax = (float)(d.D - 1);
 
-    auto load_u_plane = [&](int pz) {
-        if (pz < 0 || pz >= d.D) return;
-        const int slot = pz % NP;
-        for (int idx = tid; idx < PS; idx += BT_X * BT_Y) {
-            const int ey = idx / EX, ex = idx - ey * EX;
-            const int gx = x0t - R + ex, gy = y0t - R + ey;
-            const bool ok = gx >= 0 && gx < d.W && gy >= 0 && gy < d.H;
-            const long long gi = ((long long)pz * d.H + gy) * d.W + gx;
-#pragma unroll
-            for (int ch = 0; ch < 3; ++ch) U[(ch * NP + slot) * PS + idx] = ok ? __ldg(u + (size_t)ch * V + gi) * in_scale : 0.f;
-        }
-    };
-    auto load_g_plane = [&](int pz) {
-        if (pz < 0 || pz >= d.D) return;
-        for (int idx = tid; idx < PS; idx += BT_X * BT_Y) {
-            const int ey = idx / EX, ex = idx - ey * EX;
-            const int gx = x0t - R + ex, gy = y0t - R + ey;
-            const bool ok = gx >= 0 && gx < d.W && gy >= 0 && gy < d.H;
-            const long long gi = ((long long)pz * d.H + gy) * d.W + gx;
-#pragma unroll
-            for (int ch = 0; ch < 3; ++ch) G[ch * PS + idx] = ok ? __ldg(gp + (size_t)ch * V + gi) : 0.f;
-        }
-    };
+    PlaneMap<R> map;
+    map.init(x0t, y0t, d);
+    float ru[3][T::NE], rg[3][T::NE];
+    const int s_first = zs - R, s_last = ze - 1 + R;
+    for (int pz = s_first - R; pz <= s_first + R; ++pz) {
+        plane_fetch<R, 3>(map, u, V, pz, d, in_scale, ru);
+        plane_store<R, 3>(U + (((pz % NP) + NP) % NP) * PS, NP * PS, ru);
+    }
+    plane_fetch<R, 3>(map, gp, V, s_first, d, 1.f, rg);
+    plane_store<R, 3>(G, PS, rg);
+    // the incoming gradient vanishes outside the (dilated) fixed mask: planes of a tile that are all zero are skipped
+    bool g_nonzero = __syncthreads_or(plane_nonzero<R, 3>(rg));
 
     float acc[NP][3];
 #pragma unroll
     for (int i = 0; i < NP; ++i) acc[i][0] = acc[i][1] = acc[i][2] = 0.f;
 
-    const int s_first = zs - R, s_last = ze - 1 + R;
-    for (int pz = s_first - R; pz <= s_first + R; ++pz) load_u_plane(pz);
-    load_g_plane(s_first);
-    __syncthreads();
-
+    int slot = ((s_first % NP) + NP) % NP;             // ring slot of source plane s
+    int slot_in = (((s_first + R + 1) % NP) + NP) % NP;  // where the prefetched plane s+R+1 goes (= slot of plane s-R)
+    int gi = ((s_first - R) * d.H + y) * d.W + x;       // index of target (x, y, s-R)
     for (int s = s_first; s <= s_last; ++s) {
-        if (active && s >= 0 && s < d.D) {
-            const int slot = s % NP;
-            // ---- interpolation transpose: sources (x+ox, y+oy, s) deposit into targets (x, y, s-R..s+R) ----
+        plane_fetch<R, 3>(map, u, V, s + R + 1, d, in_scale, ru);   // in flight while plane s is processed
+        plane_fetch<R, 3>(map, gp, V, s + 1, d, 1.f, rg);
+        if (g_nonzero && active && s >= 0 && s < d.D) {
+            const float* Us = U + slot * PS;
+            const float sf = (float)s;
+            // ---- interpolation transpose ----
 #pragma unroll
             for (int oy = -R; oy <= R; ++oy) {
-                const int sy = y + oy;
-                if (sy < 0 || sy >= d.H) continue;
+                if (BORDER && (y + oy < 0 || y + oy >= d.H)) continue;
 #pragma unroll
                 for (int ox = -R; ox <= R; ++ox) {
-                    const int sx = x + ox;
-                    if (sx < 0 || sx >= d.W) continue;
-                    const int li = (ly + R + oy) * EX + lx + R + ox;
-                    const float wx = irs_hat(irs_clampf((float)sx + U[(0 * NP + slot) * PS + li], 0.f, xmax), x);
-                    if (wx == 0.f) continue;
-                    const float wy = irs_hat(irs_clampf((float)sy + U[(1 * NP + slot) * PS + li], 0.f, ymax), y);
-                    if (wy == 0.f) continue;
-                    const float pz = irs_clampf((float)s + U[(2 * NP + slot) * PS + li], 0.f, zmax);
+                    if (BORDER && (x + ox < 0 || x + ox >= d.W)) continue;
+                    const int li = lc + oy * EX + ox;
+                    float cx = Us[li], cy = Us[NP * PS + li];
+                    if (BORDER) {  // clamp(s + u) - s
+                        cx = irs_clampf(cx, -(xf + (float)ox), xmax - (xf + (float)ox));
+                        cy = irs_clampf(cy, -(yf + (float)oy), ymax - (yf + (float)oy));
+                    }
+                    float wx, wy;
+                    if (R == 1) {  // |c| < 1: the hat function reduces to one max / one subtraction
+                        wx = ox < 0 ? fmaxf(cx, 0.f) : (ox > 0 ? fmaxf(-cx, 0.f) : 1.f - fabsf(cx));
+                        wy = oy < 0 ? fmaxf(cy, 0.f) : (oy > 0 ? fmaxf(-cy, 0.f) : 1.f - fabsf(cy));
+                    } else {
+                        wx = fmaxf(0.f, 1.f - fabsf(cx + (float)ox));
+                        wy = fmaxf(0.f, 1.f - fabsf(cy + (float)oy));
+                    }
                     const float wxy = wx * wy;
+                    float cz = Us[2 * NP * PS + li];
+                    if (BORDER) cz = irs_clampf(cz, -sf, zmax - sf);
                     const float g0 = G[li], g1 = G[PS + li], g2 = G[2 * PS + li];
+                    if (R == 1) {
+                        const float wm = wxy * fmaxf(-cz, 0.f), w0 = wxy * (1.f - fabsf(cz)), wp = wxy * fmaxf(cz, 0.f);
+                        acc[0][0] += wm * g0; acc[0][1] += wm * g1; acc[0][2] += wm * g2;
+                        acc[1][0] += w0 * g0; acc[1][1] += w0 * g1; acc[1][2] += w0 * g2;
+                        acc[2][0] += wp * g0; acc[2][1] += wp * g1; acc[2][2] += wp * g2;
+                    } else {
+                        if (wxy == 0.f) continue;
 #pragma unroll
-                    for (int dz = -R; dz <= R; ++dz) {
-                        const float w = wxy * irs_hat(pz, s + dz);
-                        acc[dz + R][0] += w * g0; acc[dz + R][1] += w * g1; acc[dz + R][2] += w * g2;
+                        for (int dz = -R; dz <= R; ++dz) {
+                            const float w = wxy * fmaxf(0.f, 1.f - fabsf(cz - (float)dz));
+                            acc[dz + R][0] += w * g0; acc[dz + R][1] += w * g1; acc[dz + R][2] += w * g2;
+                        }
                     }
                 }
             }
             // ---- direct + position term of target (x, y, s) ----
             if (s >= zs && s < ze) {
-                const int lc = (ly + R) * EX + lx + R;
                 const float g0 = G[lc], g1 = G[PS + lc], g2 = G[2 * PS + lc];
-                float px = (float)x + U[(0 * NP + slot) * PS + lc];
-                float py = (float)y + U[(1 * NP + slot) * PS + lc];
-                float pz = (float)s + U[(2 * NP + slot) * PS + lc];
-                const float mx = irs_inside(px, d.W), my = irs_inside(py, d.H), mz = irs_inside(pz, d.D);
-                px = irs_clampf(px, 0.f, xmax); py = irs_clampf(py, 0.f, ymax); pz = irs_clampf(pz, 0.f, zmax);
-                const float fx0 = floorf(px), fy0 = floorf(py), fz0 = floorf(pz);
-                const int ix = (int)fx0, iy = (int)fy0, iz = (int)fz0;
-                IrsCell cell;
-                cell.fx = px - fx0; cell.fy = py - fy0; cell.fz = pz - fz0;
-                cell.sx = (ix + 1 < d.W) ? 1 : 0;
-                cell.sy = (iy + 1 < d.H) ? EX : 0;
-                cell.sz = (iz + 1 < d.D) ? (((iz + 1) % NP) - (iz % NP)) * PS : 0;
-                cell.i000 = (iz % NP) * PS + (iy - (y0t - R)) * EX + (ix - (x0t - R));
-                float jx = 0.f, jy = 0.f, jz = 0.f, dx, dy, dz;
-                irs_interp_grad(cell, [&](int k) { return U[k]; }, dx, dy, dz);
-                jx += g0 * dx; jy += g0 * dy; jz += g0 * dz;
-                irs_interp_grad(cell, [&](int k) { return U[NP * PS + k]; }, dx, dy, dz);
+                float px = xf + Us[lc], py = yf + Us[NP * PS + lc], pz = sf + Us[2 * NP * PS + lc];
+                float mx = 1.f, my = 1.f, mz = 1.f;
+                if (BORDER) {
+                    mx = irs_inside(px, d.W); my = irs_inside(py, d.H); mz = irs_inside(pz, d.D);
+                    px = irs_clampf(px, 0.f, xmax); py = irs_clampf(py, 0.f, ymax); pz = irs_clampf(pz, 0.f, zmax);
+                }
+                int i000, sz;
+                float fx, fy, fz, dx, dy, dz, jx, jy, jz;
+                ring_cell<R>(px, py, pz, x0t, y0t, s, slot, i000, sz, fx, fy, fz);
+                ring_interp_grad<EX>(U, i000, sz, fx, fy, fz, dx, dy, dz);
+                jx = g0 * dx; jy = g0 * dy; jz = g0 * dz;
+                ring_interp_grad<EX>(U + NP * PS, i000, sz, fx, fy, fz, dx, dy, dz);
                 jx += g1 * dx; jy += g1 * dy; jz += g1 * dz;
-                irs_interp_grad(cell, [&](int k) { return U[2 * NP * PS + k]; }, dx, dy, dz);
+                ring_interp_grad<EX>(U + 2 * NP * PS, i000, sz, fx, fy, fz, dx, dy, dz);
                 jx += g2 * dx; jy += g2 * dy; jz += g2 * dz;
                 acc[R][0] += g0 + mx * jx; acc[R][1] += g1 + my * jy; acc[R][2] += g2 + mz * jz;
             }
         }
         // ---- target plane s-R is complete ----
-        const int t = s - R;
-        if (active && t >= zs && t < ze) {
-            const long long gi = ((long long)t * d.H + y) * d.W + x;
-            g[gi] = acc[0][0] * out_scale; g[V + gi] = acc[0][1] * out_scale; g[2 * V + gi] = acc[0][2] * out_scale;
+        if (active && s - R >= zs && s - R < ze) {
+            g[gi] = acc[0][0] * out_scale; g[Vi + gi] = acc[0][1] * out_scale; g[2 * Vi + gi] = acc[0][2] * out_scale;
         }
 #pragma unroll
         for (int i = 0; i < NP - 1; ++i) { acc[i][0] = acc[i + 1][0]; acc[i][1] = acc[i + 1][1]; acc[i][2] = acc[i + 1][2]; }
         acc[NP - 1][0] = acc[NP - 1][1] = acc[NP - 1][2] = 0.f;
-        __syncthreads();                 // everyone is done with plane s-R of the ring and with G
-        load_u_plane(s + 1 + R);         // overwrites the slot of plane s-R
-        load_g_plane(s + 1);
-        __syncthreads();
+        __syncthreads();                 // everyone is done with ring plane s-R and with G
+        plane_store<R, 3>(U + slot_in * PS, NP * PS, ru);
+        plane_store<R, 3>(G, PS, rg);
+        g_nonzero = __syncthreads_or(plane_nonzero<R, 3>(rg));
+        slot = slot + 1 == NP ? 0 : slot + 1;
+        slot_in = slot_in + 1 == NP ? 0 : slot_in + 1;
+        gi += HW;
     }
 }
 
-__global__ void __launch_bounds__(BT_X * BT_Y)
+__global__ void __launch_bounds__(TILE_T)
 svf_step_bwd_tile_kernel(const float* __restrict__ in, float in_scale, const float* __restrict__ gp_all,
                          float* __restrict__ g_all, const float* __restrict__ maxabs, int radius_max, float out_scale,
                          int seg_len, IrsDims d) {
     extern __shared__ float smem[];
     const int R = (int)floorf(__ldg(maxabs)) + 1;
-    if (R > radius_max) return;  // the scatter kernel owns this step (after svf_step_bwd_kernel wrote the other terms)
+    if (R > radius_max) return;  // the scatter kernels own this step
     const long long V = d.V();
     const size_t off = (size_t)blockIdx.y * 3 * V;
-    const int tiles_x = (d.W + BT_X - 1) / BT_X, tiles_y = (d.H + BT_Y - 1) / BT_Y;
+    const int tiles_x = (d.W + TILE_X - 1) / TILE_X, tiles_y = (d.H + TILE_Y - 1) / TILE_Y;
     const int bx = blockIdx.x % tiles_x, by = (blockIdx.x / tiles_x) % tiles_y, bz = blockIdx.x / (tiles_x * tiles_y);
-    const int x0t = bx * BT_X, y0t = by * BT_Y, zs = bz * seg_len, ze = min(zs + seg_len, d.D);
+    const int x0t = bx * TILE_X, y0t = by * TILE_Y, zs = bz * seg_len, ze = min(zs + seg_len, d.D);
+    // the tile, its halo and every clamped position stay strictly inside the volume?
+    auto interior = [&](int Rr) {
+        return x0t - 2 * Rr >= 0 && x0t + TILE_X - 1 + 2 * Rr <= d.W - 1 && y0t - 2 * Rr >= 0 &&
+               y0t + TILE_Y - 1 + 2 * Rr <= d.H - 1 && zs - 2 * Rr >= 0 && ze - 1 + 2 * Rr <= d.D - 1;
+    };
     if (R == 1) {
-        svf_bwd_tile_body<1>(in + off, in_scale, gp_all + off, g_all + off, out_scale, d, x0t, y0t, zs, ze, smem);
+        if (interior(1)) svf_bwd_tile_body<1, false>(in + off, in_scale, gp_all + off, g_all + off, out_scale, d, x0t, y0t, zs, ze, smem);
+        else svf_bwd_tile_body<1, true>(in + off, in_scale, gp_all + off, g_all + off, out_scale, d, x0t, y0t, zs, ze, smem);
     } else if (R == 2) {
-        svf_bwd_tile_body<2>(in + off, in_scale, gp_all + off, g_all + off, out_scale, d, x0t, y0t, zs, ze, smem);
+        svf_bwd_tile_body<2, true>(in + off, in_scale, gp_all + off, g_all + off, out_scale, d, x0t, y0t, zs, ze, smem);
     } else {  // rare: wide gather straight from global memory
-        const int x = x0t + (threadIdx.x % BT_X), y = y0t + (threadIdx.x / BT_X);
+        const int x = x0t + (threadIdx.x % TILE_X), y = y0t + (threadIdx.x / TILE_X);
         if (x >= d.W || y >= d.H) return;
         for (int z = zs; z < ze; ++z)
             irs_body_svf_bwd(in + off, in_scale, gp_all + off, g_all + off, R, out_scale, V,
@@ -223,7 +410,28 @@ svf_step_bwd_tile_kernel(const float* __restrict__ in, float in_scale, const flo
 }
 
 constexpr size_t svf_bwd_tile_smem(int R) {
-    return sizeof(float) * (size_t)(3 * (2 * R + 1) + 3) * (BT_X + 2 * R) * (BT_Y + 2 * R);
+    return sizeof(float) * (size_t)(3 * (2 * R + 1) + 3) * (TILE_X + 2 * R) * (TILE_Y + 2 * R);
+}
+constexpr size_t svf_fwd_tile_smem(int R) {
+    return sizeof(float) * (size_t)(3 * (2 * R + 1)) * (TILE_X + 2 * R) * (TILE_Y + 2 * R);
+}
+
+// z-segment length: the (tiles x segments x chains) CTAs should fill whole waves of the 148 SMs, while each segment
+// pays `halo` extra plane-iterations.  Picks the segment count with the lowest modelled time.
+static int svf_seg_len(IrsDims d, int C, int slots, int halo) {
+    const long long tiles = (long long)((d.W + TILE_X - 1) / TILE_X) * ((d.H + TILE_Y - 1) / TILE_Y) * C;
+    int best_len = d.D;
+    double best_cost = 1e300;
+    for (int nseg = 1; nseg <= d.D; ++nseg) {
+        const int len = (d.D + nseg - 1) / nseg;
+        if (len < 4 && nseg > 1) break;
+        const int nseg_eff = (d.D + len - 1) / len;
+        const long long ctas = tiles * nseg_eff;
+        const long long waves = (ctas + slots - 1) / slots;
+        const double cost = (double)waves * (len + halo);
+        if (cost < best_cost - 1e-9) { best_cost = cost; best_len = len; }
+    }
+    return best_len;
 }
 
 __global__ void __launch_bounds__(256)
@@ -249,17 +457,32 @@ svf_outputs_kernel(const float* __restrict__ u_all, const float* __restrict__ li
     }
 }
 
+template <typename K>
+static int resident_ctas(K kernel, size_t smem) {
+    int per_sm = 0, sms = 148, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, TILE_T, smem) != cudaSuccess || per_sm < 1) per_sm = 2;
+    return per_sm * sms;
+}
+
 }  // namespace
 
 int irs_launch_svf_fwd(const float* v, float* hist, float* maxabs, int n_steps, int C, IrsDims d, cudaStream_t st) {
     const size_t F = (size_t)C * 3 * d.V();
     cudaError_t e = cudaMemsetAsync(maxabs, 0, sizeof(float) * n_steps, st);
     if (e != cudaSuccess) return (int)e;
-    dim3 grid((unsigned)((d.V() + 255) / 256), C);
     const float scale0 = 1.0f / (float)(1 << n_steps);
+    constexpr int RF = 2;
+    static int slots = 0;
+    if (slots == 0) slots = resident_ctas(svf_step_fwd_tile_kernel<RF>, svf_fwd_tile_smem(RF));
+    const int seg_len = svf_seg_len(d, C, slots, 2 * RF + 2);
+    const int tiles = ((d.W + TILE_X - 1) / TILE_X) * ((d.H + TILE_Y - 1) / TILE_Y);
+    dim3 tgrid(tiles * ((d.D + seg_len - 1) / seg_len), C);
     for (int k = 0; k < n_steps; ++k) {
         const float* in = (k == 0) ? v : hist + (size_t)(k - 1) * F;
-        svf_step_fwd_kernel<<<grid, 256, 0, st>>>(in, k == 0 ? scale0 : 1.0f, hist + (size_t)k * F, maxabs + k, d);
+        svf_step_fwd_tile_kernel<RF><<<tgrid, TILE_T, svf_fwd_tile_smem(RF), st>>>(in, k == 0 ? scale0 : 1.0f,
+                                                                                 hist + (size_t)k * F, maxabs + k, seg_len, d);
     }
     return (int)cudaGetLastError();
 }
@@ -275,10 +498,10 @@ int irs_launch_svf_bwd(const float* v, const float* hist, const float* maxabs, f
         if (e != cudaSuccess) return (int)e;
         configured = true;
     }
-    const int tiles = ((d.W + BT_X - 1) / BT_X) * ((d.H + BT_Y - 1) / BT_Y);
-    // z segments: long enough to amortise the 2R extra source planes, short enough to fill 148 SMs
-    int seg_len = 32;
-    while (seg_len > 8 && (long long)tiles * ((d.D + seg_len - 1) / seg_len) * C < 4 * 148) seg_len /= 2;
+    const int tiles = ((d.W + TILE_X - 1) / TILE_X) * ((d.H + TILE_Y - 1) / TILE_Y);
+    static int slots = 0;
+    if (slots == 0) slots = resident_ctas(svf_step_bwd_tile_kernel, smem);
+    const int seg_len = svf_seg_len(d, C, slots, 6);
     const int nseg = (d.D + seg_len - 1) / seg_len;
     dim3 tgrid(tiles * nseg, C);
     dim3 vgrid((unsigned)((d.V() + 255) / 256), C);
@@ -288,7 +511,7 @@ int irs_launch_svf_bwd(const float* v, const float* hist, const float* maxabs, f
         const float* in = (k == 0) ? v : hist + (size_t)(k - 1) * F;
         float* out = (k == 0) ? g_v : (((n_steps - 1 - k) & 1) ? g_u : g_work);
         const float in_scale = (k == 0) ? scale0 : 1.0f;
-        svf_step_bwd_tile_kernel<<<tgrid, BT_X * BT_Y, smem, st>>>(in, in_scale, gp, out, maxabs + k, gather_radius_max,
+        svf_step_bwd_tile_kernel<<<tgrid, TILE_T, smem, st>>>(in, in_scale, gp, out, maxabs + k, gather_radius_max,
                                                                   in_scale, seg_len, d);
         svf_step_bwd_scatter_pre_kernel<<<vgrid, 256, 0, st>>>(in, in_scale, gp, out, maxabs + k, gather_radius_max,
                                                                in_scale, d);
