@@ -161,7 +161,8 @@ int irs_welford_std(const float* m2, double count, float* std_out, long long n, 
 #define IRS_HYPER_REG_M 52
 #define IRS_HYPER_REG_V 54
 #define IRS_HYPER_ITER 56        /* iteration counter: the Philox offset */
-#define IRS_HYPER_SIZE 64
+#define IRS_HYPER_SCRATCH 64     /* 24 doubles of reduction scratch used inside a step */
+#define IRS_HYPER_SIZE 96
 
 /* layout of one row of the per-chain `stats` output (doubles) */
 #define IRS_STAT_ALPHA 0         /* virtual decimation factor */
@@ -220,7 +221,7 @@ typedef struct irs_sgld_buffers {
     float* field_b;              /* (C,3,V) scratch */
     float* grad_v;               /* (C,3,V) sigma^2 dL/d css: what SGD applies */
     float* maxabs;               /* svf_steps floats */
-    double* hyper;               /* IRS_HYPER_SIZE doubles */
+    double* hyper;               /* IRS_HYPER_SIZE doubles (parameters, optimiser state, scratch) */
     double* stats;               /* C * IRS_STAT_SIZE doubles */
     float* gmm_table;            /* C * 16 floats: per chain (lw[8], prec[8]) after that chain's update */
     double* partials;            /* irs_sgld_partials_doubles() doubles */
@@ -229,7 +230,7 @@ typedef struct irs_sgld_buffers {
 
 size_t irs_sgld_partials_doubles(const irs_sgld_config* cfg);
 
-/* enqueue one transition on `stream` (about 40 + 2 C kernel launches; capturable in a CUDA graph) */
+/* enqueue one transition on `stream` (about 60 + 2 C kernel launches; capturable in a CUDA graph) */
 int irs_sgld_step(const irs_sgld_config* cfg, const irs_sgld_buffers* buf, void* stream);
 
 /* Profiling aid: one eager transition with a CUDA event between stages; synchronises the stream and writes the

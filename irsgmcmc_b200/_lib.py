@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libirsgmcmc.so')
 
 c_float_p = ctypes.c_void_p
-HYPER_SIZE = 64
+HYPER_SIZE = 96
 STAT_SIZE = 8
 MAX_K = 8
 

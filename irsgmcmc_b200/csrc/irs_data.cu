@@ -43,30 +43,50 @@ box_tile_kernel(const float* __restrict__ in0, const float* __restrict__ in1, co
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
     // ---- load tile + halo with the pre-operation ----
+    // column chunks of a row: lane and lane + 32; their (clamped) x offsets are fixed for the whole tile
+    const int gx0 = x0 - S + lane, gx1 = gx0 + 32;
+    const bool has1 = lane + 32 < EX;
+    const int cx0 = irs_clampi(gx0, 0, d.W - 1), cx1 = irs_clampi(gx1, 0, d.W - 1);
+    const bool okx0 = gx0 >= 0 && gx0 < d.W, okx1 = gx1 >= 0 && gx1 < d.W;
+    const float* p0 = in0 + off;
+    const float* p1 = in1 ? in1 + off : nullptr;
+    const float* p2 = in2 ? in2 + off : nullptr;
     for (int row = warp; row < EZ * EY; row += 8) {
-        const int tz = row / EY, ty = row % EY;
+        const int tz = row / EY, ty = row - tz * EY;
         const int gz = z0 - S + tz, gy = y0 - S + ty;
-        for (int tx = lane; tx < EX; tx += 32) {
-            const int gx = x0 - S + tx;
-            float val;
-            if (!BWD) {
-                const long long gi = ((long long)irs_clampi(gz, 0, d.D - 1) * d.H + irs_clampi(gy, 0, d.H - 1)) * d.W +
-                                     irs_clampi(gx, 0, d.W - 1);
-                const float a = __ldg(in0 + off + gi);
-                val = (MODE == BOX_FWD_VAR) ? a * a : a;
-            } else {
-                val = 0.f;
-                if (gz >= 0 && gz < d.D && gy >= 0 && gy < d.H && gx >= 0 && gx < d.W) {
-                    const long long gi = ((long long)gz * d.H + gy) * d.W + gx;
-                    if (MODE == BOX_BWD_VAR) {
-                        const float g = sign * __ldg(in0 + off + gi), a = __ldg(in1 + off + gi), r = __ldg(in2 + off + gi);
-                        val = -0.5f * g * a * r * r * r;
-                    } else {
-                        val = __ldg(in0 + off + gi);
-                    }
+        float* arow = A + row * EX;
+        if (!BWD) {
+            const int rbase = (irs_clampi(gz, 0, d.D - 1) * d.H + irs_clampi(gy, 0, d.H - 1)) * d.W;
+            const float a = __ldg(p0 + rbase + cx0);
+            arow[lane] = (MODE == BOX_FWD_VAR) ? a * a : a;
+            if (has1) {
+                const float b = __ldg(p0 + rbase + cx1);
+                arow[lane + 32] = (MODE == BOX_FWD_VAR) ? b * b : b;
+            }
+        } else {
+            const bool rin = gz >= 0 && gz < d.D && gy >= 0 && gy < d.H;
+            const int rbase = (gz * d.H + gy) * d.W;
+            float va = 0.f, vb = 0.f;
+            if (rin && okx0) {
+                const int gi = rbase + gx0;
+                if (MODE == BOX_BWD_VAR) {
+                    const float g = sign * __ldg(p0 + gi), a = __ldg(p1 + gi), r = __ldg(p2 + gi);
+                    va = -0.5f * g * a * r * r * r;
+                } else {
+                    va = __ldg(p0 + gi);
                 }
             }
-            A[(tz * EY + ty) * EX + tx] = val;
+            if (has1 && rin && okx1) {
+                const int gi = rbase + gx1;
+                if (MODE == BOX_BWD_VAR) {
+                    const float g = sign * __ldg(p0 + gi), a = __ldg(p1 + gi), r = __ldg(p2 + gi);
+                    vb = -0.5f * g * a * r * r * r;
+                } else {
+                    vb = __ldg(p0 + gi);
+                }
+            }
+            arow[lane] = va;
+            if (has1) arow[lane + 32] = vb;
         }
     }
     __syncthreads();
@@ -215,6 +235,90 @@ gmm_stats_kernel(const float* __restrict__ z, const unsigned char* __restrict__ 
     stats_row[IRS_STAT_NLL_PRE] = total[IRS_SUM_NLL];
 }
 
+// ---- fused-step version of the above, split so that the mixture is evaluated once per voxel ----------------------------
+// pass A: per masked voxel one mixture evaluation -> sums (NLL, sum r^2, rho_k, Q_k) and the VD residual r written out.
+//         FINALIZE: no lag sums needed (virtual decimation off, or a stored factor is reused): the last block steps Adam.
+template <bool FINALIZE>
+__global__ void __launch_bounds__(256)
+gmm_stats_a_kernel(const float* __restrict__ z, const unsigned char* __restrict__ mask, double* __restrict__ hyper,
+                   IrsHyperCfg cfg, double* __restrict__ partials, unsigned int* __restrict__ counter,
+                   float* __restrict__ r_out, double* __restrict__ totals_out, double* __restrict__ stats_row,
+                   float* __restrict__ table_out, const double* __restrict__ alpha_fixed, int V) {
+    __shared__ IrsGmm g;
+    __shared__ double sh[IRS_SUM_COUNT * 32];
+    __shared__ double total[IRS_SUM_COUNT];
+    if (threadIdx.x == 0) irs_gmm_table(hyper + IRS_HYPER_LOG_STD, hyper + IRS_HYPER_LOGITS, cfg.K, g);
+    __syncthreads();
+    const IrsGmm gl = g;
+    float acc[IRS_SUM_COUNT];
+#pragma unroll
+    for (int k = 0; k < IRS_SUM_COUNT; ++k) acc[k] = 0.f;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < V; i += gridDim.x * blockDim.x) {
+        float r = 0.f;
+        if (mask[i]) {
+            const float zi = z[i];
+            float rho[IRS_MAX_K], wp;
+            const float lp = irs_gmm_eval(gl, zi, rho, wp);
+            const float z2 = zi * zi;
+            r = z2 * wp;
+            acc[IRS_SUM_NLL] -= lp;
+            acc[IRS_SUM_RR] += r * r;
+#pragma unroll
+            for (int k = 0; k < IRS_MAX_K; ++k) if (k < gl.K) {
+                acc[IRS_SUM_RHO + k] += rho[k];
+                acc[IRS_SUM_Q + k] += rho[k] * z2 * gl.prec[k];
+            }
+        }
+        if (!FINALIZE) r_out[i] = r;
+    }
+    double blk[IRS_SUM_COUNT];
+    irs_block_sum<IRS_SUM_COUNT>(acc, blk, sh);
+    if (!irs_grid_sum<IRS_SUM_COUNT>(blk, partials, counter, total)) return;
+    if (!FINALIZE) {
+        if (threadIdx.x < IRS_SUM_COUNT) totals_out[threadIdx.x] = total[threadIdx.x];
+        return;
+    }
+    if (threadIdx.x != 0) return;
+    const double alpha32 = irs_round_f32(alpha_fixed != nullptr ? *alpha_fixed : 1.0);
+    irs_gmm_adam_step(hyper, cfg, total, alpha32);
+    IrsGmm up;
+    irs_gmm_table(hyper + IRS_HYPER_LOG_STD, hyper + IRS_HYPER_LOGITS, cfg.K, up);
+    for (int k = 0; k < IRS_MAX_K; ++k) { table_out[k] = up.lw[k]; table_out[IRS_MAX_K + k] = up.prec[k]; }
+    stats_row[IRS_STAT_ALPHA] = alpha32;
+    stats_row[IRS_STAT_NLL_PRE] = total[IRS_SUM_NLL];
+}
+
+// pass B: lag-1 products of r along D, H, W; the last block combines them with pass A's sums: VD factor, Adam step
+__global__ void __launch_bounds__(256)
+gmm_stats_b_kernel(const float* __restrict__ r, double* __restrict__ hyper, IrsHyperCfg cfg,
+                   double* __restrict__ partials, unsigned int* __restrict__ counter, double* __restrict__ totals,
+                   double* __restrict__ stats_row, float* __restrict__ table_out, IrsDims d) {
+    __shared__ double sh[3 * 32];
+    __shared__ double total[3];
+    const int V = (int)d.V(), sy = d.W, sz = d.W * d.H;
+    float acc[3] = {0.f, 0.f, 0.f};
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < V; i += gridDim.x * blockDim.x) {
+        const float ri = r[i];
+        if (ri == 0.f) continue;   // off the mask (or an exactly zero residual): no contribution
+        const int x = i % d.W, y = (i / d.W) % d.H, zc = i / sz;
+        if (zc < d.D - 1) acc[0] += ri * __ldg(r + i + sz);
+        if (y < d.H - 1) acc[1] += ri * __ldg(r + i + sy);
+        if (x < d.W - 1) acc[2] += ri * __ldg(r + i + 1);
+    }
+    double blk[3];
+    irs_block_sum<3>(acc, blk, sh);
+    if (!irs_grid_sum<3>(blk, partials, counter, total)) return;
+    if (threadIdx.x != 0) return;
+    totals[IRS_SUM_RD] = total[0]; totals[IRS_SUM_RH] = total[1]; totals[IRS_SUM_RW] = total[2];
+    const double alpha32 = irs_round_f32(irs_vd_alpha(totals, cfg.n_mask));
+    irs_gmm_adam_step(hyper, cfg, totals, alpha32);
+    IrsGmm up;
+    irs_gmm_table(hyper + IRS_HYPER_LOG_STD, hyper + IRS_HYPER_LOGITS, cfg.K, up);
+    for (int k = 0; k < IRS_MAX_K; ++k) { table_out[k] = up.lw[k]; table_out[IRS_MAX_K + k] = up.prec[k]; }
+    stats_row[IRS_STAT_ALPHA] = alpha32;
+    stats_row[IRS_STAT_NLL_PRE] = totals[IRS_SUM_NLL];
+}
+
 // g_z = alpha_c z sum_k rho_k prec_k on the mask (dL/dz of alpha * NLL with the chain's UPDATED mixture), and the
 // data term alpha_c * NLL_c for logging
 __global__ void __launch_bounds__(256)
@@ -360,13 +464,21 @@ int irs_launch_lcc_bwd(const float* g_z, float g_sign, const float* a, const flo
     return launch_box<BOX_BWD_MEAN>(work, nullptr, nullptr, 1.f, g_im, nullptr, s, C, d, st);
 }
 
+// totals: IRS_SUM_COUNT doubles of scratch; r_scratch: V floats (needed when the VD factor is recomputed)
 int irs_launch_gmm_stats_step(const float* z, const unsigned char* mask, double* hyper, const IrsHyperCfg& cfg,
                               double* partials, unsigned int* counter, double* stats_row, float* table_out,
-                              const double* alpha_fixed, IrsDims d, cudaStream_t st) {
-    IrsGmm dummy;
-    dummy.K = cfg.K;
-    gmm_stats_kernel<0><<<irs_data_blocks(d), 256, 0, st>>>(z, mask, hyper, dummy, cfg, partials, counter, stats_row,
-                                                           table_out, nullptr, alpha_fixed, d);
+                              const double* alpha_fixed, float* r_scratch, double* totals, IrsDims d, cudaStream_t st) {
+    const int V = (int)d.V();
+    if (!cfg.virtual_decimation || alpha_fixed != nullptr) {
+        gmm_stats_a_kernel<true><<<irs_data_blocks(d), 256, 0, st>>>(z, mask, hyper, cfg, partials, counter, nullptr, nullptr,
+                                                                    stats_row, table_out, alpha_fixed, V);
+        return (int)cudaGetLastError();
+    }
+    if (!r_scratch || !totals) return IRS_ERR_BAD_ARG;
+    gmm_stats_a_kernel<false><<<irs_data_blocks(d), 256, 0, st>>>(z, mask, hyper, cfg, partials, counter, r_scratch, totals,
+                                                                 stats_row, table_out, nullptr, V);
+    gmm_stats_b_kernel<<<irs_data_blocks(d), 256, 0, st>>>(r_scratch, hyper, cfg, partials, counter, totals, stats_row,
+                                                          table_out, d);
     return (int)cudaGetLastError();
 }
 

@@ -75,7 +75,7 @@ int irs_launch_lcc_bwd(const float* g_z, float g_sign, const float* a, const flo
 int irs_data_blocks(IrsDims d);
 int irs_launch_gmm_stats_step(const float* z, const unsigned char* mask, double* hyper, const IrsHyperCfg& cfg,
                               double* partials, unsigned int* counter, double* stats_row, float* table_out,
-                              const double* alpha_fixed, IrsDims d, cudaStream_t st);
+                              const double* alpha_fixed, float* r_scratch, double* totals, IrsDims d, cudaStream_t st);
 int irs_launch_vd_alpha(const float* z, const unsigned char* mask, double* hyper, const IrsHyperCfg& cfg,
                         double* partials, unsigned int* counter, double* stats_row, IrsDims d, cudaStream_t st);
 int irs_launch_gmm_init_params(double* hyper, const double* moments, int K, cudaStream_t st);

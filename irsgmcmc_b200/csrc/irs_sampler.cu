@@ -94,7 +94,7 @@ extern "C" int irs_sgld_launches_per_step(const irs_sgld_config* c) {
     n += c->svf_steps;                           // scaling and squaring
     n += 1;                                      // warp
     n += c->data_term == IRS_DATA_LCC ? 2 : 1;   // LCC boxes / SSD residual
-    n += c->C;                                   // per-chain mixture statistics + Adam
+    n += c->C * (c->virtual_decimation ? 2 : 1); // per-chain mixture statistics (+ VD lag sums) + Adam
     n += 1;                                      // dL/dz
     n += c->data_term == IRS_DATA_LCC ? 2 : 0;   // LCC adjoint boxes
     n += 1;                                      // warp grid gradient
@@ -120,7 +120,8 @@ static int sgld_step_impl(const irs_sgld_config* cfg, const irs_sgld_buffers* b,
         !b->scratch1 || !b->field_a || !b->field_b || !b->grad_v || !b->maxabs || !b->hyper || !b->stats ||
         !b->gmm_table || !b->partials || !b->counters)
         return IRS_ERR_BAD_ARG;
-    if (cfg->data_term == IRS_DATA_LCC && (!b->lcc_a || !b->lcc_rs || !b->scratch2)) return IRS_ERR_BAD_ARG;
+    if (cfg->data_term == IRS_DATA_LCC && (!b->lcc_a || !b->lcc_rs)) return IRS_ERR_BAD_ARG;
+    if (!b->scratch2) return IRS_ERR_BAD_ARG;
 
     cudaStream_t st = (cudaStream_t)stream;
     const int C = cfg->C;
@@ -175,7 +176,8 @@ static int sgld_step_impl(const irs_sgld_config* cfg, const irs_sgld_buffers* b,
     for (int c = 0; c < C; ++c) {
         IRS_TRY(irs_launch_gmm_stats_step(b->z + (size_t)c * V, b->mask, b->hyper, hc, b->partials + c * per_chain,
                                           b->counters + c, b->stats + (size_t)c * IRS_STAT_SIZE,
-                                          b->gmm_table + (size_t)c * 16, nullptr, d, st));
+                                          b->gmm_table + (size_t)c * 16, nullptr, b->scratch2 + (size_t)c * V,
+                                          b->hyper + IRS_HYPER_SCRATCH, d, st));
     }
 
     mark(tm, st);
@@ -279,7 +281,7 @@ extern "C" int irs_sgld_gmm_init(const irs_sgld_config* cfg, const irs_sgld_buff
     IRS_TRY(irs_launch_vd_alpha(b->z, b->mask, b->hyper, hc, b->partials, b->counters, b->stats, d, st));
     for (int it = 0; it < n_warmup; ++it)
         IRS_TRY(irs_launch_gmm_stats_step(b->z, b->mask, b->hyper, hc, b->partials, b->counters, b->stats, b->gmm_table,
-                                          b->stats + IRS_STAT_ALPHA, d, st));
+                                          b->stats + IRS_STAT_ALPHA, nullptr, nullptr, d, st));
     return IRS_OK;
 }
 

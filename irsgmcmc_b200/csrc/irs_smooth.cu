@@ -37,26 +37,39 @@ langevin_kernel(const float* __restrict__ v, const float* __restrict__ sigma, lo
     oc[2 * V + i] = vc[2 * V + i] + coef * s2 * e[2];
 }
 
-// one axis of the separable smoothing: out(j) = sum_t w_t in(clamp(j + t - s))  (replicate padding).  n_fields = C*3
-template <int AXIS>
+// one axis of the separable smoothing: out(j) = sum_t w_t in(clamp(j + t - s))  (replicate padding).  grid.y = C*3 fields.
+// Interior voxels take a branch-free path with constant-stride loads; only the s voxels next to a face clamp indices.
+template <int AXIS, int NT>
 __global__ void __launch_bounds__(256)
 smooth_axis_kernel(const float* __restrict__ in, float* __restrict__ out, IrsTaps taps, IrsDims d) {
-    const long long V = d.V();
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int V = (int)d.V();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= V) return;
     const float* f = in + (size_t)blockIdx.y * V;
-    const int x = (int)(i % d.W), y = (int)((i / d.W) % d.H), z = (int)(i / ((long long)d.W * d.H));
-    const int s = (taps.n - 1) / 2;
     const int n = AXIS == 0 ? d.W : (AXIS == 1 ? d.H : d.D);
-    const int j = AXIS == 0 ? x : (AXIS == 1 ? y : z);
-    const long long stride = AXIS == 0 ? 1 : (AXIS == 1 ? d.W : (long long)d.W * d.H);
-    const long long base = i - (long long)j * stride;
+    const int stride = AXIS == 0 ? 1 : (AXIS == 1 ? d.W : d.W * d.H);
+    const int j = AXIS == 0 ? i % d.W : (AXIS == 1 ? (i / d.W) % d.H : i / (d.W * d.H));
+    constexpr int s = (NT - 1) / 2;
     float acc = 0.f;
-    for (int t = 0; t < taps.n; ++t) {
-        const int jj = irs_clampi(j + t - s, 0, n - 1);
-        acc += taps.w[t] * __ldg(f + base + (long long)jj * stride);
+    if (j >= s && j + s < n) {
+        const float* p = f + (i - s * stride);
+#pragma unroll
+        for (int t = 0; t < NT; ++t) acc += taps.w[t] * __ldg(p + t * stride);
+    } else {
+        const int base = i - j * stride;
+#pragma unroll
+        for (int t = 0; t < NT; ++t) acc += taps.w[t] * __ldg(f + base + irs_clampi(j + t - s, 0, n - 1) * stride);
     }
     out[(size_t)blockIdx.y * V + i] = acc;
+}
+
+template <int NT>
+static void launch_smooth3_nt(const float* in, float* work, float* out, const IrsTaps& taps, int C, IrsDims d,
+                              cudaStream_t st) {
+    dim3 grid((unsigned)((d.V() + 255) / 256), C * 3);
+    smooth_axis_kernel<2, NT><<<grid, 256, 0, st>>>(in, out, taps, d);
+    smooth_axis_kernel<1, NT><<<grid, 256, 0, st>>>(out, work, taps, d);
+    smooth_axis_kernel<0, NT><<<grid, 256, 0, st>>>(work, out, taps, d);
 }
 
 // energy of one chain: sum over 3 components x 3 axes of squared forward differences (last one counted twice)
@@ -212,10 +225,16 @@ int irs_launch_langevin(const float* v, const float* sigma, long long sigma_cs, 
 // in -> (z pass) out -> (y pass) work -> (x pass) out : the reference's order (utils/util.py:402-404)
 int irs_launch_smooth3(const float* in, float* work, float* out, const IrsTaps& taps, int C, IrsDims d,
                        cudaStream_t st) {
-    dim3 grid((unsigned)((d.V() + 255) / 256), C * 3);
-    smooth_axis_kernel<2><<<grid, 256, 0, st>>>(in, out, taps, d);
-    smooth_axis_kernel<1><<<grid, 256, 0, st>>>(out, work, taps, d);
-    smooth_axis_kernel<0><<<grid, 256, 0, st>>>(work, out, taps, d);
+    switch (taps.n) {
+        case 3: launch_smooth3_nt<3>(in, work, out, taps, C, d, st); break;
+        case 5: launch_smooth3_nt<5>(in, work, out, taps, C, d, st); break;
+        case 7: launch_smooth3_nt<7>(in, work, out, taps, C, d, st); break;
+        case 9: launch_smooth3_nt<9>(in, work, out, taps, C, d, st); break;
+        case 11: launch_smooth3_nt<11>(in, work, out, taps, C, d, st); break;
+        case 13: launch_smooth3_nt<13>(in, work, out, taps, C, d, st); break;
+        case 15: launch_smooth3_nt<15>(in, work, out, taps, C, d, st); break;
+        default: return IRS_ERR_UNSUPPORTED;
+    }
     return (int)cudaGetLastError();
 }
 
