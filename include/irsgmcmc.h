@@ -161,6 +161,8 @@ int irs_welford_std(const float* m2, double count, float* std_out, long long n, 
 #define IRS_HYPER_REG_M 52
 #define IRS_HYPER_REG_V 54
 #define IRS_HYPER_ITER 56        /* iteration counter: the Philox offset */
+#define IRS_HYPER_GMM_BETA_POW 57 /* beta1^t, beta2^t of the mixture optimiser (running products) */
+#define IRS_HYPER_REG_BETA_POW 59 /* same for the regulariser optimiser */
 #define IRS_HYPER_SCRATCH 64     /* 24 doubles of reduction scratch used inside a step */
 #define IRS_HYPER_SIZE 96
 

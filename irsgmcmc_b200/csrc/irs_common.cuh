@@ -258,28 +258,34 @@ __device__ __forceinline__ void irs_block_sum(const float* vals, double* out, do
     __syncthreads();
 }
 
-// Deterministic grid reduction: every block stores its NV partial sums, the last block to arrive adds them up in block
-// order.  Returns true (in ALL threads of that last block) when `total` (shared memory, NV doubles) is valid.
-// `partials` holds gridDim.x * NV doubles; `counter` is a zero-initialised uint that the last block resets.
+// Deterministic grid reduction: every block stores its NV partial sums, the last block to arrive adds them up in a
+// fixed order.  Returns true (in ALL threads of that last block) when `total` (shared memory, NV doubles) is valid.
+// `partials` holds NV * gridDim.x doubles laid out [value][block]; `counter` is a zero-initialised uint that the last
+// block resets.  Only the first `n_used` values are reduced.
 template <int NV>
 __device__ __forceinline__ bool irs_grid_sum(const double* block_vals, double* partials, unsigned int* counter,
-                                             double* total) {
+                                             double* total, int n_used = NV) {
     __shared__ bool is_last;
+    const unsigned int G = gridDim.x;
     if (threadIdx.x == 0) {
-        for (int i = 0; i < NV; ++i) partials[(size_t)blockIdx.x * NV + i] = block_vals[i];
+        for (int i = 0; i < n_used; ++i) partials[(size_t)i * G + blockIdx.x] = block_vals[i];
         __threadfence();
         unsigned int ticket = atomicAdd(counter, 1u);
-        is_last = (ticket == gridDim.x - 1);
+        is_last = (ticket == G - 1);
     }
     __syncthreads();
     if (!is_last) return false;
     __threadfence();
-    // NV values summed over gridDim.x blocks, fixed order per value: thread i < NV handles value i, strided by warps
-    for (int i = threadIdx.x >> 5; i < NV; i += (blockDim.x >> 5)) {
-        double s = 0.0;
-        for (unsigned int b = threadIdx.x & 31; b < gridDim.x; b += 32) s += partials[(size_t)b * NV + i];
-        s = irs_warp_sum(s);
-        if ((threadIdx.x & 31) == 0) total[i] = s;
+    // one warp per value, lanes stride over the blocks with four independent accumulators (fixed order -> deterministic)
+    const int lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    for (int i = threadIdx.x >> 5; i < n_used; i += nwarps) {
+        const double* p = partials + (size_t)i * G;
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+        unsigned int b = lane;
+        for (; b + 96 < G; b += 128) { s0 += p[b]; s1 += p[b + 32]; s2 += p[b + 64]; s3 += p[b + 96]; }
+        for (; b < G; b += 32) s0 += p[b];
+        double s = irs_warp_sum((s0 + s1) + (s2 + s3));
+        if (lane == 0) total[i] = s;
     }
     __syncthreads();
     if (threadIdx.x == 0) *counter = 0u;

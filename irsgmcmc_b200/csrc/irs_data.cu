@@ -24,12 +24,12 @@ __device__ __forceinline__ float adj_weight(int j, int o, int n, int S) {
 //   FWD_VAR  : in0 = a (pre: a^2), in1 = zF  -> out0 = rs = 1/sqrt(box/k^3 + 1e-10), out1 = z = zF - a rs  (zF null: a rs)
 //   BWD_VAR  : in0 = g, in1 = a, in2 = rs (pre: -g a rs^3 / 2) -> out0 = ga = g rs + 2 a adjbox/k^3        (g = sign * in0)
 //   BWD_MEAN : in0 = ga                      -> out0 = ga - adjbox/k^3
-template <int MODE>
+template <int MODE, int S>
 __global__ void __launch_bounds__(256)
 box_tile_kernel(const float* __restrict__ in0, const float* __restrict__ in1, const float* __restrict__ in2,
-                float sign, float* __restrict__ out0, float* __restrict__ out1, int S, IrsDims d) {
+                float sign, float* __restrict__ out0, float* __restrict__ out1, IrsDims d) {
     extern __shared__ float smem[];
-    const int EX = TX + 2 * S, EY = TY + 2 * S, EZ = TZ + 2 * S;
+    constexpr int EX = TX + 2 * S, EY = TY + 2 * S, EZ = TZ + 2 * S;
     float* A = smem;                 // EZ x EY x EX  (input tile; reused for the y-pass result EZ x TY x TX)
     float* B = smem + EZ * EY * EX;  // EZ x EY x TX  (x-pass result)
     constexpr bool BWD = (MODE == BOX_BWD_VAR || MODE == BOX_BWD_MEAN);
@@ -51,6 +51,7 @@ box_tile_kernel(const float* __restrict__ in0, const float* __restrict__ in1, co
     const float* p0 = in0 + off;
     const float* p1 = in1 ? in1 + off : nullptr;
     const float* p2 = in2 ? in2 + off : nullptr;
+#pragma unroll 3
     for (int row = warp; row < EZ * EY; row += 8) {
         const int tz = row / EY, ty = row - tz * EY;
         const int gz = z0 - S + tz, gy = y0 - S + ty;
@@ -91,25 +92,43 @@ box_tile_kernel(const float* __restrict__ in0, const float* __restrict__ in1, co
     }
     __syncthreads();
 
+    // adjoint: the fold weights differ from 1 only for outputs on a face of the volume
+    const bool fold_x = BWD && (x0 == 0 || x0 + TX >= d.W), fold_y = BWD && (y0 == 0 || y0 + TY >= d.H),
+               fold_z = BWD && (z0 == 0 || z0 + TZ >= d.D);
+
     // ---- x pass: B[tz][ty][x] = sum_o w A[tz][ty][x + S + o] ----
     {
         const int gx = x0 + lane;
+#pragma unroll 2
         for (int row = warp; row < EZ * EY; row += 8) {
             const float* a = A + row * EX + lane + S;
             float acc = 0.f;
-            for (int o = -S; o <= S; ++o) acc += (BWD ? adj_weight(gx, o, d.W, S) : 1.f) * a[o];
+            if (fold_x) {
+#pragma unroll
+                for (int o = -S; o <= S; ++o) acc += adj_weight(gx, o, d.W, S) * a[o];
+            } else {
+#pragma unroll
+                for (int o = -S; o <= S; ++o) acc += a[o];
+            }
             B[row * TX + lane] = acc;
         }
     }
     __syncthreads();
 
     // ---- y pass: A[tz][y][x] = sum_o w B[tz][y + S + o][x]   (A reused as EZ x TY x TX) ----
+#pragma unroll 2
     for (int row = warp; row < EZ * TY; row += 8) {
         const int tz = row / TY, ty = row % TY;
         const int gy = y0 + ty;
         const float* b = B + (tz * EY + ty + S) * TX + lane;
         float acc = 0.f;
-        for (int o = -S; o <= S; ++o) acc += (BWD ? adj_weight(gy, o, d.H, S) : 1.f) * b[o * TX];
+        if (fold_y) {
+#pragma unroll
+            for (int o = -S; o <= S; ++o) acc += adj_weight(gy, o, d.H, S) * b[o * TX];
+        } else {
+#pragma unroll
+            for (int o = -S; o <= S; ++o) acc += b[o * TX];
+        }
         A[row * TX + lane] = acc;
     }
     __syncthreads();
@@ -118,12 +137,19 @@ box_tile_kernel(const float* __restrict__ in0, const float* __restrict__ in1, co
     const int gx = x0 + lane, gy = y0 + warp;
     if (gx >= d.W || gy >= d.H) return;
     const float inv_k3 = 1.0f / (float)((2 * S + 1) * (2 * S + 1) * (2 * S + 1));
+#pragma unroll
     for (int tz = 0; tz < TZ; ++tz) {
         const int gz = z0 + tz;
         if (gz >= d.D) break;
         const float* a = A + ((tz + S) * TY + warp) * TX + lane;
         float acc = 0.f;
-        for (int o = -S; o <= S; ++o) acc += (BWD ? adj_weight(gz, o, d.D, S) : 1.f) * a[o * TY * TX];
+        if (fold_z) {
+#pragma unroll
+            for (int o = -S; o <= S; ++o) acc += adj_weight(gz, o, d.D, S) * a[o * TY * TX];
+        } else {
+#pragma unroll
+            for (int o = -S; o <= S; ++o) acc += a[o * TY * TX];
+        }
         const float box = acc * inv_k3;
         const size_t gi = off + ((size_t)gz * d.H + gy) * d.W + gx;
         if (MODE == BOX_FWD_MEAN) {
@@ -141,22 +167,32 @@ box_tile_kernel(const float* __restrict__ in0, const float* __restrict__ in1, co
     }
 }
 
-template <int MODE>
-int launch_box(const float* in0, const float* in1, const float* in2, float sign, float* out0, float* out1, int S, int C,
-               IrsDims d, cudaStream_t st) {
-    const int EX = TX + 2 * S, EY = TY + 2 * S, EZ = TZ + 2 * S;
-    const size_t smem = sizeof(float) * ((size_t)EZ * EY * EX + (size_t)EZ * EY * TX);
+template <int MODE, int S>
+int launch_box_s(const float* in0, const float* in1, const float* in2, float sign, float* out0, float* out1, int C,
+                 IrsDims d, cudaStream_t st) {
+    constexpr int EX = TX + 2 * S, EY = TY + 2 * S, EZ = TZ + 2 * S;
+    constexpr size_t smem = sizeof(float) * ((size_t)EZ * EY * EX + (size_t)EZ * EY * TX);
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(box_tile_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(box_tile_kernel<MODE, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
         configured = true;
     }
-    if (smem > 96 * 1024) return IRS_ERR_UNSUPPORTED;
     const int tiles = ((d.W + TX - 1) / TX) * ((d.H + TY - 1) / TY) * ((d.D + TZ - 1) / TZ);
     dim3 grid(tiles, C);
-    box_tile_kernel<MODE><<<grid, 256, smem, st>>>(in0, in1, in2, sign, out0, out1, S, d);
+    box_tile_kernel<MODE, S><<<grid, 256, smem, st>>>(in0, in1, in2, sign, out0, out1, d);
     return (int)cudaGetLastError();
+}
+
+template <int MODE>
+int launch_box(const float* in0, const float* in1, const float* in2, float sign, float* out0, float* out1, int S, int C,
+               IrsDims d, cudaStream_t st) {
+    switch (S) {
+        case 1: return launch_box_s<MODE, 1>(in0, in1, in2, sign, out0, out1, C, d, st);
+        case 2: return launch_box_s<MODE, 2>(in0, in1, in2, sign, out0, out1, C, d, st);
+        case 3: return launch_box_s<MODE, 3>(in0, in1, in2, sign, out0, out1, C, d, st);
+        default: return IRS_ERR_UNSUPPORTED;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -449,7 +485,7 @@ masked_moments_kernel(const float* __restrict__ z, const unsigned char* __restri
 
 int irs_data_blocks(IrsDims d) {
     long long b = (d.V() + 255) / 256;
-    return (int)(b < 1184 ? b : 1184);  // 8 CTAs per SM x 148 SMs
+    return (int)(b < 592 ? b : 592);  // 4 CTAs per SM x 148 SMs: enough loads in flight, short final reduction
 }
 
 int irs_launch_lcc_fwd(const float* im, const float* zF, int s, float* a, float* rs, float* z, int C, IrsDims d,

@@ -28,45 +28,66 @@ struct IrsHyperCfg {
 
 IRS_HD double irs_round_f32(double x) { return (double)(float)x; }
 
+// The mixture parameters, their Adam moments and the VD factor are fp32 tensors in the reference, and this code runs
+// on ONE thread at the end of a reduction kernel: everything transcendental is done in fp32 (a chain of fp64 exp / log
+// / pow calls costs tens of microseconds of pure latency); only the differences of the large fp64 sums stay in fp64.
+
 // log pi = log_softmax(logits + 1e-2)   (reference model/loss.py:67-69)
-IRS_HD void irs_log_proportions(const double* logits, int K, double* logpi) {
-    double m = -1e300;
-    for (int k = 0; k < K; ++k) m = fmax(m, logits[k] + 1e-2);
-    double s = 0.0;
-    for (int k = 0; k < K; ++k) s += exp(logits[k] + 1e-2 - m);
-    const double lse = m + log(s);
-    for (int k = 0; k < K; ++k) logpi[k] = logits[k] + 1e-2 - lse;
+IRS_HD void irs_log_proportions(const double* logits, int K, float* logpi) {
+    float m = -INFINITY;
+    for (int k = 0; k < K; ++k) m = fmaxf(m, (float)logits[k] + 1e-2f);
+    float s = 0.f;
+    for (int k = 0; k < K; ++k) s += expf((float)logits[k] + 1e-2f - m);
+    const float lse = m + logf(s);
+    for (int k = 0; k < K; ++k) logpi[k] = (float)logits[k] + 1e-2f - lse;
 }
 
 IRS_HD void irs_gmm_table(const double* log_std, const double* logits, int K, IrsGmm& g) {
-    double logpi[IRS_MAX_K];
+    float logpi[IRS_MAX_K];
     irs_log_proportions(logits, K, logpi);
     g.K = K;
     for (int k = 0; k < IRS_MAX_K; ++k) {
-        g.lw[k] = k < K ? (float)(logpi[k] - log_std[k]) : -INFINITY;
-        g.prec[k] = k < K ? (float)exp(-2.0 * log_std[k]) : 0.f;
+        g.lw[k] = k < K ? logpi[k] - (float)log_std[k] : -INFINITY;
+        g.prec[k] = k < K ? expf(-2.0f * (float)log_std[k]) : 0.f;
     }
 }
 
 // reference utils/util.py:446-485.  NaN when a lag-1 correlation is <= 0, like the reference.
 IRS_HD double irs_vd_alpha(const double* sums, double n_mask) {
     const double var = sums[IRS_SUM_RR] / n_mask;
-    double prod = 1.0;
+    float prod = 1.f;
     for (int a = 0; a < 3; ++a) {
-        const double corr = (sums[IRS_SUM_RD + a] / n_mask) / var;
-        prod *= fmin(1.0, -2.0 / 3.14159265358979323846 * log(corr));
+        const float corr = (float)((sums[IRS_SUM_RD + a] / n_mask) / var);
+        prod *= fminf(1.f, -0.63661977236758134f * logf(corr));
     }
-    return sqrt(prod);
+    return (double)sqrtf(prod);
 }
 
+// one Adam update of a scalar parameter.  f32: the parameter and its moments are fp32 tensors in the reference
+// (optimizers/adam_rate_decay.py:86-97: sqrt(v) / sqrt(bc2) + eps ;  p -= (clr / bc1) * m / denom)
 IRS_HD void irs_adam_update(double& p, double& m, double& v, double g, double lr, double decay, double bc1, double bc2,
                             double b1, double b2, double eps, bool f32) {
+    if (f32) {
+        const float gf = (float)g;
+        const float mf = (float)b1 * (float)m + (float)(1.0 - b1) * gf;
+        const float vf = (float)b2 * (float)v + (float)(1.0 - b2) * gf * gf;
+        const float denom = sqrtf(vf) / (float)sqrt(bc2) + (float)eps;
+        const float step = (float)((lr / decay) / bc1);
+        m = (double)mf; v = (double)vf;
+        p = (double)((float)p - step * (mf / denom));
+        return;
+    }
     m = b1 * m + (1.0 - b1) * g;
     v = b2 * v + (1.0 - b2) * g * g;
-    if (f32) { m = irs_round_f32(m); v = irs_round_f32(v); }
     const double denom = sqrt(v) / sqrt(bc2) + eps;
     p -= (lr / decay) / bc1 * (m / denom);
-    if (f32) p = irs_round_f32(p);
+}
+
+// bias corrections 1 - beta^t without pow(): beta^t is kept as a running product next to the step counter
+IRS_HD void irs_adam_bias(double* beta_pow, double b1, double b2, double step_before, double& bc1, double& bc2) {
+    if (step_before == 0.0) { beta_pow[0] = 1.0; beta_pow[1] = 1.0; }
+    beta_pow[0] *= b1; beta_pow[1] *= b2;
+    bc1 = 1.0 - beta_pow[0]; bc2 = 1.0 - beta_pow[1];
 }
 
 // One Adam step on (log_std, logits) with loss  alpha * NLL - sum_k logN(log_std_k; loc, scale) - logDir(log pi; a)
@@ -75,73 +96,82 @@ IRS_HD void irs_gmm_adam_step(double* hyper, const IrsHyperCfg& cfg, const doubl
     const int K = cfg.K;
     double* ls = hyper + IRS_HYPER_LOG_STD;
     double* lg = hyper + IRS_HYPER_LOGITS;
-    double logpi[IRS_MAX_K], g_ls[IRS_MAX_K], g_lg[IRS_MAX_K];
+    float logpi[IRS_MAX_K];
+    double g_ls[IRS_MAX_K], g_lg[IRS_MAX_K];
     irs_log_proportions(lg, K, logpi);
     double rho_total = 0.0;
     for (int k = 0; k < K; ++k) rho_total += sums[IRS_SUM_RHO + k];
+    const double inv_s2 = 1.0 / (cfg.gmm_prior_scale * cfg.gmm_prior_scale);
     for (int k = 0; k < K; ++k) {
-        const double pi_k = exp(logpi[k]);
-        const double s2 = cfg.gmm_prior_scale * cfg.gmm_prior_scale;
-        g_ls[k] = alpha * (sums[IRS_SUM_RHO + k] - sums[IRS_SUM_Q + k]) + (ls[k] - cfg.gmm_prior_loc) / s2;
+        const double pi_k = (double)expf(logpi[k]);
+        g_ls[k] = alpha * (sums[IRS_SUM_RHO + k] - sums[IRS_SUM_Q + k]) + (ls[k] - cfg.gmm_prior_loc) * inv_s2;
         g_lg[k] = alpha * (-sums[IRS_SUM_RHO + k] + pi_k * rho_total) - (cfg.dirichlet_alpha - 1.0) * (1.0 - K * pi_k);
     }
     const double step0 = hyper[IRS_HYPER_GMM_STEP];
     const double decay = 1.0 + step0 * cfg.lr_decay;
-    const double step = step0 + 1.0;
-    const double bc1 = 1.0 - pow(cfg.beta1, step), bc2 = 1.0 - pow(cfg.beta2, step);
+    double bc1, bc2;
+    irs_adam_bias(hyper + IRS_HYPER_GMM_BETA_POW, cfg.beta1, cfg.beta2, step0, bc1, bc2);
     for (int k = 0; k < K; ++k) {
-        irs_adam_update(ls[k], hyper[IRS_HYPER_M_LOG_STD + k], hyper[IRS_HYPER_V_LOG_STD + k], irs_round_f32(g_ls[k]),
+        irs_adam_update(ls[k], hyper[IRS_HYPER_M_LOG_STD + k], hyper[IRS_HYPER_V_LOG_STD + k], g_ls[k],
                         cfg.lr_log_std, decay, bc1, bc2, cfg.beta1, cfg.beta2, cfg.eps, true);
-        irs_adam_update(lg[k], hyper[IRS_HYPER_M_LOGITS + k], hyper[IRS_HYPER_V_LOGITS + k], irs_round_f32(g_lg[k]),
+        irs_adam_update(lg[k], hyper[IRS_HYPER_M_LOGITS + k], hyper[IRS_HYPER_V_LOGITS + k], g_lg[k],
                         cfg.lr_logits, decay, bc1, bc2, cfg.beta1, cfg.beta2, cfg.eps, true);
     }
-    hyper[IRS_HYPER_GMM_STEP] = step;
+    hyper[IRS_HYPER_GMM_STEP] = step0 + 1.0;
 }
 
 // Regulariser: per-chain loss value, the coefficient c_c = dL/dy_c that multiplies dE/dv in the field gradient, and one
 // Adam step on the hyper-parameters (reference model/loss.py:197-198,264-312; trainer/trainer.py:334-339,353-354).
 // With the ExpGamma hyper-prior on log y the two dof/(2y) terms cancel exactly; the simplified
 // form is evaluated so that no 3e6-sized fp terms are subtracted.
-IRS_HD void irs_reg_hyper_step(double* hyper, const IrsHyperCfg& cfg, int C, double* stats) {
-    double g0 = 0.0, g1 = 0.0;
+// per-chain part: loss value, field-gradient coefficient, contributions to the hyper-parameter gradients
+IRS_HD void irs_reg_chain_terms(const double* hyper, const IrsHyperCfg& cfg, double* st, double& g0, double& g1) {
+    const double y = st[IRS_STAT_ENERGY];
     if (cfg.reg_type == IRS_REG_LOGNORMAL) {
         const double loc = hyper[IRS_HYPER_REG_P], log_scale = hyper[IRS_HYPER_REG_P + 1];
         const double scale = exp(log_scale), s2 = scale * scale;
-        for (int c = 0; c < C; ++c) {
-            double* st = stats + (size_t)c * IRS_STAT_SIZE;
-            const double y = st[IRS_STAT_ENERGY], ly = log(y), r = ly - loc;
-            st[IRS_STAT_REG] = ly + log_scale + 0.5 * r * r / s2 + (0.5 * cfg.dof - 1.0) * ly;
-            st[IRS_STAT_REG_COEF] = cfg.reg_learnable ? 0.5 * cfg.w_reg + r / (s2 * y)
-                                                      : (r / s2 + 0.5 * cfg.dof) / y;
-            g0 += -r / s2;
-            g1 += 1.0 - r * r / s2;
-        }
-        if (cfg.reg_learnable) {
-            g1 += (log_scale - cfg.reg_prior_loc) / (cfg.reg_prior_scale * cfg.reg_prior_scale);
-            const double step0 = hyper[IRS_HYPER_REG_STEP], decay = 1.0 + step0 * cfg.lr_decay, step = step0 + 1.0;
-            const double bc1 = 1.0 - pow(cfg.beta1, step), bc2 = 1.0 - pow(cfg.beta2, step);
-            irs_adam_update(hyper[IRS_HYPER_REG_P], hyper[IRS_HYPER_REG_M], hyper[IRS_HYPER_REG_V], g0, cfg.lr_reg0,
-                            decay, bc1, bc2, cfg.beta1, cfg.beta2, cfg.eps, false);
-            irs_adam_update(hyper[IRS_HYPER_REG_P + 1], hyper[IRS_HYPER_REG_M + 1], hyper[IRS_HYPER_REG_V + 1], g1,
-                            cfg.lr_reg1, decay, bc1, bc2, cfg.beta1, cfg.beta2, cfg.eps, false);
-            hyper[IRS_HYPER_REG_STEP] = step;
-        }
+        const double ly = log(y), r = ly - loc;
+        st[IRS_STAT_REG] = ly + log_scale + 0.5 * r * r / s2 + (0.5 * cfg.dof - 1.0) * ly;
+        st[IRS_STAT_REG_COEF] = cfg.reg_learnable ? 0.5 * cfg.w_reg + r / (s2 * y) : (r / s2 + 0.5 * cfg.dof) / y;
+        g0 = -r / s2;
+        g1 = 1.0 - r * r / s2;
     } else {
         const double lw = hyper[IRS_HYPER_REG_P], w = exp(lw);
-        for (int c = 0; c < C; ++c) {
-            double* st = stats + (size_t)c * IRS_STAT_SIZE;
-            const double y = st[IRS_STAT_ENERGY];
-            st[IRS_STAT_REG] = 0.5 * w * y - 0.5 * cfg.dof * lw;
-            st[IRS_STAT_REG_COEF] = 0.5 * w;
-            g0 += 0.5 * w * y - 0.5 * cfg.dof;
-        }
-        if (cfg.reg_learnable) {
-            g0 += -(cfg.w_reg_prior_shape - cfg.w_reg_prior_rate * w);
-            const double step0 = hyper[IRS_HYPER_REG_STEP], decay = 1.0 + step0 * cfg.lr_decay, step = step0 + 1.0;
-            const double bc1 = 1.0 - pow(cfg.beta1, step), bc2 = 1.0 - pow(cfg.beta2, step);
-            irs_adam_update(hyper[IRS_HYPER_REG_P], hyper[IRS_HYPER_REG_M], hyper[IRS_HYPER_REG_V], irs_round_f32(g0),
-                            cfg.lr_reg0, decay, bc1, bc2, cfg.beta1, cfg.beta2, cfg.eps, true);
-            hyper[IRS_HYPER_REG_STEP] = step;
-        }
+        st[IRS_STAT_REG] = 0.5 * w * y - 0.5 * cfg.dof * lw;
+        st[IRS_STAT_REG_COEF] = 0.5 * w;
+        g0 = 0.5 * w * y - 0.5 * cfg.dof;
+        g1 = 0.0;
     }
+}
+
+// hyper-prior gradients + one Adam step, given the chain-summed gradients
+IRS_HD void irs_reg_adam(double* hyper, const IrsHyperCfg& cfg, double g0, double g1) {
+    if (!cfg.reg_learnable) return;
+    const double step0 = hyper[IRS_HYPER_REG_STEP], decay = 1.0 + step0 * cfg.lr_decay;
+    double bc1, bc2;
+    irs_adam_bias(hyper + IRS_HYPER_REG_BETA_POW, cfg.beta1, cfg.beta2, step0, bc1, bc2);
+    if (cfg.reg_type == IRS_REG_LOGNORMAL) {
+        g1 += (hyper[IRS_HYPER_REG_P + 1] - cfg.reg_prior_loc) / (cfg.reg_prior_scale * cfg.reg_prior_scale);
+        irs_adam_update(hyper[IRS_HYPER_REG_P], hyper[IRS_HYPER_REG_M], hyper[IRS_HYPER_REG_V], g0, cfg.lr_reg0, decay,
+                        bc1, bc2, cfg.beta1, cfg.beta2, cfg.eps, false);
+        irs_adam_update(hyper[IRS_HYPER_REG_P + 1], hyper[IRS_HYPER_REG_M + 1], hyper[IRS_HYPER_REG_V + 1], g1,
+                        cfg.lr_reg1, decay, bc1, bc2, cfg.beta1, cfg.beta2, cfg.eps, false);
+    } else {
+        const double w = exp(hyper[IRS_HYPER_REG_P]);
+        g0 += -(cfg.w_reg_prior_shape - cfg.w_reg_prior_rate * w);
+        irs_adam_update(hyper[IRS_HYPER_REG_P], hyper[IRS_HYPER_REG_M], hyper[IRS_HYPER_REG_V], irs_round_f32(g0),
+                        cfg.lr_reg0, decay, bc1, bc2, cfg.beta1, cfg.beta2, cfg.eps, true);
+    }
+    hyper[IRS_HYPER_REG_STEP] = step0 + 1.0;
+}
+
+// serial composition (host emulation; the device kernel spreads the chains over threads)
+IRS_HD void irs_reg_hyper_step(double* hyper, const IrsHyperCfg& cfg, int C, double* stats) {
+    double g0 = 0.0, g1 = 0.0;
+    for (int c = 0; c < C; ++c) {
+        double a, b;
+        irs_reg_chain_terms(hyper, cfg, stats + (size_t)c * IRS_STAT_SIZE, a, b);
+        g0 += a; g1 += b;
+    }
+    irs_reg_adam(hyper, cfg, g0, g1);
 }

@@ -18,9 +18,20 @@ ssd_residual_kernel(const float* __restrict__ fixed, const float* __restrict__ w
 }
 
 // regulariser loss / coefficient / Adam step for all chains, then advance the Philox offset
-__global__ void reg_hyper_kernel(double* hyper, IrsHyperCfg cfg, int C, double* stats) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    irs_reg_hyper_step(hyper, cfg, C, stats);
+__global__ void __launch_bounds__(128) reg_hyper_kernel(double* hyper, IrsHyperCfg cfg, int C, double* stats) {
+    __shared__ double s0[128], s1[128];
+    double g0 = 0.0, g1 = 0.0;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {   // chains in parallel: each needs a log / exp in fp64
+        double a, b;
+        irs_reg_chain_terms(hyper, cfg, stats + (size_t)c * IRS_STAT_SIZE, a, b);
+        g0 += a; g1 += b;
+    }
+    s0[threadIdx.x] = g0; s1[threadIdx.x] = g1;
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    g0 = 0.0; g1 = 0.0;
+    for (int t = 0; t < blockDim.x; ++t) { g0 += s0[t]; g1 += s1[t]; }   // fixed order: deterministic
+    irs_reg_adam(hyper, cfg, g0, g1);
     hyper[IRS_HYPER_ITER] += 1.0;
 }
 
@@ -99,7 +110,7 @@ extern "C" int irs_sgld_launches_per_step(const irs_sgld_config* c) {
     n += c->data_term == IRS_DATA_LCC ? 2 : 0;   // LCC adjoint boxes
     n += 1;                                      // warp grid gradient
     n += 1;                                      // regulariser hyper step
-    n += 2 * c->svf_steps;                       // SVF adjoint (gather + large-displacement scatter)
+    n += 2 * c->svf_steps;                       // SVF adjoint (tiled gather + large-displacement scatter, early exit)
     n += 1;                                      // regulariser gradient + SGD update
     return n;
 }
@@ -198,7 +209,7 @@ static int sgld_step_impl(const irs_sgld_config* cfg, const irs_sgld_buffers* b,
 
     mark(tm, st);
     // (9) regulariser loss, coefficient and hyper-parameter Adam step              trainer.py:311,334-339,353-354
-    reg_hyper_kernel<<<1, 32, 0, st>>>(b->hyper, hc, C, b->stats);
+    reg_hyper_kernel<<<1, 128, 0, st>>>(b->hyper, hc, C, b->stats);
     IRS_LAUNCH_CHECK();
 
     mark(tm, st);

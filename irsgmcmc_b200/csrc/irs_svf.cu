@@ -41,20 +41,6 @@ svf_step_fwd_kernel(const float* __restrict__ in, float in_scale, float* __restr
     }
 }
 
-// large-displacement regime (R > radius_max): direct + position terms; the scatter kernel then adds the transpose
-__global__ void __launch_bounds__(256)
-svf_step_bwd_scatter_pre_kernel(const float* __restrict__ in, float in_scale, const float* __restrict__ gp_all,
-                                float* __restrict__ g_all, const float* __restrict__ maxabs, int radius_max,
-                                float out_scale, IrsDims d) {
-    const int R = (int)floorf(__ldg(maxabs)) + 1;
-    if (R <= radius_max) return;
-    const long long V = d.V();
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= V) return;
-    const size_t off = (size_t)blockIdx.y * 3 * V;
-    irs_body_svf_bwd(in + off, in_scale, gp_all + off, g_all + off, -1, out_scale, V, i, d);
-}
-
 // exact scatter form of the interpolation transpose for steps whose displacement exceeds the gather window
 __global__ void __launch_bounds__(256)
 svf_step_bwd_scatter_kernel(const float* __restrict__ in, float in_scale, const float* __restrict__ gp_all,
@@ -378,13 +364,12 @@ __device__ __forceinline__ void svf_bwd_tile_body(const float* __restrict__ u, f
     }
 }
 
-__global__ void __launch_bounds__(TILE_T)
+__global__ void __launch_bounds__(TILE_T, 4)
 svf_step_bwd_tile_kernel(const float* __restrict__ in, float in_scale, const float* __restrict__ gp_all,
                          float* __restrict__ g_all, const float* __restrict__ maxabs, int radius_max, float out_scale,
                          int seg_len, IrsDims d) {
     extern __shared__ float smem[];
     const int R = (int)floorf(__ldg(maxabs)) + 1;
-    if (R > radius_max) return;  // the scatter kernels own this step
     const long long V = d.V();
     const size_t off = (size_t)blockIdx.y * 3 * V;
     const int tiles_x = (d.W + TILE_X - 1) / TILE_X, tiles_y = (d.H + TILE_Y - 1) / TILE_Y;
@@ -395,16 +380,17 @@ svf_step_bwd_tile_kernel(const float* __restrict__ in, float in_scale, const flo
         return x0t - 2 * Rr >= 0 && x0t + TILE_X - 1 + 2 * Rr <= d.W - 1 && y0t - 2 * Rr >= 0 &&
                y0t + TILE_Y - 1 + 2 * Rr <= d.H - 1 && zs - 2 * Rr >= 0 && ze - 1 + 2 * Rr <= d.D - 1;
     };
-    if (R == 1) {
+    if (R <= radius_max && R == 1) {
         if (interior(1)) svf_bwd_tile_body<1, false>(in + off, in_scale, gp_all + off, g_all + off, out_scale, d, x0t, y0t, zs, ze, smem);
         else svf_bwd_tile_body<1, true>(in + off, in_scale, gp_all + off, g_all + off, out_scale, d, x0t, y0t, zs, ze, smem);
-    } else if (R == 2) {
+    } else if (R <= radius_max && R == 2) {
         svf_bwd_tile_body<2, true>(in + off, in_scale, gp_all + off, g_all + off, out_scale, d, x0t, y0t, zs, ze, smem);
-    } else {  // rare: wide gather straight from global memory
+    } else {  // rare: wide gather straight from global memory; beyond radius_max only the direct + position terms
+              // (the scatter kernel that follows adds the interpolation transpose with atomics)
         const int x = x0t + (threadIdx.x % TILE_X), y = y0t + (threadIdx.x / TILE_X);
         if (x >= d.W || y >= d.H) return;
         for (int z = zs; z < ze; ++z)
-            irs_body_svf_bwd(in + off, in_scale, gp_all + off, g_all + off, R, out_scale, V,
+            irs_body_svf_bwd(in + off, in_scale, gp_all + off, g_all + off, R <= radius_max ? R : -1, out_scale, V,
                              ((long long)z * d.H + y) * d.W + x, d);
     }
 }
@@ -513,8 +499,6 @@ int irs_launch_svf_bwd(const float* v, const float* hist, const float* maxabs, f
         const float in_scale = (k == 0) ? scale0 : 1.0f;
         svf_step_bwd_tile_kernel<<<tgrid, TILE_T, smem, st>>>(in, in_scale, gp, out, maxabs + k, gather_radius_max,
                                                                   in_scale, seg_len, d);
-        svf_step_bwd_scatter_pre_kernel<<<vgrid, 256, 0, st>>>(in, in_scale, gp, out, maxabs + k, gather_radius_max,
-                                                               in_scale, d);
         svf_step_bwd_scatter_kernel<<<vgrid, 256, 0, st>>>(in, in_scale, gp, out, maxabs + k, gather_radius_max,
                                                            in_scale, d);
         gp = out;
