@@ -289,23 +289,39 @@ gmm_stats_a_kernel(const float* __restrict__ z, const unsigned char* __restrict_
     float acc[IRS_SUM_COUNT];
 #pragma unroll
     for (int k = 0; k < IRS_SUM_COUNT; ++k) acc[k] = 0.f;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < V; i += gridDim.x * blockDim.x) {
-        float r = 0.f;
-        if (mask[i]) {
-            const float zi = z[i];
-            float rho[IRS_MAX_K], wp;
-            const float lp = irs_gmm_eval(gl, zi, rho, wp);
-            const float z2 = zi * zi;
-            r = z2 * wp;
-            acc[IRS_SUM_NLL] -= lp;
-            acc[IRS_SUM_RR] += r * r;
+    auto one = [&](float zi) {
+        float rho[IRS_MAX_K], wp;
+        const float lp = irs_gmm_eval(gl, zi, rho, wp);
+        const float z2 = zi * zi, r = z2 * wp;
+        acc[IRS_SUM_NLL] -= lp;
+        acc[IRS_SUM_RR] += r * r;
 #pragma unroll
-            for (int k = 0; k < IRS_MAX_K; ++k) if (k < gl.K) {
-                acc[IRS_SUM_RHO + k] += rho[k];
-                acc[IRS_SUM_Q + k] += rho[k] * z2 * gl.prec[k];
-            }
+        for (int k = 0; k < IRS_MAX_K; ++k) if (k < gl.K) {
+            acc[IRS_SUM_RHO + k] += rho[k];
+            acc[IRS_SUM_Q + k] += rho[k] * z2 * gl.prec[k];
         }
-        if (!FINALIZE) r_out[i] = r;
+        return r;
+    };
+    const bool vec = (V % 4 == 0) && ((reinterpret_cast<uintptr_t>(z) | reinterpret_cast<uintptr_t>(mask) |
+                                       reinterpret_cast<uintptr_t>(r_out)) & 15) == 0;
+    if (vec) {   // 128-bit loads, four voxels per thread and iteration
+        for (int i = (blockIdx.x * blockDim.x + threadIdx.x) * 4; i < V; i += gridDim.x * blockDim.x * 4) {
+            const uchar4 m4 = *reinterpret_cast<const uchar4*>(mask + i);
+            float4 r4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (m4.x | m4.y | m4.z | m4.w) {
+                const float4 z4 = __ldg(reinterpret_cast<const float4*>(z + i));
+                if (m4.x) r4.x = one(z4.x);
+                if (m4.y) r4.y = one(z4.y);
+                if (m4.z) r4.z = one(z4.z);
+                if (m4.w) r4.w = one(z4.w);
+            }
+            if (!FINALIZE) *reinterpret_cast<float4*>(r_out + i) = r4;
+        }
+    } else {
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < V; i += gridDim.x * blockDim.x) {
+            const float r = mask[i] ? one(z[i]) : 0.f;
+            if (!FINALIZE) r_out[i] = r;
+        }
     }
     double blk[IRS_SUM_COUNT];
     irs_block_sum<IRS_SUM_COUNT>(acc, blk, sh);
@@ -333,13 +349,31 @@ gmm_stats_b_kernel(const float* __restrict__ r, double* __restrict__ hyper, IrsH
     __shared__ double total[3];
     const int V = (int)d.V(), sy = d.W, sz = d.W * d.H;
     float acc[3] = {0.f, 0.f, 0.f};
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < V; i += gridDim.x * blockDim.x) {
-        const float ri = r[i];
-        if (ri == 0.f) continue;   // off the mask (or an exactly zero residual): no contribution
-        const int x = i % d.W, y = (i / d.W) % d.H, zc = i / sz;
-        if (zc < d.D - 1) acc[0] += ri * __ldg(r + i + sz);
-        if (y < d.H - 1) acc[1] += ri * __ldg(r + i + sy);
-        if (x < d.W - 1) acc[2] += ri * __ldg(r + i + 1);
+    if (d.W % 4 == 0 && (reinterpret_cast<uintptr_t>(r) & 15) == 0) {
+        for (int i = (blockIdx.x * blockDim.x + threadIdx.x) * 4; i < V; i += gridDim.x * blockDim.x * 4) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(r + i));
+            if (a.x == 0.f && a.y == 0.f && a.z == 0.f && a.w == 0.f) continue;   // off the mask: no contribution
+            const int x = i % d.W, y = (i / d.W) % d.H, zc = i / sz;
+            if (zc < d.D - 1) {
+                const float4 b = __ldg(reinterpret_cast<const float4*>(r + i + sz));
+                acc[0] += a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w;
+            }
+            if (y < d.H - 1) {
+                const float4 b = __ldg(reinterpret_cast<const float4*>(r + i + sy));
+                acc[1] += a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w;
+            }
+            const float nx = x + 4 < d.W ? __ldg(r + i + 4) : 0.f;
+            acc[2] += a.x * a.y + a.y * a.z + a.z * a.w + a.w * nx;
+        }
+    } else {
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < V; i += gridDim.x * blockDim.x) {
+            const float ri = r[i];
+            if (ri == 0.f) continue;   // off the mask (or an exactly zero residual): no contribution
+            const int x = i % d.W, y = (i / d.W) % d.H, zc = i / sz;
+            if (zc < d.D - 1) acc[0] += ri * __ldg(r + i + sz);
+            if (y < d.H - 1) acc[1] += ri * __ldg(r + i + sy);
+            if (x < d.W - 1) acc[2] += ri * __ldg(r + i + 1);
+        }
     }
     double blk[3];
     irs_block_sum<3>(acc, blk, sh);
@@ -373,15 +407,27 @@ gmm_grad_kernel(const float* __restrict__ z_all, const unsigned char* __restrict
     const float* z = z_all + (size_t)c * V;
     float* go = g_all + (size_t)c * V;
     float nll = 0.f;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < V; i += (long long)gridDim.x * blockDim.x) {
-        float gz = 0.f;
-        if (mask[i]) {
-            float rho[IRS_MAX_K], wp;
-            const float zi = z[i];
-            nll -= irs_gmm_eval(g, zi, rho, wp);
-            gz = alpha * zi * wp;
+    auto one = [&](float zi) {
+        float rho[IRS_MAX_K], wp;
+        nll -= irs_gmm_eval(g, zi, rho, wp);
+        return alpha * zi * wp;
+    };
+    if (V % 4 == 0 && ((reinterpret_cast<uintptr_t>(z) | reinterpret_cast<uintptr_t>(mask) | reinterpret_cast<uintptr_t>(go)) & 15) == 0) {
+        for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < V; i += (long long)gridDim.x * blockDim.x * 4) {
+            const uchar4 m4 = *reinterpret_cast<const uchar4*>(mask + i);
+            float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (m4.x | m4.y | m4.z | m4.w) {
+                const float4 z4 = __ldg(reinterpret_cast<const float4*>(z + i));
+                if (m4.x) g4.x = one(z4.x);
+                if (m4.y) g4.y = one(z4.y);
+                if (m4.z) g4.z = one(z4.z);
+                if (m4.w) g4.w = one(z4.w);
+            }
+            *reinterpret_cast<float4*>(go + i) = g4;
         }
-        go[i] = gz;
+    } else {
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < V; i += (long long)gridDim.x * blockDim.x)
+            go[i] = mask[i] ? one(z[i]) : 0.f;
     }
     double blk[1];
     irs_block_sum<1>(&nll, blk, sh);

@@ -72,6 +72,184 @@ static void launch_smooth3_nt(const float* in, float* work, float* out, const Ir
     smooth_axis_kernel<0, NT><<<grid, 256, 0, st>>>(work, out, taps, d);
 }
 
+// ---- 128-bit versions: one thread owns four consecutive x voxels (needs W % 4 == 0 and 16-byte aligned pointers) -----
+__device__ __forceinline__ float4 ld4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ float4 fma4(float w, float4 a, float4 acc) {
+    acc.x += w * a.x; acc.y += w * a.y; acc.z += w * a.z; acc.w += w * a.w;
+    return acc;
+}
+
+template <int AXIS, int NT>   // AXIS 1 = y, 2 = z
+__global__ void __launch_bounds__(256)
+smooth_axis_vec_kernel(const float* __restrict__ in, float* __restrict__ out, IrsTaps taps, IrsDims d) {
+    const int V = (int)d.V();
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i >= V) return;
+    const float* f = in + (size_t)blockIdx.y * V;
+    const int n = AXIS == 1 ? d.H : d.D;
+    const int stride = AXIS == 1 ? d.W : d.W * d.H;
+    const int j = AXIS == 1 ? (i / d.W) % d.H : i / (d.W * d.H);
+    constexpr int s = (NT - 1) / 2;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (j >= s && j + s < n) {
+        const float* p = f + (i - s * stride);
+#pragma unroll
+        for (int t = 0; t < NT; ++t) acc = fma4(taps.w[t], ld4(p + t * stride), acc);
+    } else {
+        const int base = i - j * stride;
+#pragma unroll
+        for (int t = 0; t < NT; ++t) acc = fma4(taps.w[t], ld4(f + base + irs_clampi(j + t - s, 0, n - 1) * stride), acc);
+    }
+    st4(out + (size_t)blockIdx.y * V + i, acc);
+}
+
+template <int NT>   // x axis: outputs x..x+3 need inputs x-s..x+3+s: three aligned float4 loads (s <= 4), clamped at row ends
+__global__ void __launch_bounds__(256)
+smooth_x_vec_kernel(const float* __restrict__ in, float* __restrict__ out, IrsTaps taps, IrsDims d) {
+    const int V = (int)d.V();
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i >= V) return;
+    const float* f = in + (size_t)blockIdx.y * V;
+    constexpr int s = (NT - 1) / 2;
+    const int x = i % d.W;
+    const float4 c = ld4(f + i);
+    float w[12];
+    const float4 l = x >= 4 ? ld4(f + i - 4) : make_float4(c.x, c.x, c.x, c.x);           // replicate the row's first value
+    const float4 r = x + 4 < d.W ? ld4(f + i + 4) : make_float4(c.w, c.w, c.w, c.w);       // ... and its last value
+    w[0] = l.x; w[1] = l.y; w[2] = l.z; w[3] = l.w; w[4] = c.x; w[5] = c.y; w[6] = c.z; w[7] = c.w;
+    w[8] = r.x; w[9] = r.y; w[10] = r.z; w[11] = r.w;
+    float o[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) o[k] += taps.w[t] * w[4 + k + t - s];
+    }
+    st4(out + (size_t)blockIdx.y * V + i, make_float4(o[0], o[1], o[2], o[3]));
+}
+
+template <int NT>
+static void launch_smooth3_vec_nt(const float* in, float* work, float* out, const IrsTaps& taps, int C, IrsDims d,
+                                  cudaStream_t st) {
+    dim3 grid((unsigned)((d.V() / 4 + 255) / 256), C * 3);
+    smooth_axis_vec_kernel<2, NT><<<grid, 256, 0, st>>>(in, out, taps, d);
+    smooth_axis_vec_kernel<1, NT><<<grid, 256, 0, st>>>(out, work, taps, d);
+    smooth_x_vec_kernel<NT><<<grid, 256, 0, st>>>(work, out, taps, d);
+}
+
+static bool vec_ok(IrsDims d, const void* a, const void* b = nullptr, const void* c = nullptr, const void* e = nullptr) {
+    auto al = [](const void* p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+    return d.W % 4 == 0 && al(a) && al(b) && al(c) && al(e);
+}
+
+__global__ void __launch_bounds__(256)
+langevin_vec_kernel(const float* __restrict__ v, const float* __restrict__ sigma, long long sigma_cs, float coef,
+                    IrsRng rng, float* __restrict__ out, IrsDims d) {
+    const int V = (int)d.V();
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i >= V) return;
+    const int c = blockIdx.y;
+    const float* vc = v + (size_t)c * 3 * V;
+    float* oc = out + (size_t)c * 3 * V;
+    float4 a[3] = {ld4(vc + i), ld4(vc + V + i), ld4(vc + 2 * V + i)};
+    if (coef != 0.f) {
+        float e[4][3];
+        if (rng.explicit_values != nullptr) {
+            const float* ec = rng.explicit_values + (size_t)c * 3 * V;
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) {
+                const float4 t = ld4(ec + ch * V + i);
+                e[0][ch] = t.x; e[1][ch] = t.y; e[2][ch] = t.z; e[3][ch] = t.w;
+            }
+        } else {
+            const unsigned long long it = rng.iter_ptr ? (unsigned long long)(*rng.iter_ptr) : rng.iter;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) irs_normal3(rng.seed, (uint32_t)(i + k), (uint32_t)(rng.chain0 + c), it, e[k]);
+        }
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+            float4 sg = make_float4(1.f, 1.f, 1.f, 1.f);
+            if (sigma != nullptr) sg = ld4(sigma + (size_t)c * sigma_cs + (size_t)ch * V + i);
+            a[ch].x += coef * sg.x * e[0][ch]; a[ch].y += coef * sg.y * e[1][ch];
+            a[ch].z += coef * sg.z * e[2][ch]; a[ch].w += coef * sg.w * e[3][ch];
+        }
+    }
+    st4(oc + i, a[0]); st4(oc + V + i, a[1]); st4(oc + 2 * V + i, a[2]);
+}
+
+// d energy / d v for four consecutive x voxels of one channel (row neighbours from the aligned neighbours l, r)
+__device__ __forceinline__ float4 energy_grad4(const float* __restrict__ f, int i, int x, int y, int z, IrsDims d) {
+    const int sy = d.W, sz = d.W * d.H;
+    const float4 c = ld4(f + i);
+    const float lft = x > 0 ? __ldg(f + i - 1) : 0.f, rgt = x + 4 < d.W ? __ldg(f + i + 4) : 0.f;
+    const float4 ym = y > 0 ? ld4(f + i - sy) : c, yp = y < d.H - 1 ? ld4(f + i + sy) : c;
+    const float4 zm = z > 0 ? ld4(f + i - sz) : c, zp = z < d.D - 1 ? ld4(f + i + sz) : c;
+    float4 g;
+    g.x = irs_diff_energy_grad(lft, c.x, c.y, x, d.W) + irs_diff_energy_grad(ym.x, c.x, yp.x, y, d.H) + irs_diff_energy_grad(zm.x, c.x, zp.x, z, d.D);
+    g.y = irs_diff_energy_grad(c.x, c.y, c.z, x + 1, d.W) + irs_diff_energy_grad(ym.y, c.y, yp.y, y, d.H) + irs_diff_energy_grad(zm.y, c.y, zp.y, z, d.D);
+    g.z = irs_diff_energy_grad(c.y, c.z, c.w, x + 2, d.W) + irs_diff_energy_grad(ym.z, c.z, yp.z, y, d.H) + irs_diff_energy_grad(zm.z, c.z, zp.z, z, d.D);
+    g.w = irs_diff_energy_grad(c.z, c.w, rgt, x + 3, d.W) + irs_diff_energy_grad(ym.w, c.w, yp.w, y, d.H) + irs_diff_energy_grad(zm.w, c.w, zp.w, z, d.D);
+    return g;
+}
+
+__global__ void __launch_bounds__(256)
+sgd_update_vec_kernel(float* __restrict__ v, const float* __restrict__ sigma, long long sigma_cs,
+                      const float* __restrict__ css, const float* __restrict__ g_css, const double* __restrict__ coef,
+                      long long coef_stride, float tau, float* __restrict__ grad_v, IrsDims d) {
+    const int V = (int)d.V();
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i >= V) return;
+    const int c = blockIdx.y;
+    const float k = (float)coef[(size_t)c * coef_stride];
+    const int x = i % d.W, y = (i / d.W) % d.H, z = i / (d.W * d.H);
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+        const size_t o = ((size_t)c * 3 + ch) * V + i;
+        const float4 ge = energy_grad4(css + ((size_t)c * 3 + ch) * V, i, x, y, z, d);
+        const float4 gc = ld4(g_css + o);
+        float4 sg = make_float4(1.f, 1.f, 1.f, 1.f);
+        if (sigma != nullptr) sg = ld4(sigma + (size_t)c * sigma_cs + (size_t)ch * V + i);
+        float4 g, vv = *reinterpret_cast<const float4*>(v + o);
+        g.x = sg.x * sg.x * (gc.x + k * ge.x); g.y = sg.y * sg.y * (gc.y + k * ge.y);
+        g.z = sg.z * sg.z * (gc.z + k * ge.z); g.w = sg.w * sg.w * (gc.w + k * ge.w);
+        if (grad_v != nullptr) st4(grad_v + o, g);
+        vv.x -= tau * g.x; vv.y -= tau * g.y; vv.z -= tau * g.z; vv.w -= tau * g.w;
+        st4(v + o, vv);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+reg_energy_vec_kernel(const float* __restrict__ v, double* __restrict__ energy, long long energy_stride,
+                      double* __restrict__ partials, unsigned int* __restrict__ counters, IrsDims d) {
+    __shared__ double sh[32];
+    __shared__ double total[1];
+    const int V = (int)d.V(), sy = d.W, sz = d.W * d.H;
+    const int c = blockIdx.y;
+    const float* vc = v + (size_t)c * 3 * V;
+    float acc = 0.f;
+    for (int i = (blockIdx.x * blockDim.x + threadIdx.x) * 4; i < V; i += gridDim.x * blockDim.x * 4) {
+        const int x = i % d.W, y = (i / d.W) % d.H, z = i / sz;
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+            const float* f = vc + (size_t)ch * V;
+            const float4 a = ld4(f + i);
+            const float nx = x + 4 < d.W ? __ldg(f + i + 4) : 0.f;
+            const float4 py = y < d.H - 1 ? ld4(f + i + sy) : a, pz = z < d.D - 1 ? ld4(f + i + sz) : a;
+            acc += irs_diff_energy(a.x, a.y, x, d.W) + irs_diff_energy(a.y, a.z, x + 1, d.W) +
+                   irs_diff_energy(a.z, a.w, x + 2, d.W) + irs_diff_energy(a.w, nx, x + 3, d.W);
+            acc += irs_diff_energy(a.x, py.x, y, d.H) + irs_diff_energy(a.y, py.y, y, d.H) +
+                   irs_diff_energy(a.z, py.z, y, d.H) + irs_diff_energy(a.w, py.w, y, d.H);
+            acc += irs_diff_energy(a.x, pz.x, z, d.D) + irs_diff_energy(a.y, pz.y, z, d.D) +
+                   irs_diff_energy(a.z, pz.z, z, d.D) + irs_diff_energy(a.w, pz.w, z, d.D);
+        }
+    }
+    double blk[1];
+    irs_block_sum<1>(&acc, blk, sh);
+    if (irs_grid_sum<1>(blk, partials + (size_t)c * gridDim.x, counters + c, total)) {
+        if (threadIdx.x == 0) energy[(size_t)c * energy_stride] = total[0];
+    }
+}
+
 // energy of one chain: sum over 3 components x 3 axes of squared forward differences (last one counted twice)
 __global__ void __launch_bounds__(256)
 reg_energy_kernel(const float* __restrict__ v, double* __restrict__ energy, long long energy_stride,
@@ -217,6 +395,11 @@ diff_bwd_kernel(const float* __restrict__ g_nabla, float* __restrict__ g_v, int 
 
 int irs_launch_langevin(const float* v, const float* sigma, long long sigma_cs, float coef, IrsRng rng, float* out,
                         int C, IrsDims d, cudaStream_t st) {
+    if (vec_ok(d, v, sigma, out, rng.explicit_values) && (sigma_cs % 4) == 0) {
+        dim3 vgrid((unsigned)((d.V() / 4 + 255) / 256), C);
+        langevin_vec_kernel<<<vgrid, 256, 0, st>>>(v, sigma, sigma_cs, coef, rng, out, d);
+        return (int)cudaGetLastError();
+    }
     dim3 grid((unsigned)((d.V() + 255) / 256), C);
     langevin_kernel<<<grid, 256, 0, st>>>(v, sigma, sigma_cs, coef, rng, out, d);
     return (int)cudaGetLastError();
@@ -225,6 +408,16 @@ int irs_launch_langevin(const float* v, const float* sigma, long long sigma_cs, 
 // in -> (z pass) out -> (y pass) work -> (x pass) out : the reference's order (utils/util.py:402-404)
 int irs_launch_smooth3(const float* in, float* work, float* out, const IrsTaps& taps, int C, IrsDims d,
                        cudaStream_t st) {
+    if (vec_ok(d, in, work, out) && taps.n <= 9) {
+        switch (taps.n) {
+            case 3: launch_smooth3_vec_nt<3>(in, work, out, taps, C, d, st); break;
+            case 5: launch_smooth3_vec_nt<5>(in, work, out, taps, C, d, st); break;
+            case 7: launch_smooth3_vec_nt<7>(in, work, out, taps, C, d, st); break;
+            case 9: launch_smooth3_vec_nt<9>(in, work, out, taps, C, d, st); break;
+            default: return IRS_ERR_UNSUPPORTED;
+        }
+        return (int)cudaGetLastError();
+    }
     switch (taps.n) {
         case 3: launch_smooth3_nt<3>(in, work, out, taps, C, d, st); break;
         case 5: launch_smooth3_nt<5>(in, work, out, taps, C, d, st); break;
@@ -246,13 +439,19 @@ int irs_reg_energy_blocks(IrsDims d) {
 int irs_launch_reg_energy(const float* v, double* energy, long long energy_stride, double* partials,
                           unsigned int* counters, int C, IrsDims d, cudaStream_t st) {
     dim3 grid(irs_reg_energy_blocks(d), C);
-    reg_energy_kernel<<<grid, 256, 0, st>>>(v, energy, energy_stride, partials, counters, d);
+    if (vec_ok(d, v)) reg_energy_vec_kernel<<<grid, 256, 0, st>>>(v, energy, energy_stride, partials, counters, d);
+    else reg_energy_kernel<<<grid, 256, 0, st>>>(v, energy, energy_stride, partials, counters, d);
     return (int)cudaGetLastError();
 }
 
 int irs_launch_sgd_update(float* v, const float* sigma, long long sigma_cs, const float* css, const float* g_css,
                           const double* coef, long long coef_stride, float tau, float* grad_v, int C, IrsDims d,
                           cudaStream_t st) {
+    if (vec_ok(d, v, sigma, css, g_css) && vec_ok(d, grad_v) && (sigma_cs % 4) == 0) {
+        dim3 vgrid((unsigned)((d.V() / 4 + 255) / 256), C);
+        sgd_update_vec_kernel<<<vgrid, 256, 0, st>>>(v, sigma, sigma_cs, css, g_css, coef, coef_stride, tau, grad_v, d);
+        return (int)cudaGetLastError();
+    }
     dim3 grid((unsigned)((d.V() + 255) / 256), C);
     sgd_update_kernel<<<grid, 256, 0, st>>>(v, sigma, sigma_cs, css, g_css, coef, coef_stride, tau, grad_v, d);
     return (int)cudaGetLastError();
