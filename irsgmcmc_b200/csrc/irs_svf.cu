@@ -11,6 +11,8 @@
 // (every s with a non-zero hat weight lies inside it), so no atomics are issued -- ATen scatters 24 atomicAdds per
 // voxel here.  Candidates are pruned axis by axis (a zero x-weight skips the y/z loads).  For R above
 // gather_radius_max the exact scatter kernel below takes over (large deformations; still CUDA, no CPU path).
+#include <cstdlib>
+
 #include "irs_kernels.cuh"
 #include "irs_bodies.cuh"
 
@@ -65,35 +67,43 @@ svf_step_bwd_scatter_kernel(const float* __restrict__ in, float in_scale, const 
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int TILE_X = 32, TILE_Y = 8, TILE_T = TILE_X * TILE_Y;
 
-template <int R>
+// EX = valid row width, RS = row stride in shared memory.  RS is a multiple of 32 floats so that all rows alias the same
+// banks: the lanes of a warp sit in distinct columns, hence gathers whose cells lie in different rows do not conflict
+// (with RS = EX = 36 a lane pair 4 apart in neighbouring rows collides -- measured 2.4 wavefronts per load).
+// The forward kernel (R = 2, data-dependent cells) pads; the adjoint's R = 1 path reads candidates at fixed offsets
+// from the thread's own column (conflict-free with RS = EX) and prefers the smaller footprint.
+template <int R, bool PAD = false>
 struct Tile {
-    static constexpr int EX = TILE_X + 2 * R, EY = TILE_Y + 2 * R, PS = EX * EY, NP = 2 * R + 1;
-    static constexpr int NE = (PS + TILE_T - 1) / TILE_T;  // plane elements per thread
+    static constexpr int EX = TILE_X + 2 * R, EY = TILE_Y + 2 * R, RS = PAD ? 64 : EX, PS = RS * EY, NP = 2 * R + 1;
+    static constexpr int NE = (EX * EY + TILE_T - 1) / TILE_T;  // plane elements per thread
 };
 
 // the plane elements a thread moves from global to shared memory: fixed for the whole march
-template <int R>
+template <typename T, int R>
 struct PlaneMap {
-    int gofs[Tile<R>::NE];   // offset inside a (H, W) plane, or -1 outside the volume
+    int gofs[T::NE];   // offset inside a (H, W) plane, or -1 outside the volume
+    int sofs[T::NE];   // offset inside a shared-memory plane, or -1 for no element
     __device__ __forceinline__ void init(int x0t, int y0t, IrsDims d) {
 #pragma unroll
-        for (int k = 0; k < Tile<R>::NE; ++k) {
+        for (int k = 0; k < T::NE; ++k) {
             const int e = threadIdx.x + k * TILE_T;
-            const int ey = e / Tile<R>::EX, ex = e - ey * Tile<R>::EX;
+            const int ey = e / T::EX, ex = e - ey * T::EX;
             const int gx = x0t - R + ex, gy = y0t - R + ey;
-            gofs[k] = (e < Tile<R>::PS && gx >= 0 && gx < d.W && gy >= 0 && gy < d.H) ? gy * d.W + gx : -1;
+            const bool valid = e < T::EX * T::EY;
+            gofs[k] = (valid && gx >= 0 && gx < d.W && gy >= 0 && gy < d.H) ? gy * d.W + gx : -1;
+            sofs[k] = valid ? ey * T::RS + ex : -1;
         }
     }
 };
 
-template <int R, int NCH>
-__device__ __forceinline__ void plane_fetch(const PlaneMap<R>& m, const float* __restrict__ src, long long V, int pz,
-                                            IrsDims d, float scale, float (&reg)[NCH][Tile<R>::NE]) {
+template <typename T, int R, int NCH>
+__device__ __forceinline__ void plane_fetch(const PlaneMap<T, R>& m, const float* __restrict__ src, long long V, int pz,
+                                            IrsDims d, float scale, float (&reg)[NCH][T::NE]) {
     const bool zin = pz >= 0 && pz < d.D;
     const int zofs = pz * d.H * d.W;   // 3 V < 2^31 (IRS_CHECK_DIMS): 32-bit element offsets
     const int Vi = (int)V;
 #pragma unroll
-    for (int k = 0; k < Tile<R>::NE; ++k) {
+    for (int k = 0; k < T::NE; ++k) {
         const bool ok = zin && m.gofs[k] >= 0;
         const int o = zofs + m.gofs[k];
 #pragma unroll
@@ -101,42 +111,42 @@ __device__ __forceinline__ void plane_fetch(const PlaneMap<R>& m, const float* _
     }
 }
 
-template <int R, int NCH>
-__device__ __forceinline__ bool plane_nonzero(const float (&reg)[NCH][Tile<R>::NE]) {
+template <typename T, int NCH>
+__device__ __forceinline__ bool plane_nonzero(const float (&reg)[NCH][T::NE]) {
     bool nz = false;
 #pragma unroll
-    for (int k = 0; k < Tile<R>::NE; ++k)
+    for (int k = 0; k < T::NE; ++k)
 #pragma unroll
         for (int ch = 0; ch < NCH; ++ch) nz = nz || (reg[ch][k] != 0.f);
     return nz;
 }
 
-template <int R, int NCH>
-__device__ __forceinline__ void plane_store(float* __restrict__ dst, int ch_stride, const float (&reg)[NCH][Tile<R>::NE]) {
+template <typename T, int R, int NCH>
+__device__ __forceinline__ void plane_store(const PlaneMap<T, R>& m, float* __restrict__ dst, int ch_stride,
+                                            const float (&reg)[NCH][T::NE]) {
 #pragma unroll
-    for (int k = 0; k < Tile<R>::NE; ++k) {
-        const int e = threadIdx.x + k * TILE_T;
-        if (e < Tile<R>::PS) {
+    for (int k = 0; k < T::NE; ++k) {
+        if (m.sofs[k] >= 0) {
 #pragma unroll
-            for (int ch = 0; ch < NCH; ++ch) dst[ch * ch_stride + e] = reg[ch][k];
+            for (int ch = 0; ch < NCH; ++ch) dst[ch * ch_stride + m.sofs[k]] = reg[ch][k];
         }
     }
 }
 
 // trilinear cell in the ring: index of the (x0,y0,z0) corner and the z-corner offset; x/y corner offsets are 1 and EX.
 // slot_z = ring slot of plane z (the thread's own plane); the cell's planes lie within z-R .. z+R.
-template <int R>
+template <typename T, int R>
 __device__ __forceinline__ void ring_cell(float px, float py, float pz, int x0t, int y0t, int z, int slot_z, int& i000,
                                           int& sz, float& fx, float& fy, float& fz) {
     const float x0 = floorf(px), y0 = floorf(py), z0 = floorf(pz);
     fx = px - x0; fy = py - y0; fz = pz - z0;
     const int ix = (int)x0, iy = (int)y0, iz = (int)z0;
     int s0 = slot_z + (iz - z);
-    s0 += s0 < 0 ? Tile<R>::NP : 0;
-    s0 -= s0 >= Tile<R>::NP ? Tile<R>::NP : 0;
-    const int s1 = (s0 + 1 == Tile<R>::NP) ? 0 : s0 + 1;
-    i000 = s0 * Tile<R>::PS + (iy - (y0t - R)) * Tile<R>::EX + (ix - (x0t - R));
-    sz = (s1 - s0) * Tile<R>::PS;
+    s0 += s0 < 0 ? T::NP : 0;
+    s0 -= s0 >= T::NP ? T::NP : 0;
+    const int s1 = (s0 + 1 == T::NP) ? 0 : s0 + 1;
+    i000 = s0 * T::PS + (iy - (y0t - R)) * T::RS + (ix - (x0t - R));
+    sz = (s1 - s0) * T::PS;
 }
 
 template <int EX>
@@ -173,7 +183,7 @@ template <int R>
 __global__ void __launch_bounds__(TILE_T)
 svf_step_fwd_tile_kernel(const float* __restrict__ in_all, float in_scale, float* __restrict__ out_all,
                          float* __restrict__ maxabs, int seg_len, IrsDims d) {
-    using T = Tile<R>;
+    using T = Tile<R, true>;
     extern __shared__ float smem[];
     float* U = smem;  // [3][NP][PS]
     const long long V = d.V();
@@ -184,15 +194,15 @@ svf_step_fwd_tile_kernel(const float* __restrict__ in_all, float in_scale, float
     const int x0t = bx * TILE_X, y0t = by * TILE_Y, zs = bz * seg_len, ze = min(zs + seg_len, d.D);
     const int lx = threadIdx.x % TILE_X, ly = threadIdx.x / TILE_X, x = x0t + lx, y = y0t + ly;
     const bool active = x < d.W && y < d.H;
-    const int lc = (ly + R) * T::EX + lx + R;
+    const int lc = (ly + R) * T::RS + lx + R;
     const float xmax = (float)(d.W - 1), ymax = (float)(d.H - 1), zmax = (float)(d.D - 1);
 
-    PlaneMap<R> map;
+    PlaneMap<T, R> map;
     map.init(x0t, y0t, d);
     float reg[3][T::NE];
     for (int pz = zs - R; pz <= zs + R; ++pz) {
-        plane_fetch<R, 3>(map, in, V, pz, d, in_scale, reg);
-        plane_store<R, 3>(U + (((pz % T::NP) + T::NP) % T::NP) * T::PS, T::NP * T::PS, reg);
+        plane_fetch<T, R, 3>(map, in, V, pz, d, in_scale, reg);
+        plane_store<T, R, 3>(map, U + (((pz % T::NP) + T::NP) % T::NP) * T::PS, T::NP * T::PS, reg);
     }
     __syncthreads();
 
@@ -202,7 +212,7 @@ svf_step_fwd_tile_kernel(const float* __restrict__ in_all, float in_scale, float
     int gi = (zs * d.H + y) * d.W + x;
     const int HW = d.H * d.W, Vi = (int)V;
     for (int z = zs; z < ze; ++z) {
-        plane_fetch<R, 3>(map, in, V, z + R + 1, d, in_scale, reg);  // in flight while this plane is processed
+        plane_fetch<T, R, 3>(map, in, V, z + R + 1, d, in_scale, reg);  // in flight while this plane is processed
         if (active) {
             const float* Uz = U + slot * T::PS + lc;
             const float ux = Uz[0], uy = Uz[T::NP * T::PS], uz = Uz[2 * T::NP * T::PS];
@@ -213,16 +223,16 @@ svf_step_fwd_tile_kernel(const float* __restrict__ in_all, float in_scale, float
                             pz = irs_clampf((float)z + uz, 0.f, zmax);
                 int i000, sz;
                 float fx, fy, fz;
-                ring_cell<R>(px, py, pz, x0t, y0t, z, slot, i000, sz, fx, fy, fz);
-                out[gi] = ux + ring_interp<T::EX>(U, i000, sz, fx, fy, fz);
-                out[Vi + gi] = uy + ring_interp<T::EX>(U + T::NP * T::PS, i000, sz, fx, fy, fz);
-                out[2 * Vi + gi] = uz + ring_interp<T::EX>(U + 2 * T::NP * T::PS, i000, sz, fx, fy, fz);
+                ring_cell<T, R>(px, py, pz, x0t, y0t, z, slot, i000, sz, fx, fy, fz);
+                out[gi] = ux + ring_interp<T::RS>(U, i000, sz, fx, fy, fz);
+                out[Vi + gi] = uy + ring_interp<T::RS>(U + T::NP * T::PS, i000, sz, fx, fy, fz);
+                out[2 * Vi + gi] = uz + ring_interp<T::RS>(U + 2 * T::NP * T::PS, i000, sz, fx, fy, fz);
             } else {
                 irs_body_svf_fwd(in, in_scale, out, V, gi, d);
             }
         }
         __syncthreads();  // plane z-R is no longer needed
-        plane_store<R, 3>(U + slot_in * T::PS, T::NP * T::PS, reg);
+        plane_store<T, R, 3>(map, U + slot_in * T::PS, T::NP * T::PS, reg);
         __syncthreads();
         slot = slot + 1 == T::NP ? 0 : slot + 1;
         slot_in = slot_in + 1 == T::NP ? 0 : slot_in + 1;
@@ -249,7 +259,7 @@ __device__ __forceinline__ void svf_bwd_tile_body(const float* __restrict__ u, f
                                                   const float* __restrict__ gp, float* __restrict__ g, float out_scale,
                                                   IrsDims d, int x0t, int y0t, int zs, int ze, float* smem) {
     using T = Tile<R>;
-    constexpr int NP = T::NP, PS = T::PS, EX = T::EX;
+    constexpr int NP = T::NP, PS = T::PS, EX = T::RS;
     float* U = smem;                // [3][NP][PS]  velocity ring, slot = plane mod NP (scaled)
     float* G = smem + 3 * NP * PS;  // [3][PS]      incoming gradient of the current source plane
     const long long V = d.V();
@@ -260,18 +270,18 @@ __device__ __forceinline__ void svf_bwd_tile_body(const float* __restrict__ u, f
     const float xf = (float)x, yf = (float)y;
     const float xmax = (float)(d.W - 1), ymax = (float)(d.H - 1), zmax = (float)(d.D - 1);
 
-    PlaneMap<R> map;
+    PlaneMap<T, R> map;
     map.init(x0t, y0t, d);
     float ru[3][T::NE], rg[3][T::NE];
     const int s_first = zs - R, s_last = ze - 1 + R;
     for (int pz = s_first - R; pz <= s_first + R; ++pz) {
-        plane_fetch<R, 3>(map, u, V, pz, d, in_scale, ru);
-        plane_store<R, 3>(U + (((pz % NP) + NP) % NP) * PS, NP * PS, ru);
+        plane_fetch<T, R, 3>(map, u, V, pz, d, in_scale, ru);
+        plane_store<T, R, 3>(map, U + (((pz % NP) + NP) % NP) * PS, NP * PS, ru);
     }
-    plane_fetch<R, 3>(map, gp, V, s_first, d, 1.f, rg);
-    plane_store<R, 3>(G, PS, rg);
+    plane_fetch<T, R, 3>(map, gp, V, s_first, d, 1.f, rg);
+    plane_store<T, R, 3>(map, G, PS, rg);
     // the incoming gradient vanishes outside the (dilated) fixed mask: planes of a tile that are all zero are skipped
-    bool g_nonzero = __syncthreads_or(plane_nonzero<R, 3>(rg));
+    bool g_nonzero = __syncthreads_or(plane_nonzero<T, 3>(rg));
 
     float acc[NP][3];
 #pragma unroll
@@ -281,8 +291,8 @@ __device__ __forceinline__ void svf_bwd_tile_body(const float* __restrict__ u, f
     int slot_in = (((s_first + R + 1) % NP) + NP) % NP;  // where the prefetched plane s+R+1 goes (= slot of plane s-R)
     int gi = ((s_first - R) * d.H + y) * d.W + x;       // index of target (x, y, s-R)
     for (int s = s_first; s <= s_last; ++s) {
-        plane_fetch<R, 3>(map, u, V, s + R + 1, d, in_scale, ru);   // in flight while plane s is processed
-        plane_fetch<R, 3>(map, gp, V, s + 1, d, 1.f, rg);
+        plane_fetch<T, R, 3>(map, u, V, s + R + 1, d, in_scale, ru);   // in flight while plane s is processed
+        plane_fetch<T, R, 3>(map, gp, V, s + 1, d, 1.f, rg);
         if (g_nonzero && active && s >= 0 && s < d.D) {
             const float* Us = U + slot * PS;
             const float sf = (float)s;
@@ -337,12 +347,12 @@ __device__ __forceinline__ void svf_bwd_tile_body(const float* __restrict__ u, f
                 }
                 int i000, sz;
                 float fx, fy, fz, dx, dy, dz, jx, jy, jz;
-                ring_cell<R>(px, py, pz, x0t, y0t, s, slot, i000, sz, fx, fy, fz);
-                ring_interp_grad<EX>(U, i000, sz, fx, fy, fz, dx, dy, dz);
+                ring_cell<T, R>(px, py, pz, x0t, y0t, s, slot, i000, sz, fx, fy, fz);
+                ring_interp_grad<T::RS>(U, i000, sz, fx, fy, fz, dx, dy, dz);
                 jx = g0 * dx; jy = g0 * dy; jz = g0 * dz;
-                ring_interp_grad<EX>(U + NP * PS, i000, sz, fx, fy, fz, dx, dy, dz);
+                ring_interp_grad<T::RS>(U + NP * PS, i000, sz, fx, fy, fz, dx, dy, dz);
                 jx += g1 * dx; jy += g1 * dy; jz += g1 * dz;
-                ring_interp_grad<EX>(U + 2 * NP * PS, i000, sz, fx, fy, fz, dx, dy, dz);
+                ring_interp_grad<T::RS>(U + 2 * NP * PS, i000, sz, fx, fy, fz, dx, dy, dz);
                 jx += g2 * dx; jy += g2 * dy; jz += g2 * dz;
                 acc[R][0] += g0 + mx * jx; acc[R][1] += g1 + my * jy; acc[R][2] += g2 + mz * jz;
             }
@@ -355,9 +365,9 @@ __device__ __forceinline__ void svf_bwd_tile_body(const float* __restrict__ u, f
         for (int i = 0; i < NP - 1; ++i) { acc[i][0] = acc[i + 1][0]; acc[i][1] = acc[i + 1][1]; acc[i][2] = acc[i + 1][2]; }
         acc[NP - 1][0] = acc[NP - 1][1] = acc[NP - 1][2] = 0.f;
         __syncthreads();                 // everyone is done with ring plane s-R and with G
-        plane_store<R, 3>(U + slot_in * PS, NP * PS, ru);
-        plane_store<R, 3>(G, PS, rg);
-        g_nonzero = __syncthreads_or(plane_nonzero<R, 3>(rg));
+        plane_store<T, R, 3>(map, U + slot_in * PS, NP * PS, ru);
+        plane_store<T, R, 3>(map, G, PS, rg);
+        g_nonzero = __syncthreads_or(plane_nonzero<T, 3>(rg));
         slot = slot + 1 == NP ? 0 : slot + 1;
         slot_in = slot_in + 1 == NP ? 0 : slot_in + 1;
         gi += HW;
@@ -399,17 +409,23 @@ constexpr size_t svf_bwd_tile_smem(int R) {
     return sizeof(float) * (size_t)(3 * (2 * R + 1) + 3) * (TILE_X + 2 * R) * (TILE_Y + 2 * R);
 }
 constexpr size_t svf_fwd_tile_smem(int R) {
-    return sizeof(float) * (size_t)(3 * (2 * R + 1)) * (TILE_X + 2 * R) * (TILE_Y + 2 * R);
+    return sizeof(float) * (size_t)(3 * (2 * R + 1)) * 64 * (TILE_Y + 2 * R);
 }
 
 // z-segment length: the (tiles x segments x chains) CTAs should fill whole waves of the 148 SMs, while each segment
 // pays `halo` extra plane-iterations.  Picks the segment count with the lowest modelled time.
 static int svf_seg_len(IrsDims d, int C, int slots, int halo) {
+    if (const char* e = getenv("IRS_SVF_SEG")) {   // development override
+        const int v = atoi(e);
+        if (v >= 1) return v < d.D ? v : d.D;
+    }
     const long long tiles = (long long)((d.W + TILE_X - 1) / TILE_X) * ((d.H + TILE_Y - 1) / TILE_Y) * C;
     int best_len = d.D;
     double best_cost = 1e300;
     for (int nseg = 1; nseg <= d.D; ++nseg) {
         const int len = (d.D + nseg - 1) / nseg;
+        if (len > 32 && len < d.D) continue;   // measured: long segments lose more to load imbalance than they save in halo
+        if (len > 32 && nseg == 1 && d.D > 32) continue;
         if (len < 4 && nseg > 1) break;
         const int nseg_eff = (d.D + len - 1) / len;
         const long long ctas = tiles * nseg_eff;
