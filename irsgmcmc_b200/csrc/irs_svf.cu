@@ -43,20 +43,23 @@ svf_step_fwd_kernel(const float* __restrict__ in, float in_scale, float* __restr
     }
 }
 
-// exact scatter form of the interpolation transpose for steps whose displacement exceeds the gather window
+// exact scatter form of the interpolation transpose for steps whose displacement exceeds the gather window.
+// Launched after every tiled adjoint step with a small persistent grid: when the step was handled by the gather
+// (the normal case) all CTAs leave after one uniform load -- a full-size grid of empty CTAs would cost ~7 us per step.
 __global__ void __launch_bounds__(256)
 svf_step_bwd_scatter_kernel(const float* __restrict__ in, float in_scale, const float* __restrict__ gp_all,
                             float* __restrict__ g_all, const float* __restrict__ maxabs, int radius_max,
-                            float out_scale, IrsDims d) {
+                            float out_scale, int C, IrsDims d) {
     const int R = (int)floorf(__ldg(maxabs)) + 1;
     if (R <= radius_max) return;
     const long long V = d.V();
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= V) return;
-    const size_t off = (size_t)blockIdx.y * 3 * V;
-    float* g = g_all + off;
-    irs_body_svf_bwd_scatter(in + off, in_scale, gp_all + off, out_scale, V, i, d,
-                             [&](long long t, int ch, float val) { atomicAdd(g + (size_t)ch * V + t, val); });
+    for (int c = 0; c < C; ++c) {
+        const size_t off = (size_t)c * 3 * V;
+        float* g = g_all + off;
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < V; i += (long long)gridDim.x * blockDim.x)
+            irs_body_svf_bwd_scatter(in + off, in_scale, gp_all + off, out_scale, V, i, d,
+                                     [&](long long t, int ch, float val) { atomicAdd(g + (size_t)ch * V + t, val); });
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -262,6 +265,9 @@ __device__ __forceinline__ void svf_bwd_tile_body(const float* __restrict__ u, f
     constexpr int NP = T::NP, PS = T::PS, EX = T::RS;
     float* U = smem;                // [3][NP][PS]  velocity ring, slot = plane mod NP (scaled)
     float* G = smem + 3 * NP * PS;  // [3][PS]      incoming gradient of the current source plane
+    // per-row "incoming gradient is non-zero" flags of the current / next source plane: the gradient vanishes outside the
+    // (dilated) fixed mask, and a warp (= one row of targets) whose three source rows are all zero skips the transpose
+    __shared__ int row_nz[2][T::EY];
     const long long V = d.V();
     const int Vi = (int)V, HW = d.H * d.W;
     const int lx = threadIdx.x % TILE_X, ly = threadIdx.x / TILE_X, x = x0t + lx, y = y0t + ly;
@@ -278,9 +284,19 @@ __device__ __forceinline__ void svf_bwd_tile_body(const float* __restrict__ u, f
         plane_fetch<T, R, 3>(map, u, V, pz, d, in_scale, ru);
         plane_store<T, R, 3>(map, U + (((pz % NP) + NP) % NP) * PS, NP * PS, ru);
     }
+    auto flag_rows = [&](int buf) {
+#pragma unroll
+        for (int k = 0; k < T::NE; ++k) {
+            if (map.sofs[k] >= 0 && (rg[0][k] != 0.f || rg[1][k] != 0.f || rg[2][k] != 0.f)) row_nz[buf][map.sofs[k] / T::RS] = 1;
+        }
+    };
+    if (threadIdx.x < 2 * T::EY) row_nz[threadIdx.x / T::EY][threadIdx.x % T::EY] = 0;
+    __syncthreads();
     plane_fetch<T, R, 3>(map, gp, V, s_first, d, 1.f, rg);
     plane_store<T, R, 3>(map, G, PS, rg);
-    // the incoming gradient vanishes outside the (dilated) fixed mask: planes of a tile that are all zero are skipped
+    int cur = 0;
+    flag_rows(cur);
+    // planes of a tile whose incoming gradient is entirely zero are skipped altogether
     bool g_nonzero = __syncthreads_or(plane_nonzero<T, 3>(rg));
 
     float acc[NP][3];
@@ -293,10 +309,15 @@ __device__ __forceinline__ void svf_bwd_tile_body(const float* __restrict__ u, f
     for (int s = s_first; s <= s_last; ++s) {
         plane_fetch<T, R, 3>(map, u, V, s + R + 1, d, in_scale, ru);   // in flight while plane s is processed
         plane_fetch<T, R, 3>(map, gp, V, s + 1, d, 1.f, rg);
+        if (threadIdx.x < T::EY) row_nz[cur ^ 1][threadIdx.x] = 0;   // last read before the previous barrier pair
+        bool rows_nz = false;
+#pragma unroll
+        for (int oy = -R; oy <= R; ++oy) rows_nz = rows_nz || (row_nz[cur][ly + R + oy] != 0);
         if (g_nonzero && active && s >= 0 && s < d.D) {
             const float* Us = U + slot * PS;
             const float sf = (float)s;
             // ---- interpolation transpose ----
+            if (rows_nz) {
 #pragma unroll
             for (int oy = -R; oy <= R; ++oy) {
                 if (BORDER && (y + oy < 0 || y + oy >= d.H)) continue;
@@ -336,8 +357,9 @@ __device__ __forceinline__ void svf_bwd_tile_body(const float* __restrict__ u, f
                     }
                 }
             }
+            }
             // ---- direct + position term of target (x, y, s) ----
-            if (s >= zs && s < ze) {
+            if (s >= zs && s < ze && row_nz[cur][ly + R] != 0) {
                 const float g0 = G[lc], g1 = G[PS + lc], g2 = G[2 * PS + lc];
                 float px = xf + Us[lc], py = yf + Us[NP * PS + lc], pz = sf + Us[2 * NP * PS + lc];
                 float mx = 1.f, my = 1.f, mz = 1.f;
@@ -367,6 +389,8 @@ __device__ __forceinline__ void svf_bwd_tile_body(const float* __restrict__ u, f
         __syncthreads();                 // everyone is done with ring plane s-R and with G
         plane_store<T, R, 3>(map, U + slot_in * PS, NP * PS, ru);
         plane_store<T, R, 3>(map, G, PS, rg);
+        cur ^= 1;
+        flag_rows(cur);
         g_nonzero = __syncthreads_or(plane_nonzero<T, 3>(rg));
         slot = slot + 1 == NP ? 0 : slot + 1;
         slot_in = slot_in + 1 == NP ? 0 : slot_in + 1;
@@ -506,7 +530,8 @@ int irs_launch_svf_bwd(const float* v, const float* hist, const float* maxabs, f
     const int seg_len = svf_seg_len(d, C, slots, 6);
     const int nseg = (d.D + seg_len - 1) / seg_len;
     dim3 tgrid(tiles * nseg, C);
-    dim3 vgrid((unsigned)((d.V() + 255) / 256), C);
+    const long long vblocks = (d.V() + 255) / 256;
+    dim3 vgrid((unsigned)(vblocks < 1184 ? vblocks : 1184), 1);   // persistent: see svf_step_bwd_scatter_kernel
     // ping-pong between g_work and the caller's g_u buffer (g_u is only read by the first adjoint step)
     const float* gp = g_u;
     for (int k = n_steps - 1; k >= 0; --k) {
@@ -516,7 +541,7 @@ int irs_launch_svf_bwd(const float* v, const float* hist, const float* maxabs, f
         svf_step_bwd_tile_kernel<<<tgrid, TILE_T, smem, st>>>(in, in_scale, gp, out, maxabs + k, gather_radius_max,
                                                                   in_scale, seg_len, d);
         svf_step_bwd_scatter_kernel<<<vgrid, 256, 0, st>>>(in, in_scale, gp, out, maxabs + k, gather_radius_max,
-                                                           in_scale, d);
+                                                           in_scale, C, d);
         gp = out;
     }
     return (int)cudaGetLastError();
