@@ -179,6 +179,36 @@ __device__ __forceinline__ void ring_interp_grad(const float* __restrict__ U, in
     gz = b1 - b0;
 }
 
+// packed fp32 pair FMA (Blackwell FFMA2): d = a * b + c on both halves, one issue slot
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+    unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a), rb = *reinterpret_cast<unsigned long long*>(&b),
+                       rc = *reinterpret_cast<unsigned long long*>(&c), rd;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+    return *reinterpret_cast<float2*>(&rd);
+}
+
+// position term of the adjoint: sum_c g_c * grad trilinear[u_c](p).  Interpolation is linear in the corner values, so
+// the three components are combined at the eight corners first (w = g . u) and ONE gradient is interpolated.
+template <int RS>
+__device__ __forceinline__ void ring_interp_grad_dot(const float* __restrict__ U, int ch_stride, int i, int sz, float g0,
+                                                     float g1, float g2, float fx, float fy, float fz, float& jx,
+                                                     float& jy, float& jz) {
+    const float* U1 = U + ch_stride;
+    const float* U2 = U + 2 * ch_stride;
+#define IRS_W(o) (g0 * U[(o)] + g1 * U1[(o)] + g2 * U2[(o)])
+    const float v000 = IRS_W(i), v001 = IRS_W(i + 1), v010 = IRS_W(i + RS), v011 = IRS_W(i + RS + 1);
+    const float v100 = IRS_W(i + sz), v101 = IRS_W(i + sz + 1), v110 = IRS_W(i + sz + RS), v111 = IRS_W(i + sz + RS + 1);
+#undef IRS_W
+    const float d00 = v001 - v000, d01 = v011 - v010, d10 = v101 - v100, d11 = v111 - v110;
+    const float a00 = v000 + fx * d00, a01 = v010 + fx * d01, a10 = v100 + fx * d10, a11 = v110 + fx * d11;
+    const float e0 = a01 - a00, e1 = a11 - a10;
+    const float b0 = a00 + fy * e0, b1 = a10 + fy * e1;
+    const float dx0 = d00 + fy * (d01 - d00), dx1 = d10 + fy * (d11 - d10);
+    jx = dx0 + fz * (dx1 - dx0);
+    jy = e0 + fz * (e1 - e0);
+    jz = b1 - b0;
+}
+
 // ---- forward step -----------------------------------------------------------------------------------------------------
 // Threads whose displacement stays inside the ring window (|u| < R) gather from shared memory; the others (large
 // deformations) fall back to the global gather, so the kernel is exact for any field.
@@ -299,9 +329,10 @@ __device__ __forceinline__ void svf_bwd_tile_body(const float* __restrict__ u, f
     // planes of a tile whose incoming gradient is entirely zero are skipped altogether
     bool g_nonzero = __syncthreads_or(plane_nonzero<T, 3>(rg));
 
-    float acc[NP][3];
+    float2 acc01[NP];   // components x, y of the 2R+1 target planes (packed: updated with FFMA2)
+    float acc2[NP];     // component z
 #pragma unroll
-    for (int i = 0; i < NP; ++i) acc[i][0] = acc[i][1] = acc[i][2] = 0.f;
+    for (int i = 0; i < NP; ++i) { acc01[i] = make_float2(0.f, 0.f); acc2[i] = 0.f; }
 
     int slot = ((s_first % NP) + NP) % NP;             // ring slot of source plane s
     int slot_in = (((s_first + R + 1) % NP) + NP) % NP;  // where the prefetched plane s+R+1 goes (= slot of plane s-R)
@@ -341,18 +372,19 @@ __device__ __forceinline__ void svf_bwd_tile_body(const float* __restrict__ u, f
                     const float wxy = wx * wy;
                     float cz = Us[2 * NP * PS + li];
                     if (BORDER) cz = irs_clampf(cz, -sf, zmax - sf);
-                    const float g0 = G[li], g1 = G[PS + li], g2 = G[2 * PS + li];
+                    const float2 g01 = make_float2(G[li], G[PS + li]);
+                    const float g2 = G[2 * PS + li];
                     if (R == 1) {
                         const float wm = wxy * fmaxf(-cz, 0.f), w0 = wxy * (1.f - fabsf(cz)), wp = wxy * fmaxf(cz, 0.f);
-                        acc[0][0] += wm * g0; acc[0][1] += wm * g1; acc[0][2] += wm * g2;
-                        acc[1][0] += w0 * g0; acc[1][1] += w0 * g1; acc[1][2] += w0 * g2;
-                        acc[2][0] += wp * g0; acc[2][1] += wp * g1; acc[2][2] += wp * g2;
+                        acc01[0] = ffma2(make_float2(wm, wm), g01, acc01[0]); acc2[0] += wm * g2;
+                        acc01[1] = ffma2(make_float2(w0, w0), g01, acc01[1]); acc2[1] += w0 * g2;
+                        acc01[2] = ffma2(make_float2(wp, wp), g01, acc01[2]); acc2[2] += wp * g2;
                     } else {
                         if (wxy == 0.f) continue;
 #pragma unroll
                         for (int dz = -R; dz <= R; ++dz) {
                             const float w = wxy * fmaxf(0.f, 1.f - fabsf(cz - (float)dz));
-                            acc[dz + R][0] += w * g0; acc[dz + R][1] += w * g1; acc[dz + R][2] += w * g2;
+                            acc01[dz + R] = ffma2(make_float2(w, w), g01, acc01[dz + R]); acc2[dz + R] += w * g2;
                         }
                     }
                 }
@@ -368,24 +400,19 @@ __device__ __forceinline__ void svf_bwd_tile_body(const float* __restrict__ u, f
                     px = irs_clampf(px, 0.f, xmax); py = irs_clampf(py, 0.f, ymax); pz = irs_clampf(pz, 0.f, zmax);
                 }
                 int i000, sz;
-                float fx, fy, fz, dx, dy, dz, jx, jy, jz;
+                float fx, fy, fz, jx, jy, jz;
                 ring_cell<T, R>(px, py, pz, x0t, y0t, s, slot, i000, sz, fx, fy, fz);
-                ring_interp_grad<T::RS>(U, i000, sz, fx, fy, fz, dx, dy, dz);
-                jx = g0 * dx; jy = g0 * dy; jz = g0 * dz;
-                ring_interp_grad<T::RS>(U + NP * PS, i000, sz, fx, fy, fz, dx, dy, dz);
-                jx += g1 * dx; jy += g1 * dy; jz += g1 * dz;
-                ring_interp_grad<T::RS>(U + 2 * NP * PS, i000, sz, fx, fy, fz, dx, dy, dz);
-                jx += g2 * dx; jy += g2 * dy; jz += g2 * dz;
-                acc[R][0] += g0 + mx * jx; acc[R][1] += g1 + my * jy; acc[R][2] += g2 + mz * jz;
+                ring_interp_grad_dot<T::RS>(U, NP * PS, i000, sz, g0, g1, g2, fx, fy, fz, jx, jy, jz);
+                acc01[R].x += g0 + mx * jx; acc01[R].y += g1 + my * jy; acc2[R] += g2 + mz * jz;
             }
         }
         // ---- target plane s-R is complete ----
         if (active && s - R >= zs && s - R < ze) {
-            g[gi] = acc[0][0] * out_scale; g[Vi + gi] = acc[0][1] * out_scale; g[2 * Vi + gi] = acc[0][2] * out_scale;
+            g[gi] = acc01[0].x * out_scale; g[Vi + gi] = acc01[0].y * out_scale; g[2 * Vi + gi] = acc2[0] * out_scale;
         }
 #pragma unroll
-        for (int i = 0; i < NP - 1; ++i) { acc[i][0] = acc[i + 1][0]; acc[i][1] = acc[i + 1][1]; acc[i][2] = acc[i + 1][2]; }
-        acc[NP - 1][0] = acc[NP - 1][1] = acc[NP - 1][2] = 0.f;
+        for (int i = 0; i < NP - 1; ++i) { acc01[i] = acc01[i + 1]; acc2[i] = acc2[i + 1]; }
+        acc01[NP - 1] = make_float2(0.f, 0.f); acc2[NP - 1] = 0.f;
         __syncthreads();                 // everyone is done with ring plane s-R and with G
         plane_store<T, R, 3>(map, U + slot_in * PS, NP * PS, ru);
         plane_store<T, R, 3>(map, G, PS, rg);
