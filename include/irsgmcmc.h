@@ -128,6 +128,17 @@ int irs_vd_factor_residual(const float* r, const unsigned char* mask, double* al
                            unsigned int* counter, int D, int H, int W, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------ *
+ * Per-sample evaluation -- replaces calc_no_non_diffeomorphic_voxels + calc_det_J (utils/util.py:72-91,209-212) and
+ * calc_DSC_GPU (utils/util.py:123-148).
+ *   log_det (C,D,H,W) optional: log det J of the transformation T (normalised units, spacing 2/(n-1));
+ *   n_folded: C ints = number of voxels whose log det J is NaN (negative determinant)
+ *   counts (C, n_labels, 3) unsigned: |A = l|, |B = l|, |A = l and B = l| for int16 label volumes; labels != 0
+ * ------------------------------------------------------------------------------------------------------------------ */
+int irs_log_det_jacobian(const float* T, float* log_det, int* n_folded, int C, int D, int H, int W, void* stream);
+int irs_dice_counts(const short* seg_a, long long a_chain_stride, const short* seg_b, const int* labels_host,
+                    int n_labels, unsigned int* counts, int C, long long V, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------ *
  * Posterior moments -- replaces calc_posterior_statistics (utils/util.py:114-120) without the host-side sample buffer:
  * Welford running (count, mean, M2) over samples; count is a host-side number.
  *   sample (n_new, n) : n_new new samples of n values each;  mean, m2: n floats updated in place

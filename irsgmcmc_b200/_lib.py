@@ -83,6 +83,8 @@ SYMBOLS = {
     'irs_gmm_log_pdf': (_i, [_vp, _ll, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'irs_vd_factor': (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _vp]),
     'irs_vd_factor_residual': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    'irs_log_det_jacobian': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    'irs_dice_counts': (_i, [_vp, _ll, _vp, _vp, _i, _vp, _i, _ll, _vp]),
     'irs_welford_update': (_i, [_vp, _i, _ll, _d, _vp, _vp, _vp]),
     'irs_welford_std': (_i, [_vp, _d, _vp, _ll, _vp]),
     'irs_sgld_partials_doubles': (_sz, [ctypes.POINTER(SgldConfig)]),

@@ -227,3 +227,36 @@ class RegLoss_LogNormal(RegLoss_EnergyBased):
 
     def _mlog_energy_prior(self, y, *args, **kwargs):
         return y.log() + self.log_scale + 0.5 * ((y.log() - self.loc) / self.scale) ** 2
+
+
+class Entropy(nn.Module, ABC):
+    """base class for the entropy of a probability distribution"""
+
+    @abstractmethod
+    def forward(self, **kwargs):
+        pass
+
+
+class EntropyMultivariateNormal(Entropy):
+    """
+    entropy-related terms of the diagonal + rank-1 Gaussian q(v) = N(mu, diag(sigma^2) + u u^T) used by the VI warm start
+    (reference model/loss.py:342-372): with (log_var, u) the log-determinant part; with (sample, mu, log_var, u) the
+    Mahalanobis part via the Sherman-Morrison identity.  Elementwise torch expressions over the field (VI is section 8f
+    "next": it runs on the same CUDA operators as the SGLD step through autograd).
+    """
+
+    def forward(self, **kwargs):
+        if len(kwargs) == 2:
+            log_var, u = kwargs['log_var'], kwargs['u']
+            sigma = torch.exp(0.5 * log_var)
+            dims = tuple(range(1, log_var.dim()))
+            return 0.5 * (torch.log1p(torch.sum((u / sigma) ** 2, dim=dims)) + torch.sum(log_var, dim=dims))
+        if len(kwargs) == 4:
+            sample, mu, log_var, u = kwargs['sample'], kwargs['mu'], kwargs['log_var'], kwargs['u']
+            sigma = torch.exp(0.5 * log_var)
+            dims = tuple(range(1, log_var.dim()))
+            sample_n, u_n = (sample - mu) / sigma, u / sigma
+            t1 = torch.sum(sample_n ** 2, dim=dims)
+            t2 = torch.sum(sample_n * u_n, dim=dims) ** 2 / (1.0 + torch.sum(u_n ** 2, dim=dims))
+            return 0.5 * (t1 - t2)
+        raise NotImplementedError

@@ -242,3 +242,32 @@ def welford_std(m2, count):
     out = torch.empty_like(m2)
     _lib.check(lib.irs_welford_std(_lib.ptr(m2), float(count), _lib.ptr(out), m2.numel(), _lib.stream()))
     return out
+
+
+def log_det_jacobian(T, want_log_det=True):
+    """log det J of a transformation (C,3,D,H,W) and the per-sample count of folded (NaN) voxels"""
+    lib = _lib.load()
+    _lib.require_cuda(T)
+    _f32(T)
+    C, D, H, W = _dims(T)
+    log_det = torch.empty(C, D, H, W, device=T.device, dtype=torch.float32) if want_log_det else None
+    counts = torch.empty(C, device=T.device, dtype=torch.int32)
+    _lib.check(lib.irs_log_det_jacobian(_lib.ptr(T), _lib.ptr(log_det), _lib.ptr(counts), C, D, H, W, _lib.stream()))
+    return counts, log_det
+
+
+def dice_counts(seg_a, seg_b, labels):
+    """(C, n_labels, 3) counts |A = l|, |B = l|, |A = l and B = l| for int16 label volumes (seg_a may be shared by chains)"""
+    import ctypes
+    lib = _lib.load()
+    _lib.require_cuda(seg_a, seg_b)
+    if seg_a.dtype != torch.int16 or seg_b.dtype != torch.int16:
+        raise NotImplementedError('int16 segmentations only')
+    C = seg_b.shape[0]
+    V = seg_b[0].numel()
+    stride = 0 if seg_a.shape[0] == 1 else V
+    lab = (ctypes.c_int * len(labels))(*[int(x) for x in labels])
+    counts = torch.empty(C, len(labels), 3, device=seg_b.device, dtype=torch.int32)
+    _lib.check(lib.irs_dice_counts(_lib.ptr(seg_a), stride, _lib.ptr(seg_b), lab, len(labels), _lib.ptr(counts), C, V,
+                                   _lib.stream()))
+    return counts

@@ -131,6 +131,145 @@ class Trainer:
             else:
                 reg_loss.log_w_reg.copy_(s.hyper[50].to(reg_loss.log_w_reg.dtype))
 
+    # -- VI warm start (reference trainer.py:79-223), on the drop-in modules through autograd ------------------------
+    def _build_VI_modules(self):
+        """the objects the reference's ConfigParser would create for VI from the JSON (parse_config.py:110-148,215-249)"""
+        from .. import model as M
+        from ..optimizers import Adam
+        from ..utils import RegistrationModule, SVF_3D, Sobolev_kernel_1D
+        cfg, sc, dev = self.config, self.sampler.cfg, self.device
+        n = self.dims
+        dof = 3.0 * float(np.prod(n))
+        data_loss = (M.SSD() if sc.data_loss == 'ssd' else M.GMM(sc.no_components, sc.s)).to(dev)
+        reg_cls = getattr(M, sc.reg_loss)
+        reg_loss = reg_cls(w_reg=sc.w_reg, diff_op='GradientOperator', dims=n, learnable=sc.reg_learnable).to(dev)
+        mods = {'data_loss': data_loss, 'reg_loss': reg_loss, 'entropy_loss': M.EntropyMultivariateNormal(),
+                'scale_prior': M.LogScaleNormalPrior(*sc.gmm_scale_prior).to(dev),
+                'proportion_prior': M.DirichletPrior(sc.no_components, sc.dirichlet_alpha).to(dev),
+                'transformation_module': SVF_3D(n, sc.svf_steps).to(dev), 'registration_module': RegistrationModule()}
+        if sc.reg_learnable:
+            if sc.reg_loss == 'RegLoss_LogNormal':
+                mods['loc_prior'] = M.LogEnergyExpGammaPrior(sc.w_reg, dof).to(dev)
+                mods['reg_scale_prior'] = M.LogScaleNormalPrior(*sc.reg_scale_prior).to(dev)
+                mods['optimizer_reg'] = Adam([{'params': [reg_loss.loc], 'lr': sc.lr_reg},
+                                              {'params': [reg_loss.log_scale], 'lr': sc.lr_reg}], lr_decay=sc.lr_decay)
+            else:
+                shape = 0.5 * dof
+                mods['w_reg_prior'] = M.LogPrecisionExpGammaPrior(shape=shape, rate=1.0 / shape).to(dev)
+                mods['optimizer_reg'] = Adam(reg_loss.parameters(), lr=sc.lr_reg, lr_decay=sc.lr_decay)
+        mods['optimizer_GMM'] = Adam([{'params': [data_loss.log_std], 'lr': sc.lr_log_std},
+                                      {'params': [data_loss.logits], 'lr': sc.lr_logits}], lr_decay=sc.lr_decay)
+        if sc.sobolev_enabled:
+            taps = torch.from_numpy(Sobolev_kernel_1D(sc.sobolev_s, sc.sobolev_lambda)[0]).float().unsqueeze(0)
+            S3 = torch.stack((taps, taps, taps), 0).to(dev)
+            mods['S'] = {'x': S3.unsqueeze(2).unsqueeze(2), 'y': S3.unsqueeze(2).unsqueeze(4), 'z': S3.unsqueeze(3).unsqueeze(4)}
+            mods['padding'] = (sc.sobolev_s,) * 6
+        return mods
+
+    def _step_GMM(self, m, residuals, alpha=1.0):
+        """reference trainer.py:68-77"""
+        data_loss = m['data_loss']
+        data_term = data_loss(residuals.detach()).sum() * alpha
+        data_term = data_term - m['scale_prior'](data_loss.log_scales).sum() - m['proportion_prior'](data_loss.log_proportions).sum()
+        m['optimizer_GMM'].zero_grad()
+        data_term.backward()
+        m['optimizer_GMM'].step()
+
+    def _get_VD_factor(self, m, residuals, mask):
+        """reference trainer.py:507-514"""
+        from ..utils import calc_VD_factor, rescale_residuals
+        if not self.virutal_decimation:
+            return 1.0
+        return calc_VD_factor(rescale_residuals(residuals.detach(), mask, m['data_loss']), mask)
+
+    def _calc_sample_loss_VI(self, m, fixed, moving, var_params_q_v, v_sample_unsmoothed, jitter_unit=None):
+        """reference trainer.py:79-117 (Trainer.__calc_sample_loss_VI)"""
+        from ..utils import SobolevGrad, calc_no_non_diffeomorphic_voxels, transform_coordinates, add_noise_uniform_field
+        data_loss, reg_loss = m['data_loss'], m['reg_loss']
+        v_sample = SobolevGrad.apply(v_sample_unsmoothed, m['S'], m['padding']) if 'S' in m else v_sample_unsmoothed
+        transformation, displacement = m['transformation_module'](v_sample)
+        with torch.no_grad():
+            no_folded, log_det_J = calc_no_non_diffeomorphic_voxels(transformation, reg_loss.diff_op)
+        if self.add_noise_uniform:
+            if jitter_unit is not None:   # explicit U[0,1) numbers: exact parity tests
+                transformation = transformation + transform_coordinates(-2.0 * self.alpha * jitter_unit + self.alpha)
+            else:
+                transformation = add_noise_uniform_field(transformation, self.alpha)
+        im_moving_warped = m['registration_module'](moving['im'], transformation)
+        output = {'displacement': displacement, 'transformation': transformation, 'im_moving_warped': im_moving_warped,
+                  'log_det_J': log_det_J}
+        residuals = data_loss.map(fixed['im'], im_moving_warped)
+        alpha = self._get_VD_factor(m, residuals, fixed['mask'])
+        residuals_masked = residuals[fixed['mask']]
+        self._step_GMM(m, residuals_masked, alpha)
+        data_term = data_loss(residuals_masked).sum() * alpha
+        reg_term, log_y = reg_loss(v_sample)
+        reg_term = reg_term.sum()
+        entropy_term = m['entropy_loss'](sample=v_sample_unsmoothed, mu=var_params_q_v['mu'],
+                                         log_var=var_params_q_v['log_var'], u=var_params_q_v['u']).sum()
+        aux = {'alpha': alpha, 'reg_energy': log_y.exp(), 'no_non_diffeomorphic_voxels': no_folded,
+               'residuals': residuals_masked}
+        loss_terms = {'data': data_term, 'reg': reg_term, 'entropy': entropy_term}
+        if reg_loss.learnable:
+            if reg_loss.__class__.__name__ == 'RegLoss_LogNormal':
+                loss_terms['reg_loc_prior'] = m['loc_prior'](log_y).sum()
+            else:
+                loss_terms['w_reg_prior'] = m['w_reg_prior'](reg_loss.log_w_reg)
+        return loss_terms, output, aux
+
+    def _run_VI(self, var_params_q_v=None, no_iters=None, modules=None, lr=None, noise=None):
+        """
+        fit the Gaussian variational posterior q(v) (reference trainer.py:119-223): per iteration two antithetic samples,
+        loss = data + reg - entropy, Adam on (mu, log_var, u) and on the regulariser hyper-parameters; the shared mixture
+        is stepped inside each sample's loss.  Returns (var_params_q_v, modules, history of loss terms).
+        `noise`: optional iterator of (eps, x, jitter1, jitter2) for exact parity tests.
+        """
+        from ..optimizers import Adam
+        tr = self.config['trainer']
+        no_iters = int(tr.get('no_iters_VI', 0)) if no_iters is None else no_iters
+        var_params_q_v = var_params_q_v or self.var_params_q_v
+        vp = {k: v.detach().clone().to(self.device).requires_grad_(True) for k, v in var_params_q_v.items()}
+        m = modules or self._build_VI_modules()
+        a = self.config.get('optimizer_q_v', {}).get('args', {})
+        lr = lr or {'mu': a.get('lr_mu', 0.01), 'log_var': a.get('lr_log_var', 0.01), 'u': a.get('lr_u', 0.01)}
+        optimizer_q_v = Adam([{'params': [vp[k]], 'lr': lr[k]} for k in ('mu', 'log_var', 'u')],
+                             lr_decay=a.get('lr_decay', 1e-3))
+        fixed = {k: v.to(self.device) for k, v in self.fixed.items()}
+        moving = {k: v.to(self.device) for k, v in self.moving.items()}
+        history = []
+        for it in range(no_iters):
+            sigma = torch.exp(0.5 * vp['log_var'])
+            if noise is not None:
+                eps, x, j1, j2 = next(noise)
+            else:
+                eps, x, j1, j2 = torch.randn_like(sigma), torch.randn(1, device=self.device), None, None
+            delta = eps * sigma + x * vp['u']          # utils/sampler.py:4-21, antithetic pair
+            lt1, output, aux = self._calc_sample_loss_VI(m, fixed, moving, vp, vp['mu'] + delta, j1)
+            lt2, _, _ = self._calc_sample_loss_VI(m, fixed, moving, vp, vp['mu'] - delta, j2)
+            data_loss, reg_loss = m['data_loss'], m['reg_loss']
+            data_term = (lt1['data'] + lt2['data']) / 2.0
+            data_term = data_term - m['scale_prior'](data_loss.log_scales).sum() - m['proportion_prior'](data_loss.log_proportions).sum()
+            reg_term = (lt1['reg'] + lt2['reg']) / 2.0
+            if reg_loss.learnable:
+                if reg_loss.__class__.__name__ == 'RegLoss_LogNormal':
+                    reg_term = reg_term - (lt1['reg_loc_prior'] + lt2['reg_loc_prior']) / 2.0 - m['reg_scale_prior'](reg_loss.log_scale).sum()
+                else:
+                    reg_term = reg_term - (lt1['w_reg_prior'] + lt2['w_reg_prior']) / 2.0
+            entropy_term = (lt1['entropy'] + lt2['entropy']) / 2.0 + m['entropy_loss'](log_var=vp['log_var'], u=vp['u']).sum()
+            loss = data_term + reg_term - entropy_term
+            if reg_loss.learnable:
+                m['optimizer_reg'].zero_grad()
+            optimizer_q_v.zero_grad()
+            loss.backward()
+            if reg_loss.learnable:
+                m['optimizer_reg'].step()
+            optimizer_q_v.step()
+            history.append({'data': data_term.detach(), 'reg': reg_term.detach(), 'entropy': entropy_term.detach(),
+                            'loss': loss.detach(), 'alpha': aux['alpha']})
+        self.var_params_q_v = {k: v.detach() for k, v in vp.items()}
+        self._vi_modules = m
+        return self.var_params_q_v, m, history
+
     # -- the hot path -------------------------------------------------------------------------------------------------
     def _SGLD_transition(self, fixed=None, moving=None, data_loss=None, reg_loss=None):
         """

@@ -88,7 +88,12 @@ def calc_det_J(nabla):
 
 
 def calc_no_non_diffeomorphic_voxels(transformation, diff_op):
-    """number of voxels with a NaN log det J per sample, and log det J (reference :209-212)"""
+    """number of voxels with a NaN log det J per sample, and log det J (reference :209-212); one fused kernel when the
+    operator is the forward-difference GradientOperator (no (N,3,D,H,W,3) gradient tensor is materialised)"""
+    from .diff_op import GradientOperator
+    if type(diff_op) is GradientOperator and transformation.is_cuda and transformation.dtype == torch.float32:
+        counts, log_det_J = ops.log_det_jacobian(transformation.detach().contiguous())
+        return counts.cpu().numpy(), log_det_J
     nabla = diff_op(transformation, transformation=True)
     log_det_J = calc_det_J(nabla).log()
     return torch.isnan(log_det_J).sum(dim=(1, 2, 3)).cpu().numpy(), log_det_J
@@ -111,11 +116,16 @@ def calc_posterior_statistics(samples, device='cuda:0'):
 @torch.no_grad()
 def calc_DSC_GPU(no_samples, seg_fixed, seg_moving, structures_dict):
     """Dice score per sample and structure (reference :123-148), one pass per structure over all samples"""
-    DSC = torch.zeros(no_samples, len(structures_dict))
-    a, b = seg_fixed[:no_samples].flatten(1), seg_moving[:no_samples].flatten(1)
-    for j, label in enumerate(structures_dict.values()):
+    labels = list(structures_dict.values())
+    a, b = seg_fixed[:no_samples], seg_moving[:no_samples].contiguous()
+    if a.is_cuda and a.dtype == torch.int16 and 0 not in labels and len(labels) <= 32:
+        # one pass over the volumes for all structures and samples (the reference loops samples x structures)
+        a = a[:1].contiguous() if a.stride(0) == 0 else a.contiguous()
+        cnt = ops.dice_counts(a, b, labels).double().cpu()
+        return (2.0 * cnt[..., 2] / (cnt[..., 0] + cnt[..., 1])).float().numpy()
+    DSC = torch.zeros(no_samples, len(labels))
+    a, b = a.flatten(1), b.flatten(1)
+    for j, label in enumerate(labels):
         fa, fb = a == label, b == label
-        num = 2.0 * (fa & fb).sum(1).float()
-        den = (fa.sum(1) + fb.sum(1)).float()
-        DSC[:, j] = (num / den).cpu()
+        DSC[:, j] = (2.0 * (fa & fb).sum(1).float() / (fa.sum(1) + fb.sum(1)).float()).cpu()
     return DSC.numpy()

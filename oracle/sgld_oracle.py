@@ -539,3 +539,98 @@ def welford_merge(parts):
         m2 = m2 + m2b + delta ** 2 * (n * nb / tot)
         n = tot
     return n, mean, m2
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# VI warm start: one iteration of Trainer._run_VI (reference trainer/trainer.py:79-223)
+# ----------------------------------------------------------------------------------------------------------------------
+
+class _SobolevIdentityBackward(torch.autograd.Function):
+    """SobolevGrad: smoothing in the forward pass, identity in the backward pass (reference utils/functions.py:98-109)"""
+
+    @staticmethod
+    def forward(ctx, x, taps):
+        return sobolev_smooth(x, taps)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, None
+
+
+def entropy_terms(log_var, u, sample=None, mu=None):
+    """reference model/loss.py:350-372"""
+    sigma = torch.exp(0.5 * log_var)
+    dims = (1, 2, 3, 4)
+    if sample is None:
+        return 0.5 * (torch.log1p(torch.sum((u / sigma) ** 2, dim=dims)) + torch.sum(log_var, dim=dims))
+    sn, un = (sample - mu) / sigma, u / sigma
+    return 0.5 * (torch.sum(sn ** 2, dim=dims) - torch.sum(sn * un, dim=dims) ** 2 / (1.0 + torch.sum(un ** 2, dim=dims)))
+
+
+def vi_sample_loss(st, fixed, moving, vp, v_unsmoothed, jitter_unit, reg_leaves):
+    """reference trainer/trainer.py:79-117; steps the shared mixture like the reference does (detached residuals)"""
+    cfg = st.cfg
+    dtype = v_unsmoothed.dtype
+    css = _SobolevIdentityBackward.apply(v_unsmoothed, st.taps)
+    T, disp = svf_exp_aten(css, cfg.svf_steps, cfg.exact_grid)
+    T_s = T + uniform_jitter_normalised(jitter_unit, cfg.jitter_alpha, T.shape) if cfg.jitter_alpha is not None else T
+    im_w = warp_aten(moving['im'].to(dtype), T_s)
+    F_im, mask = fixed['im'].to(dtype), fixed['mask']
+    z = lcc_map(F_im, im_w, cfg.s) if cfg.data == 'lcc' else ssd_map(F_im, im_w)
+    if cfg.virtual_decimation:
+        alpha = vd_factor(vd_residual(z.detach(), mask, st.log_std, st.logits), mask)
+    else:
+        alpha = torch.tensor(1.0, dtype=dtype)
+    gmm_step(st, z[mask], alpha)
+    data = gmm_nll(z[mask], st.log_std, st.logits) * alpha
+    y = reg_energy(css)
+    log_y = y.log()
+    terms = {'data': data, 'alpha': alpha, 'energy': y.detach(), 'im_w': im_w.detach(), 'disp': disp.detach()}
+    if cfg.reg == 'lognormal':
+        loc, log_scale = reg_leaves
+        reg = (log_y + log_scale + 0.5 * ((log_y - loc) / log_scale.exp()) ** 2 + (0.5 * st.dof - 1.0) * log_y).sum()
+        if cfg.reg_learnable:
+            terms['reg_loc_prior'] = expgamma_log_pdf(log_y, 0.5 * st.dof, 0.5 * float(np.float32(cfg.w_reg))).sum()
+    else:
+        lw, = reg_leaves
+        reg = (0.5 * lw.exp() * y - 0.5 * st.dof * lw).sum()
+        if cfg.reg_learnable:
+            shape = 0.5 * st.dof
+            terms['w_reg_prior'] = expgamma_log_pdf(lw, shape, 1.0 / shape)
+    terms['reg'] = reg
+    terms['entropy'] = entropy_terms(vp['log_var'], vp['u'], v_unsmoothed, vp['mu']).sum()
+    return terms
+
+
+def vi_iteration(st, fixed, moving, vp, eps, x, jitter1, jitter2):
+    """
+    one iteration of reference trainer/trainer.py:130-171 without the q(v) optimiser step: returns the loss terms and the
+    gradients w.r.t. (mu, log_var, u); steps the mixture (twice) and the regulariser hyper-parameters.
+    vp: dict of (1,3,D,H,W) tensors; eps ~ N(0,1) (1,3,D,H,W); x ~ N(0,1) scalar tensor.
+    """
+    cfg = st.cfg
+    vp = {k: v.detach().clone().requires_grad_(True) for k, v in vp.items()}
+    sigma = torch.exp(0.5 * vp['log_var'])
+    delta = eps * sigma + x * vp['u']
+    if cfg.reg == 'lognormal':
+        leaves = (st.loc.clone().requires_grad_(True), st.log_scale.clone().requires_grad_(True))
+    else:
+        leaves = (st.log_w_reg.clone().requires_grad_(True),)
+    t1 = vi_sample_loss(st, fixed, moving, vp, vp['mu'] + delta, jitter1, leaves)
+    t2 = vi_sample_loss(st, fixed, moving, vp, vp['mu'] - delta, jitter2, leaves)
+    data = (t1['data'] + t2['data']) / 2.0
+    reg = (t1['reg'] + t2['reg']) / 2.0
+    if cfg.reg_learnable:
+        if cfg.reg == 'lognormal':
+            reg = reg - (t1['reg_loc_prior'] + t2['reg_loc_prior']) / 2.0 - normal_log_pdf(leaves[1], 2.8, 5.0)
+        else:
+            reg = reg - (t1['w_reg_prior'] + t2['w_reg_prior']) / 2.0
+    entropy = (t1['entropy'] + t2['entropy']) / 2.0 + entropy_terms(vp['log_var'], vp['u']).sum()
+    loss = data + reg - entropy
+    wanted = (vp['mu'], vp['log_var'], vp['u']) + (leaves if cfg.reg_learnable else ())
+    grads = torch.autograd.grad(loss, wanted)
+    if cfg.reg_learnable:
+        st.adam_reg.step([g.to(p.dtype) for g, p in zip(grads[3:], st.adam_reg.params)])
+    return {'data': data.detach(), 'reg': reg.detach(), 'entropy': entropy.detach(), 'loss': loss.detach(),
+            'alpha': (t1['alpha'], t2['alpha']), 'im_w': t1['im_w'], 'disp': t1['disp']}, \
+        {'mu': grads[0], 'log_var': grads[1], 'u': grads[2]}

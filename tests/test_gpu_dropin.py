@@ -265,3 +265,95 @@ def test_trainer_facade(pkg):
     assert res['n'] == 3 * C and res['mean'].shape == (3, n, n, n) and torch.isfinite(res['std_dev']).all()
     assert len(res['DSC']) == 3 and res['DSC'][0].shape == (C, len(structures))
     assert res['samples_per_sec'] > 0
+
+
+# ---- section 8f "next" rows: evaluation kernels and the VI warm start ---------------------------------------------------
+def test_log_det_jacobian_and_dice_kernels(pkg):
+    from irsgmcmc_b200 import ops
+    from tests.util import smooth_field
+    n, C = 20, 2
+    T, _ = O.svf_exp_aten(smooth_field((C, 3, n, n, n), 6.0, 3), 6)
+    T = T.contiguous()
+    T[0, :, 5:8, 5:8, 5:8] = T[0, :, 5:8, 5:8, 5:8].flip(-1)        # fold a few voxels
+    counts, log_det = ops.log_det_jacobian(T.to(DEV))
+    ref = O.det_jacobian(O.forward_differences(T.double(), transformation=True)).log()
+    ok = torch.isfinite(ref)
+    assert counts.cpu().tolist() == torch.isnan(ref).sum(dim=(1, 2, 3)).tolist() and counts.sum() > 0
+    assert rel(log_det.cpu()[ok], ref[ok]) < 1e-4
+    labels = [10, 11, 12, 13, 16]
+    a = torch.tensor(labels + [0, 0, 7])[torch.randint(0, 8, (1, 1, n, n, n))].short()
+    b = torch.tensor(labels + [0, 0, 9])[torch.randint(0, 8, (C, 1, n, n, n))].short()
+    cnt = ops.dice_counts(a.to(DEV), b.to(DEV), labels).cpu()
+    for c in range(C):
+        for j, l in enumerate(labels):
+            assert cnt[c, j].tolist() == [int((a == l).sum()), int((b[c] == l).sum()), int(((a[0] == l) & (b[c] == l)).sum())]
+    U = pkg[0]
+    dsc = U.calc_DSC_GPU(C, a.to(DEV).expand(C, -1, -1, -1, -1), b.to(DEV), {f's{l}': l for l in labels})
+    want = [[2.0 * float(((a[0] == l) & (b[c] == l)).sum()) / float((a == l).sum() + (b[c] == l).sum()) for l in labels]
+            for c in range(C)]
+    assert np.allclose(dsc, np.array(want), rtol=1e-6)
+
+
+@pytest.mark.parametrize('reg_name', ['RegLoss_LogNormal', 'RegLoss_L2'])
+def test_vi_sample_loss_parity(pkg, reg_name):
+    """Trainer._calc_sample_loss_VI (= reference Trainer.__calc_sample_loss_VI, trainer.py:79-117) on the CUDA operators,
+    loss terms and gradients w.r.t. (mu, log_var, u) against the oracle"""
+    from irsgmcmc_b200.trainer import Trainer
+    from irsgmcmc_b200.data_loader.synthetic import make_pair
+    n = 16
+    torch.manual_seed(9)
+    fixed, moving, vp0 = make_pair(n)
+    cfg = _reference_style_config(1)
+    cfg['reg_loss']['type'] = reg_name
+    cfg['optimizer_reg'] = {'type': 'Adam', 'args': {'lr_loc': 0.01, 'lr_log_scale': 0.01, 'lr_log_w_reg': 0.01, 'lr_decay': 0.001}}
+    t = Trainer(cfg, fixed, moving, vp0, device=torch.device(DEV))
+    m = t._build_VI_modules()
+    m['data_loss'].init_parameters(0.7)
+    reg_key = 'lognormal' if reg_name == 'RegLoss_LogNormal' else 'l2'
+    eps, x, ju = torch.randn(1, 3, n, n, n), torch.randn(1), torch.rand(1, 3, n, n, n)
+    vp = {k: v.clone().to(DEV).requires_grad_(True) for k, v in vp0.items()}
+    sample = vp['mu'] + eps.to(DEV) * torch.exp(0.5 * vp['log_var']) + x.to(DEV) * vp['u']
+    fx, mv = {k: v.to(DEV) for k, v in fixed.items()}, {k: v.to(DEV) for k, v in moving.items()}
+    lt, out, aux = t._calc_sample_loss_VI(m, fx, mv, vp, sample, ju.to(DEV))
+    g_new = torch.autograd.grad(lt['data'] + lt['reg'] - lt['entropy'], [vp[k] for k in ('mu', 'log_var', 'u')])
+    results = {}
+    for dtype in (torch.float32, torch.float64):
+        st = O.State(O.Config(reg=reg_key, w_reg=1.6, exact_grid=dtype == torch.float64), torch.zeros(1, 3, n, n, n, dtype=dtype),
+                     torch.ones(1, 3, n, n, n, dtype=dtype), (n, n, n), dtype)
+        st.init_gmm(0.7)
+        vpo = {k: v.clone().to(dtype).requires_grad_(True) for k, v in vp0.items()}
+        so = vpo['mu'] + eps.to(dtype) * torch.exp(0.5 * vpo['log_var']) + x.to(dtype) * vpo['u']
+        leaves = (st.loc.clone().requires_grad_(True), st.log_scale.clone().requires_grad_(True)) if reg_key == 'lognormal' \
+            else (st.log_w_reg.clone().requires_grad_(True),)
+        cast = lambda d_: {k: (v.to(dtype) if v.dtype == torch.float32 else v) for k, v in d_.items()}
+        terms = O.vi_sample_loss(st, cast(fixed), cast(moving), vpo, so, ju.to(dtype), leaves)
+        g = torch.autograd.grad(terms['data'] + terms['reg'] - terms['entropy'], [vpo[k] for k in ('mu', 'log_var', 'u')])
+        results[dtype] = (terms, g, st)
+    t64, g64, st64 = results[torch.float64]
+    _, g32, _ = results[torch.float32]
+    assert rel(out['im_moving_warped'], t64['im_w']) < 1e-5 and rel(out['displacement'], t64['disp']) < 1e-5
+    assert abs(float(aux['alpha']) - float(t64['alpha'])) < 1e-4 * float(t64['alpha'])
+    for key in ('data', 'reg', 'entropy'):
+        assert rel(lt[key], t64[key]) < 1e-4, key
+    from tests.util import grad_ok
+    for name, a, b32, b64 in zip(('mu', 'log_var', 'u'), g_new, g32, g64):
+        assert grad_ok(a, b32, b64, f'VI grad {name}')
+    assert rel(m['data_loss'].log_std, st64.log_std) < 1e-4
+
+
+def test_run_VI_then_MCMC(pkg):
+    """config 1 of BASELINE.json in miniature: VI warm start, then SGLD chains initialised from q(v)"""
+    from irsgmcmc_b200.trainer import Trainer
+    from irsgmcmc_b200.data_loader.synthetic import make_pair
+    n, C = 16, 2
+    torch.manual_seed(3)
+    fixed, moving, vp0 = make_pair(n)
+    cfg = _reference_style_config(C, burn_in=2, samples=6, period=2)
+    cfg['trainer']['no_iters_VI'] = 4
+    t = Trainer(cfg, fixed, moving, vp0, device=torch.device(DEV))
+    vp, m, hist = t._run_VI()
+    assert len(hist) == 4 and all(torch.isfinite(h['loss']) for h in hist)
+    assert not torch.equal(vp['mu'].cpu(), vp0['mu']) and vp['log_var'].shape == vp0['log_var'].shape
+    t._SGLD_init(vp)
+    res = t._run_MCMC(m['data_loss'], m['reg_loss'], speed_test_iters=0)
+    assert res['n'] == 3 * C and torch.isfinite(res['mean']).all()

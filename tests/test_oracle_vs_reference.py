@@ -121,3 +121,43 @@ def test_dropin_distributions_match_reference(ref):
     lw = torch.tensor(0.4)
     assert torch.allclose(D.LogPrecisionExpGammaPrior(shape=0.5 * dof, rate=2.0 / dof)(lw),
                           R.LogPrecisionExpGammaPrior(shape=0.5 * dof, rate=2.0 / dof)(lw))
+
+
+@pytest.mark.parametrize('reg_name,reg_type', [('lognormal', 'RegLoss_LogNormal'), ('l2', 'RegLoss_L2')])
+def test_vi_sample_loss_matches_reference(ref, reg_name, reg_type):
+    """the VI per-sample loss (reference Trainer.__calc_sample_loss_VI, trainer/trainer.py:79-117) and its gradients"""
+    from irsgmcmc_b200.data_loader.synthetic import make_pair
+    n = 14
+    torch.manual_seed(123)
+    fixed, moving, vp0 = make_pair(n)
+    t = ref_import.make_trainer(ref, (n, n, n), 1, reg_type=reg_type, w_reg=1.6, uniform_noise=0.1)
+    t.losses['entropy'] = ref.loss.EntropyMultivariateNormal()
+    gmm, reg = t.losses['data']['loss'], t.losses['reg']['loss']
+    gmm.init_parameters(torch.tensor(1.0))
+    st = O.State(O.Config(reg=reg_name, w_reg=1.6), torch.zeros(1, 3, n, n, n), torch.ones(1, 3, n, n, n), (n, n, n))
+    st.init_gmm(1.0)
+    vp_ref = {k: v.clone().requires_grad_(True) for k, v in vp0.items()}
+    vp_or = {k: v.clone().requires_grad_(True) for k, v in vp0.items()}
+    eps, x, ju = torch.randn(1, 3, n, n, n), torch.randn(1), torch.rand(1, 3, n, n, n)
+    ref.util.get_noise_uniform = lambda shape, device, alpha, j=ju: -2.0 * alpha * j + alpha
+    sample_ref = vp_ref['mu'] + eps * torch.exp(0.5 * vp_ref['log_var']) + x * vp_ref['u']
+    lt, out, aux = t._Trainer__calc_sample_loss_VI(gmm, reg, t.losses['entropy'], fixed, moving, vp_ref, sample_ref)
+    sample_or = vp_or['mu'] + eps * torch.exp(0.5 * vp_or['log_var']) + x * vp_or['u']
+    if reg_name == 'lognormal':
+        leaves = (st.loc.clone().requires_grad_(True), st.log_scale.clone().requires_grad_(True))
+    else:
+        leaves = (st.log_w_reg.clone().requires_grad_(True),)
+    terms = O.vi_sample_loss(st, fixed, moving, vp_or, sample_or, ju, leaves)
+    assert rel(terms['im_w'], out['im_moving_warped']) < 1e-5 and rel(terms['disp'], out['displacement']) < 1e-5
+    assert abs(float(terms['alpha']) - float(aux['alpha'])) < 1e-5
+    for key in ('data', 'reg', 'entropy'):
+        assert rel(terms[key], lt[key]) < 1e-4, key
+    prior_key = 'reg_loc_prior' if reg_name == 'lognormal' else 'w_reg_prior'
+    assert rel(terms[prior_key], lt[prior_key]) < 1e-6
+    loss_ref = lt['data'] + lt['reg'] - lt['entropy']
+    loss_or = terms['data'] + terms['reg'] - terms['entropy']
+    g_ref = torch.autograd.grad(loss_ref, [vp_ref[k] for k in ('mu', 'log_var', 'u')])
+    g_or = torch.autograd.grad(loss_or, [vp_or[k] for k in ('mu', 'log_var', 'u')])
+    for a, b in zip(g_or, g_ref):
+        assert rel(a, b) < 5e-4
+    assert rel(st.log_std, gmm.log_std.detach()) < 1e-4
