@@ -59,6 +59,8 @@ int irs_warp3d_nearest_u8(const unsigned char* mask, long long mask_chain_stride
  *   v        (C,3,D,H,W) velocity in voxels
  *   hist     workspace, n_steps*C*3*D*H*W floats: u_1 .. u_n (u_0 = v / 2^n is not stored); u_n is the displacement
  *   maxabs   n_steps floats: max |u_k| of the input of step k (sizes the adjoint's gather window)
+ * Cubic volumes only (D == H == W, else IRS_ERR_UNSUPPORTED): the reference's own coordinate handling is consistent only
+ * for cubes (utils/util.py:418-429 scales channel i by shape[2+i]; its data loader pads every image to a cube).
  * ------------------------------------------------------------------------------------------------------------------ */
 size_t irs_svf_hist_floats(int C, int D, int H, int W, int n_steps);
 int irs_svf_exp_fwd(const float* v, float* hist, float* maxabs, int n_steps, int C, int D, int H, int W, void* stream);

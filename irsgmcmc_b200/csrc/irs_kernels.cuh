@@ -11,6 +11,14 @@
         if ((C) > 65535) return IRS_ERR_UNSUPPORTED;                                     \
     } while (0)
 
+// The reference's SVF maps channel i with 2/(shape[2+i]-1) but unnormalises x with W, z with D (utils/util.py:418-429
+// vs ATen): consistent only for cubes, which is all its data loader produces (data_loader/datasets.py:76-83).  The
+// voxel-unit integrator is therefore defined for cubic volumes only.
+#define IRS_CHECK_CUBE(D, H, W)                                      \
+    do {                                                             \
+        if ((D) != (H) || (H) != (W)) return IRS_ERR_UNSUPPORTED;    \
+    } while (0)
+
 #define IRS_LAUNCH_CHECK()                             \
     do {                                               \
         cudaError_t e__ = cudaGetLastError();          \

@@ -78,6 +78,7 @@ IrsHyperCfg hyper_cfg(const irs_sgld_config* c) {
 int check_config(const irs_sgld_config* c) {
     if (!c) return IRS_ERR_BAD_ARG;
     IRS_CHECK_DIMS(c->C, c->D, c->H, c->W);
+    IRS_CHECK_CUBE(c->D, c->H, c->W);
     if (c->K < 1 || c->K > IRS_MAX_K) return IRS_ERR_BAD_ARG;
     if (c->data_term != IRS_DATA_LCC && c->data_term != IRS_DATA_SSD) return IRS_ERR_BAD_ARG;
     if (c->data_term == IRS_DATA_LCC && (c->lcc_s < 1 || c->lcc_s > 3)) return IRS_ERR_BAD_ARG;

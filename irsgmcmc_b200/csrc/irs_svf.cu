@@ -581,6 +581,7 @@ extern "C" size_t irs_svf_hist_floats(int C, int D, int H, int W, int n_steps) {
 extern "C" int irs_svf_exp_fwd(const float* v, float* hist, float* maxabs, int n_steps, int C, int D, int H, int W,
                                void* stream) {
     IRS_CHECK_DIMS(C, D, H, W);
+    IRS_CHECK_CUBE(D, H, W);
     if (!v || !hist || !maxabs || n_steps < 1 || n_steps > IRS_MAX_SVF_STEPS) return IRS_ERR_BAD_ARG;
     return irs_launch_svf_fwd(v, hist, maxabs, n_steps, C, IrsDims{D, H, W}, (cudaStream_t)stream);
 }
@@ -588,6 +589,7 @@ extern "C" int irs_svf_exp_fwd(const float* v, float* hist, float* maxabs, int n
 extern "C" int irs_svf_outputs(const float* u, const float* lin_x, const float* lin_y, const float* lin_z, float* T,
                                float* disp, int C, int D, int H, int W, void* stream) {
     IRS_CHECK_DIMS(C, D, H, W);
+    IRS_CHECK_CUBE(D, H, W);
     if (!u || (T && (!lin_x || !lin_y || !lin_z))) return IRS_ERR_BAD_ARG;
     IrsDims d{D, H, W};
     dim3 grid((unsigned)((d.V() + 255) / 256), C);
@@ -599,6 +601,7 @@ extern "C" int irs_svf_exp_bwd(const float* v, const float* hist, const float* m
                                float* g_v, int n_steps, int gather_radius_max, int C, int D, int H, int W,
                                void* stream) {
     IRS_CHECK_DIMS(C, D, H, W);
+    IRS_CHECK_CUBE(D, H, W);
     if (!v || !hist || !maxabs || !g_u || !g_work || !g_v || n_steps < 1 || n_steps > IRS_MAX_SVF_STEPS)
         return IRS_ERR_BAD_ARG;
     if (gather_radius_max < 0) return IRS_ERR_BAD_ARG;
