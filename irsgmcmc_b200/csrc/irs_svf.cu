@@ -12,9 +12,11 @@
 // voxel here.  Candidates are pruned axis by axis (a zero x-weight skips the y/z loads).  For R above
 // gather_radius_max the exact scatter kernel below takes over (large deformations; still CUDA, no CPU path).
 #include <cstdlib>
+#include <type_traits>
 
 #include "irs_kernels.cuh"
 #include "irs_bodies.cuh"
+#include "irs_tma.cuh"
 
 namespace {
 
@@ -50,7 +52,7 @@ __global__ void __launch_bounds__(256)
 svf_step_bwd_scatter_kernel(const float* __restrict__ in, float in_scale, const float* __restrict__ gp_all,
                             float* __restrict__ g_all, const float* __restrict__ maxabs, int radius_max,
                             float out_scale, int C, IrsDims d) {
-    const int R = (int)floorf(__ldg(maxabs)) + 1;
+    const int R = (int)floorf(__ldg(maxabs) + 1e-3f) + 1;   // = svf_gather_radius
     if (R <= radius_max) return;
     const long long V = d.V();
     for (int c = 0; c < C; ++c) {
@@ -212,19 +214,26 @@ __device__ __forceinline__ void ring_interp_grad_dot(const float* __restrict__ U
 // ---- forward step -----------------------------------------------------------------------------------------------------
 // Threads whose displacement stays inside the ring window (|u| < R) gather from shared memory; the others (large
 // deformations) fall back to the global gather, so the kernel is exact for any field.
+// block maximum of the per-thread max |u| -> one order-independent atomic per CTA
+__device__ __forceinline__ void block_max_to_global(float m, float* __restrict__ maxabs) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    __shared__ float sm[TILE_T / 32];
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float mm = sm[0];
+        for (int w = 1; w < TILE_T / 32; ++w) mm = fmaxf(mm, sm[w]);
+        if (mm > 0.f) atomic_max_nonneg(maxabs, mm);
+    }
+}
+
 template <int R>
-__global__ void __launch_bounds__(TILE_T)
-svf_step_fwd_tile_kernel(const float* __restrict__ in_all, float in_scale, float* __restrict__ out_all,
-                         float* __restrict__ maxabs, int seg_len, IrsDims d) {
+__device__ __forceinline__ float svf_fwd_tile_body(const float* __restrict__ in, float in_scale, float* __restrict__ out,
+                                                   IrsDims d, int x0t, int y0t, int zs, int ze, float* smem) {
     using T = Tile<R, true>;
-    extern __shared__ float smem[];
     float* U = smem;  // [3][NP][PS]
     const long long V = d.V();
-    const float* in = in_all + (size_t)blockIdx.y * 3 * V;
-    float* out = out_all + (size_t)blockIdx.y * 3 * V;
-    const int tiles_x = (d.W + TILE_X - 1) / TILE_X, tiles_y = (d.H + TILE_Y - 1) / TILE_Y;
-    const int bx = blockIdx.x % tiles_x, by = (blockIdx.x / tiles_x) % tiles_y, bz = blockIdx.x / (tiles_x * tiles_y);
-    const int x0t = bx * TILE_X, y0t = by * TILE_Y, zs = bz * seg_len, ze = min(zs + seg_len, d.D);
     const int lx = threadIdx.x % TILE_X, ly = threadIdx.x / TILE_X, x = x0t + lx, y = y0t + ly;
     const bool active = x < d.W && y < d.H;
     const int lc = (ly + R) * T::RS + lx + R;
@@ -271,16 +280,21 @@ svf_step_fwd_tile_kernel(const float* __restrict__ in_all, float in_scale, float
         slot_in = slot_in + 1 == T::NP ? 0 : slot_in + 1;
         gi += HW;
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-    __shared__ float sm[TILE_T / 32];
-    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        float mm = sm[0];
-        for (int w = 1; w < TILE_T / 32; ++w) mm = fmaxf(mm, sm[w]);
-        if (mm > 0.f) atomic_max_nonneg(maxabs, mm);
-    }
+    return m;
+}
+
+template <int R>
+__global__ void __launch_bounds__(TILE_T)
+svf_step_fwd_tile_kernel(const float* __restrict__ in_all, float in_scale, float* __restrict__ out_all,
+                         float* __restrict__ maxabs, int seg_len, IrsDims d) {
+    extern __shared__ __align__(128) float smem[];
+    const long long V = d.V();
+    const int tiles_x = (d.W + TILE_X - 1) / TILE_X, tiles_y = (d.H + TILE_Y - 1) / TILE_Y;
+    const int bx = blockIdx.x % tiles_x, by = (blockIdx.x / tiles_x) % tiles_y, bz = blockIdx.x / (tiles_x * tiles_y);
+    const int x0t = bx * TILE_X, y0t = by * TILE_Y, zs = bz * seg_len, ze = min(zs + seg_len, d.D);
+    const float m = svf_fwd_tile_body<R>(in_all + (size_t)blockIdx.y * 3 * V, in_scale, out_all + (size_t)blockIdx.y * 3 * V,
+                                         d, x0t, y0t, zs, ze, smem);
+    block_max_to_global(m, maxabs);
 }
 
 // ---- adjoint step -------------------------------------------------------------------------------------------------------
@@ -425,34 +439,423 @@ __device__ __forceinline__ void svf_bwd_tile_body(const float* __restrict__ u, f
     }
 }
 
-__global__ void __launch_bounds__(TILE_T, 4)
-svf_step_bwd_tile_kernel(const float* __restrict__ in, float in_scale, const float* __restrict__ gp_all,
-                         float* __restrict__ g_all, const float* __restrict__ maxabs, int radius_max, float out_scale,
-                         int seg_len, IrsDims d) {
-    extern __shared__ float smem[];
-    const int R = (int)floorf(__ldg(maxabs)) + 1;
-    const long long V = d.V();
-    const size_t off = (size_t)blockIdx.y * 3 * V;
-    const int tiles_x = (d.W + TILE_X - 1) / TILE_X, tiles_y = (d.H + TILE_Y - 1) / TILE_Y;
-    const int bx = blockIdx.x % tiles_x, by = (blockIdx.x / tiles_x) % tiles_y, bz = blockIdx.x / (tiles_x * tiles_y);
-    const int x0t = bx * TILE_X, y0t = by * TILE_Y, zs = bz * seg_len, ze = min(zs + seg_len, d.D);
+// tile path of one adjoint step for gather radius R (from the step's max |u|): R = 1 / 2 from shared-memory rings, wider
+// windows straight from global memory; beyond radius_max only the direct + position terms (the scatter kernel that
+// follows adds the interpolation transpose with atomics)
+__device__ __forceinline__ void svf_bwd_tile_dispatch(int R, const float* __restrict__ in, float in_scale,
+                                                      const float* __restrict__ gp, float* __restrict__ g, int radius_max,
+                                                      float out_scale, IrsDims d, int x0t, int y0t, int zs, int ze,
+                                                      float* smem) {
     // the tile, its halo and every clamped position stay strictly inside the volume?
     auto interior = [&](int Rr) {
         return x0t - 2 * Rr >= 0 && x0t + TILE_X - 1 + 2 * Rr <= d.W - 1 && y0t - 2 * Rr >= 0 &&
                y0t + TILE_Y - 1 + 2 * Rr <= d.H - 1 && zs - 2 * Rr >= 0 && ze - 1 + 2 * Rr <= d.D - 1;
     };
     if (R <= radius_max && R == 1) {
-        if (interior(1)) svf_bwd_tile_body<1, false>(in + off, in_scale, gp_all + off, g_all + off, out_scale, d, x0t, y0t, zs, ze, smem);
-        else svf_bwd_tile_body<1, true>(in + off, in_scale, gp_all + off, g_all + off, out_scale, d, x0t, y0t, zs, ze, smem);
+        if (interior(1)) svf_bwd_tile_body<1, false>(in, in_scale, gp, g, out_scale, d, x0t, y0t, zs, ze, smem);
+        else svf_bwd_tile_body<1, true>(in, in_scale, gp, g, out_scale, d, x0t, y0t, zs, ze, smem);
     } else if (R <= radius_max && R == 2) {
-        svf_bwd_tile_body<2, true>(in + off, in_scale, gp_all + off, g_all + off, out_scale, d, x0t, y0t, zs, ze, smem);
-    } else {  // rare: wide gather straight from global memory; beyond radius_max only the direct + position terms
-              // (the scatter kernel that follows adds the interpolation transpose with atomics)
+        svf_bwd_tile_body<2, true>(in, in_scale, gp, g, out_scale, d, x0t, y0t, zs, ze, smem);
+    } else {
         const int x = x0t + (threadIdx.x % TILE_X), y = y0t + (threadIdx.x / TILE_X);
         if (x >= d.W || y >= d.H) return;
+        const long long V = d.V();
         for (int z = zs; z < ze; ++z)
-            irs_body_svf_bwd(in + off, in_scale, gp_all + off, g_all + off, R <= radius_max ? R : -1, out_scale, V,
+            irs_body_svf_bwd(in, in_scale, gp, g, R <= radius_max ? R : -1, out_scale, V,
                              ((long long)z * d.H + y) * d.W + x, d);
+    }
+}
+
+// out-of-line copy for kernels whose main path is another one: keeps the fallback's register pressure out of it
+__device__ __noinline__ void svf_bwd_tile_dispatch_cold(int R, const float* __restrict__ in, float in_scale,
+                                                        const float* __restrict__ gp, float* __restrict__ g, int radius_max,
+                                                        float out_scale, IrsDims d, int x0t, int y0t, int zs, int ze,
+                                                        float* smem) {
+    svf_bwd_tile_dispatch(R, in, in_scale, gp, g, radius_max, out_scale, d, x0t, y0t, zs, ze, smem);
+}
+
+// gather radius of a step from its max |u|.  The R = 1 kernels assume that x + u never ROUNDS to x +- 1 in fp32, hence the
+// margin (ulp(x) / 2 < 1e-3 for every supported volume size).
+__device__ __forceinline__ int svf_gather_radius(float maxabs) { return (int)floorf(maxabs + 1e-3f) + 1; }
+
+__global__ void __launch_bounds__(TILE_T, 4)
+svf_step_bwd_tile_kernel(const float* __restrict__ in, float in_scale, const float* __restrict__ gp_all,
+                         float* __restrict__ g_all, const float* __restrict__ maxabs, int radius_max, float out_scale,
+                         int seg_len, IrsDims d) {
+    extern __shared__ __align__(128) float smem[];
+    const int R = svf_gather_radius(__ldg(maxabs));
+    const long long V = d.V();
+    const size_t off = (size_t)blockIdx.y * 3 * V;
+    const int tiles_x = (d.W + TILE_X - 1) / TILE_X, tiles_y = (d.H + TILE_Y - 1) / TILE_Y;
+    const int bx = blockIdx.x % tiles_x, by = (blockIdx.x / tiles_x) % tiles_y, bz = blockIdx.x / (tiles_x * tiles_y);
+    const int x0t = bx * TILE_X, y0t = by * TILE_Y, zs = bz * seg_len, ze = min(zs + seg_len, d.D);
+    svf_bwd_tile_dispatch(R, in + off, in_scale, gp_all + off, g_all + off, radius_max, out_scale, d, x0t, y0t, zs, ze, smem);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// TMA-fed kernels for steps with max |u| < 1 (every step of a typical registration; the rings above remain the path for
+// larger displacements and for row pitches the TMA unit cannot address).  One thread issues ONE cp.async.bulk.tensor per
+// z-plane (tile + halo 1, three components, zeros outside the volume) into a 4-slot shared-memory ring guarded by
+// mbarriers; nobody spends issue slots on global loads, address arithmetic or bounds predicates.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int TMA_EX = TILE_X + 2, TMA_EY = TILE_Y + 2;   // valid tile + halo 1
+constexpr int TMA_NS = 4;                                  // ring slots: planes z-1, z, z+1 and one in flight
+constexpr int TMA_XO = 4;   // the TMA unit wants a 16-byte aligned innermost coordinate: boxes start at x0t - 4 (measured:
+                            // an unaligned start raises "illegal instruction"); column TMA_XO of a box is the tile's x0t
+
+template <int BW>   // box width = shared-memory row stride (floats); BW * 4 bytes must be a multiple of 16
+struct TmaRing {
+    static_assert(BW >= TMA_XO + TILE_X + 2 && (BW * 4) % 16 == 0, "box width");
+    static constexpr int CS = TMA_EY * BW;                              // component stride
+    static constexpr uint32_t BYTES = 3u * CS * 4u;                     // one plane box
+    static constexpr int SS = (int)((BYTES + 127u) / 128u * 128u / 4u); // slot stride (floats), 128-byte aligned
+};
+
+// trilinear cell in a TMA ring: q0 = ring sequence number of plane floor(pz) (slot = q & 3)
+template <int BW>
+__device__ __forceinline__ void tma_ring_cell(float px, float py, float pz, int x0t, int y0t, int z, int q_z, int& i000,
+                                              int& sz, float& fx, float& fy, float& fz) {
+    using RG = TmaRing<BW>;
+    const float x0 = floorf(px), y0 = floorf(py), z0 = floorf(pz);
+    fx = px - x0; fy = py - y0; fz = pz - z0;
+    const int ix = (int)x0, iy = (int)y0, iz = (int)z0;
+    const int s0 = (q_z + (iz - z)) & (TMA_NS - 1), s1 = (s0 + 1) & (TMA_NS - 1);
+    i000 = s0 * RG::SS + (iy - (y0t - 1)) * BW + (ix - (x0t - TMA_XO));
+    sz = (s1 - s0) * RG::SS;
+}
+
+// ---- forward step ------------------------------------------------------------------------------------------------------
+// voxels with |u| >= 0.999 (rare; only the last steps of a large deformation) take the exact global gather
+template <int BW>
+__device__ __forceinline__ float svf_fwd_tma_body(const CUtensorMap* tmap, const float* __restrict__ in, float in_scale,
+                                                  float* __restrict__ out, IrsDims d, int chain, int x0t, int y0t, int zs,
+                                                  int ze, float* smem) {
+    using RG = TmaRing<BW>;
+    float* U = smem;                                                           // [4 slots][3][EY][BW]
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + TMA_NS * RG::SS);      // one mbarrier per slot
+    const int tid = threadIdx.x;
+    const int lx = tid % TILE_X, ly = tid / TILE_X, x = x0t + lx, y = y0t + ly;
+    const bool active = x < d.W && y < d.H;
+    const int lc = (ly + 1) * BW + lx + TMA_XO;
+    const float xmax = (float)(d.W - 1), ymax = (float)(d.H - 1), zmax = (float)(d.D - 1);
+    const long long V = d.V();
+    const int Vi = (int)V, HW = d.H * d.W;
+    const int n_planes = (ze - zs) + 2;   // planes zs-1 .. ze, ring sequence number q = plane - (zs - 1)
+
+    if (tid == 0) {
+#pragma unroll
+        for (int i = 0; i < TMA_NS; ++i) irs_mbar_init(&bar[i], 1);
+        irs_mbar_fence_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        for (int q = 0; q < TMA_NS && q < n_planes; ++q) {
+            irs_mbar_expect_tx(&bar[q], RG::BYTES);
+            irs_tma_load_plane(U + q * RG::SS, tmap, &bar[q], x0t - TMA_XO, y0t - 1, zs - 1 + q, 3 * chain);
+        }
+    }
+    float m = 0.f;
+    int gi = (zs * d.H + y) * d.W + x;
+    irs_mbar_wait(&bar[0], 0);
+    irs_mbar_wait(&bar[1], 0);
+    for (int z = zs, it = 0; z < ze; ++z, ++it) {
+        irs_mbar_wait(&bar[(it + 2) & 3], ((it + 2) >> 2) & 1);   // plane z+1 has landed
+        if (active) {
+            const float* Uz = U + ((it + 1) & 3) * RG::SS + lc;
+            const float ux = Uz[0] * in_scale, uy = Uz[RG::CS] * in_scale, uz = Uz[2 * RG::CS] * in_scale;
+            const float amax = fmaxf(fabsf(ux), fmaxf(fabsf(uy), fabsf(uz)));
+            m = fmaxf(m, amax);
+            if (amax < 0.999f) {
+                const float px = irs_clampf((float)x + ux, 0.f, xmax), py = irs_clampf((float)y + uy, 0.f, ymax),
+                            pz = irs_clampf((float)z + uz, 0.f, zmax);
+                int i000, sz;
+                float fx, fy, fz;
+                tma_ring_cell<BW>(px, py, pz, x0t, y0t, z, it + 1, i000, sz, fx, fy, fz);
+                // interpolation is linear in the samples and in_scale is a power of two: scaling after is bit-identical
+                out[gi] = ux + in_scale * ring_interp<BW>(U, i000, sz, fx, fy, fz);
+                out[Vi + gi] = uy + in_scale * ring_interp<BW>(U + RG::CS, i000, sz, fx, fy, fz);
+                out[2 * Vi + gi] = uz + in_scale * ring_interp<BW>(U + 2 * RG::CS, i000, sz, fx, fy, fz);
+            } else {
+                irs_body_svf_fwd(in, in_scale, out, V, gi, d);
+            }
+        }
+        __syncthreads();   // everyone is done with plane z-1: its slot takes plane z+3
+        if (tid == 0 && it + 4 < n_planes) {
+            irs_mbar_expect_tx(&bar[it & 3], RG::BYTES);
+            irs_tma_load_plane(U + (it & 3) * RG::SS, tmap, &bar[it & 3], x0t - TMA_XO, y0t - 1, zs + 3 + it, 3 * chain);
+        }
+        gi += HW;
+    }
+    return m;
+}
+
+constexpr int FWD_BW = 40;
+constexpr size_t svf_fwd_tma_smem() { return sizeof(float) * TMA_NS * TmaRing<FWD_BW>::SS + 8 * TMA_NS; }
+
+// maxabs_prev = max |u_{k-1}| of the previous step (nullptr for the first): |u_k| <= 2 max |u_{k-1}|, so the TMA ring is
+// taken when that bound is below 1, the wider non-TMA ring otherwise
+__global__ void __launch_bounds__(TILE_T, 4)
+svf_step_fwd_tma_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restrict__ in_all, float in_scale,
+                        float* __restrict__ out_all, const float* __restrict__ maxabs_prev, float* __restrict__ maxabs,
+                        int seg_len, IrsDims d) {
+    extern __shared__ __align__(128) float smem[];
+    const long long V = d.V();
+    const int tiles_x = (d.W + TILE_X - 1) / TILE_X, tiles_y = (d.H + TILE_Y - 1) / TILE_Y;
+    const int bx = blockIdx.x % tiles_x, by = (blockIdx.x / tiles_x) % tiles_y, bz = blockIdx.x / (tiles_x * tiles_y);
+    const int x0t = bx * TILE_X, y0t = by * TILE_Y, zs = bz * seg_len, ze = min(zs + seg_len, d.D);
+    const float* in = in_all + (size_t)blockIdx.y * 3 * V;
+    float* out = out_all + (size_t)blockIdx.y * 3 * V;
+    const bool small = maxabs_prev == nullptr || 2.f * __ldg(maxabs_prev) < 0.999f;
+    float m;
+    if (small) m = svf_fwd_tma_body<FWD_BW>(&tmap, in, in_scale, out, d, blockIdx.y, x0t, y0t, zs, ze, smem);
+    else m = svf_fwd_tile_body<2>(in, in_scale, out, d, x0t, y0t, zs, ze, smem);
+    block_max_to_global(m, maxabs);
+}
+
+// ---- adjoint step ------------------------------------------------------------------------------------------------------
+// Per source plane s the CTA first turns every source voxel of the tile + halo into a RECORD
+//     { cx, cy, wz_b * g_c  (b = 0..2, c = 0..2), - }            12 floats = three 128-bit shared-memory words
+// where (cx, cy, cz) = clamp(s + u(s)) - s is the source's sub-voxel offset, g = dL/du_{k+1}(s), and wz_b is its hat
+// weight onto the target plane whose index is congruent to b modulo 3 (planes s-1, s, s+1 in rotating order).  A target
+// then needs, per in-plane neighbour, three LDS.128, two weight ops, one product and five packed FMAs -- the z weights,
+// the border clamps and the products with g are paid once per source instead of nine times.  The nine accumulators
+// (3 target planes x 3 components) never move: the loop is unrolled by three and the plane that completes is selected
+// at compile time.
+constexpr int REC_F = 12;   // floats per record
+constexpr int BWD_NG = 3;   // ring slots of the incoming gradient: plane s and two in flight (slot = plane mod 3, static)
+
+struct BwdAcc {
+    float2 p[4];   // slots 0..7
+    float s8;      // slot 8        slot = 3 * bank + component
+    __device__ __forceinline__ void clear() {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) p[i] = make_float2(0.f, 0.f);
+        s8 = 0.f;
+    }
+    template <int I> __device__ __forceinline__ float& slot() {
+        static_assert(I >= 0 && I <= 8, "slot");
+        if constexpr (I == 8) return s8;
+        else if constexpr (I & 1) return p[I >> 1].y;
+        else return p[I >> 1].x;
+    }
+};
+
+template <int OX>
+__device__ __forceinline__ float hat_small(float c) {   // |c| < 1; weight of a source at offset OX onto the target column
+    return OX < 0 ? fmaxf(c, 0.f) : (OX > 0 ? fmaxf(-c, 0.f) : 1.f - fabsf(c));
+}
+
+struct BwdTmaCtx {
+    const CUtensorMap *tmap_u, *tmap_g;
+    float *U, *G, *REC;
+    int* row_nz;          // [2][TMA_EY]
+    uint64_t *bar_u, *bar_g;
+    float in_scale, out_scale;
+    IrsDims d;
+    int x0t, y0t, zs, ze, chain;
+    float* g;
+};
+
+template <int BW>
+__device__ __forceinline__ void svf_bwd_tma_body(const BwdTmaCtx& c) {
+    using RG = TmaRing<BW>;
+    const int tid = threadIdx.x;
+    const IrsDims d = c.d;
+    const int lx = tid % TILE_X, ly = tid / TILE_X, x = c.x0t + lx, y = c.y0t + ly;
+    const bool active = x < d.W && y < d.H;
+    const int lc = (ly + 1) * BW + lx + TMA_XO;     // own voxel inside a plane box
+    const int lr = (ly + 1) * TMA_EX + lx + 1;      // own record
+    const float xf = (float)x, yf = (float)y;
+    const float xmax = (float)(d.W - 1), ymax = (float)(d.H - 1), zmax = (float)(d.D - 1);
+    const int Vi = (int)d.V(), HW = d.H * d.W;
+    const int zs = c.zs, ze = c.ze;
+    const int s_first = zs - 1, n_it = (ze - zs) + 2;   // source planes zs-1 .. ze
+    // ring sequence numbers: U plane p -> p - (zs - 2);  G plane p -> p - (zs - 1)
+    const int n_u = n_it + 2, n_g = n_it;
+
+    // the (up to two) records this thread produces per plane
+    int rec_e[2], rec_po[2], rec_row[2];
+    float rec_lox[2], rec_hix[2], rec_loy[2], rec_hiy[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const int e = tid + k * TILE_T;
+        const int ey = e / TMA_EX, ex = e - ey * TMA_EX;
+        rec_e[k] = e < TMA_EX * TMA_EY ? e : -1;
+        rec_po[k] = ey * BW + ex + (TMA_XO - 1);
+        rec_row[k] = ey;
+        const float gx = (float)(c.x0t - 1 + ex), gy = (float)(c.y0t - 1 + ey);
+        rec_lox[k] = -gx; rec_hix[k] = xmax - gx; rec_loy[k] = -gy; rec_hiy[k] = ymax - gy;
+    }
+
+    if (tid == 0) {
+#pragma unroll
+        for (int i = 0; i < TMA_NS; ++i) irs_mbar_init(&c.bar_u[i], 1);
+#pragma unroll
+        for (int i = 0; i < BWD_NG; ++i) irs_mbar_init(&c.bar_g[i], 1);
+        irs_mbar_fence_init();
+    }
+    if (tid < 2 * TMA_EY) c.row_nz[tid] = 0;
+    __syncthreads();
+    if (tid == 0) {
+        for (int q = 0; q < TMA_NS && q < n_u; ++q) {
+            irs_mbar_expect_tx(&c.bar_u[q], RG::BYTES);
+            irs_tma_load_plane(c.U + q * RG::SS, c.tmap_u, &c.bar_u[q], c.x0t - TMA_XO, c.y0t - 1, zs - 2 + q, 3 * c.chain);
+        }
+        for (int q = 0; q < BWD_NG && q < n_g; ++q) {
+            irs_mbar_expect_tx(&c.bar_g[q], RG::BYTES);
+            irs_tma_load_plane(c.G + q * RG::SS, c.tmap_g, &c.bar_g[q], c.x0t - TMA_XO, c.y0t - 1, zs - 1 + q, 3 * c.chain);
+        }
+    }
+
+    BwdAcc acc;
+    acc.clear();
+    int gi = ((s_first - 1) * d.H + y) * d.W + x;   // index of target (x, y, s-1)
+    irs_mbar_wait(&c.bar_u[0], 0);
+    irs_mbar_wait(&c.bar_u[1], 0);
+
+    // one source plane; M = (s - s_first) mod 3: target plane s -> bank M, s+1 -> bank M+1, s-1 -> bank M+2 (mod 3)
+    auto iteration = [&](auto m_tag, int it) {
+        constexpr int M = decltype(m_tag)::value;
+        constexpr int B0 = M, BP = (M + 1) % 3, BM = (M + 2) % 3;
+        const int s = s_first + it, cur = it & 1;
+        irs_mbar_wait(&c.bar_u[(it + 2) & 3], ((it + 2) >> 2) & 1);   // U plane s+1
+        irs_mbar_wait(&c.bar_g[M], (it / 3) & 1);                     // G plane s (ring of 3: slot = it mod 3 = M)
+        const float* Us = c.U + ((it + 1) & 3) * RG::SS;              // U plane s
+        const float* Gs = c.G + M * RG::SS;
+        const bool s_in = s >= 0 && s < d.D;
+        // ---- records of source plane s ----
+        if (s_in) {
+            const float sf = (float)s;
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                if (rec_e[k] < 0) continue;
+                const int po = rec_po[k];
+                const float g0 = Gs[po], g1 = Gs[RG::CS + po], g2 = Gs[2 * RG::CS + po];
+                const float cx = irs_clampf(Us[po] * c.in_scale, rec_lox[k], rec_hix[k]);
+                const float cy = irs_clampf(Us[RG::CS + po] * c.in_scale, rec_loy[k], rec_hiy[k]);
+                const float cz = irs_clampf(Us[2 * RG::CS + po] * c.in_scale, -sf, zmax - sf);
+                const float wm = fmaxf(-cz, 0.f), w0 = 1.f - fabsf(cz), wp = fmaxf(cz, 0.f);
+                float wb[3];
+                wb[B0] = w0; wb[BP] = wp; wb[BM] = wm;
+                float4* r = reinterpret_cast<float4*>(c.REC + rec_e[k] * REC_F);
+                r[0] = make_float4(cx, cy, wb[0] * g0, wb[0] * g1);
+                r[1] = make_float4(wb[0] * g2, wb[1] * g0, wb[1] * g1, wb[1] * g2);
+                r[2] = make_float4(wb[2] * g0, wb[2] * g1, wb[2] * g2, 0.f);
+                if (g0 != 0.f || g1 != 0.f || g2 != 0.f) c.row_nz[cur * TMA_EY + rec_row[k]] = 1;
+            }
+        }
+        __syncthreads();
+        if (tid < TMA_EY) c.row_nz[(cur ^ 1) * TMA_EY + tid] = 0;   // read last in the previous iteration
+        if (active && s_in) {
+            // ---- interpolation transpose: 9 in-plane neighbours x 3 target planes ----
+            const int* nz = c.row_nz + cur * TMA_EY + ly;
+            auto source_row = [&](auto oy_tag) {
+                constexpr int OY = decltype(oy_tag)::value;
+                auto source = [&](auto ox_tag) {
+                    constexpr int OX = decltype(ox_tag)::value;
+                    const float4* r = reinterpret_cast<const float4*>(c.REC + (lr + OY * TMA_EX + OX) * REC_F);
+                    const float4 r0 = r[0], r1 = r[1], r2 = r[2];
+                    const float w = hat_small<OX>(r0.x) * hat_small<OY>(r0.y);
+                    const float2 ww = make_float2(w, w);
+                    acc.p[0] = ffma2(ww, make_float2(r0.z, r0.w), acc.p[0]);
+                    acc.p[1] = ffma2(ww, make_float2(r1.x, r1.y), acc.p[1]);
+                    acc.p[2] = ffma2(ww, make_float2(r1.z, r1.w), acc.p[2]);
+                    acc.p[3] = ffma2(ww, make_float2(r2.x, r2.y), acc.p[3]);
+                    acc.s8 = fmaf(w, r2.z, acc.s8);
+                };
+                if (nz[OY + 1] != 0) {   // a source row without gradient contributes nothing (warp-uniform)
+                    source(std::integral_constant<int, -1>{});
+                    source(std::integral_constant<int, 0>{});
+                    source(std::integral_constant<int, 1>{});
+                }
+            };
+            source_row(std::integral_constant<int, -1>{});
+            source_row(std::integral_constant<int, 0>{});
+            source_row(std::integral_constant<int, 1>{});
+            // ---- direct + position term of target (x, y, s) ----
+            if (s >= zs && s < ze && nz[1] != 0) {
+                const float g0 = Gs[lc], g1 = Gs[RG::CS + lc], g2 = Gs[2 * RG::CS + lc];
+                float px = xf + Us[lc] * c.in_scale, py = yf + Us[RG::CS + lc] * c.in_scale,
+                      pz = (float)s + Us[2 * RG::CS + lc] * c.in_scale;
+                const float mx = irs_inside(px, d.W) * c.in_scale, my = irs_inside(py, d.H) * c.in_scale,
+                            mz = irs_inside(pz, d.D) * c.in_scale;
+                px = irs_clampf(px, 0.f, xmax); py = irs_clampf(py, 0.f, ymax); pz = irs_clampf(pz, 0.f, zmax);
+                int i000, sz;
+                float fx, fy, fz, jx, jy, jz;
+                tma_ring_cell<BW>(px, py, pz, c.x0t, c.y0t, s, it + 1, i000, sz, fx, fy, fz);
+                ring_interp_grad_dot<BW>(c.U, RG::CS, i000, sz, g0, g1, g2, fx, fy, fz, jx, jy, jz);
+                acc.template slot<3 * B0 + 0>() += g0 + mx * jx;
+                acc.template slot<3 * B0 + 1>() += g1 + my * jy;
+                acc.template slot<3 * B0 + 2>() += g2 + mz * jz;
+            }
+        }
+        // ---- target plane s-1 is complete ----
+        if (active && s - 1 >= zs && s - 1 < ze) {
+            c.g[gi] = acc.template slot<3 * BM + 0>() * c.out_scale;
+            c.g[Vi + gi] = acc.template slot<3 * BM + 1>() * c.out_scale;
+            c.g[2 * Vi + gi] = acc.template slot<3 * BM + 2>() * c.out_scale;
+        }
+        acc.template slot<3 * BM + 0>() = 0.f;
+        acc.template slot<3 * BM + 1>() = 0.f;
+        acc.template slot<3 * BM + 2>() = 0.f;
+        gi += HW;
+        __syncthreads();   // U plane s-1, G plane s and the records are free
+        if (tid == 0) {
+            if (it + 4 < n_u) {
+                irs_mbar_expect_tx(&c.bar_u[it & 3], RG::BYTES);
+                irs_tma_load_plane(c.U + (it & 3) * RG::SS, c.tmap_u, &c.bar_u[it & 3], c.x0t - TMA_XO, c.y0t - 1,
+                                   zs + 2 + it, 3 * c.chain);
+            }
+            if (it + BWD_NG < n_g) {
+                irs_mbar_expect_tx(&c.bar_g[M], RG::BYTES);
+                irs_tma_load_plane(c.G + M * RG::SS, c.tmap_g, &c.bar_g[M], c.x0t - TMA_XO, c.y0t - 1, zs + 2 + it,
+                                   3 * c.chain);
+            }
+        }
+    };
+
+    for (int it = 0; it < n_it; it += 3) {
+        iteration(std::integral_constant<int, 0>{}, it);
+        if (it + 1 < n_it) iteration(std::integral_constant<int, 1>{}, it + 1);
+        if (it + 2 < n_it) iteration(std::integral_constant<int, 2>{}, it + 2);
+    }
+}
+
+constexpr int BWD_BW = 40;
+constexpr size_t svf_bwd_tma_smem() {
+    return sizeof(float) * ((TMA_NS + BWD_NG) * TmaRing<BWD_BW>::SS + TMA_EX * TMA_EY * REC_F) + 8 * (TMA_NS + BWD_NG) +
+           4 * 2 * TMA_EY + 8;
+}
+
+__global__ void __launch_bounds__(TILE_T, 4)
+svf_step_bwd_tma_kernel(const __grid_constant__ CUtensorMap tmap_u, const __grid_constant__ CUtensorMap tmap_g,
+                        const float* __restrict__ in, float in_scale, const float* __restrict__ gp_all,
+                        float* __restrict__ g_all, const float* __restrict__ maxabs, int radius_max, float out_scale,
+                        int seg_len, IrsDims d) {
+    extern __shared__ __align__(128) float smem[];
+    const int R = svf_gather_radius(__ldg(maxabs));
+    const long long V = d.V();
+    const size_t off = (size_t)blockIdx.y * 3 * V;
+    const int tiles_x = (d.W + TILE_X - 1) / TILE_X, tiles_y = (d.H + TILE_Y - 1) / TILE_Y;
+    const int bx = blockIdx.x % tiles_x, by = (blockIdx.x / tiles_x) % tiles_y, bz = blockIdx.x / (tiles_x * tiles_y);
+    const int x0t = bx * TILE_X, y0t = by * TILE_Y, zs = bz * seg_len, ze = min(zs + seg_len, d.D);
+    if (R == 1 && R <= radius_max) {
+        using RG = TmaRing<BWD_BW>;
+        BwdTmaCtx c;
+        c.tmap_u = &tmap_u; c.tmap_g = &tmap_g;
+        c.U = smem;
+        c.G = smem + TMA_NS * RG::SS;
+        c.REC = smem + (TMA_NS + BWD_NG) * RG::SS;
+        c.bar_u = reinterpret_cast<uint64_t*>(c.REC + TMA_EX * TMA_EY * REC_F);
+        c.bar_g = c.bar_u + TMA_NS;
+        c.row_nz = reinterpret_cast<int*>(c.bar_g + BWD_NG);
+        c.in_scale = in_scale; c.out_scale = out_scale; c.d = d;
+        c.x0t = x0t; c.y0t = y0t; c.zs = zs; c.ze = ze; c.chain = blockIdx.y;
+        c.g = g_all + off;
+        svf_bwd_tma_body<BWD_BW>(c);
+    } else {
+        svf_bwd_tile_dispatch_cold(R, in + off, in_scale, gp_all + off, g_all + off, radius_max, out_scale, d, x0t, y0t, zs, ze,
+                                   smem);
     }
 }
 
@@ -521,16 +924,40 @@ static int resident_ctas(K kernel, size_t smem) {
 
 }  // namespace
 
+static size_t zmax(size_t a, size_t b) { return a > b ? a : b; }
+
 int irs_launch_svf_fwd(const float* v, float* hist, float* maxabs, int n_steps, int C, IrsDims d, cudaStream_t st) {
     const size_t F = (size_t)C * 3 * d.V();
     cudaError_t e = cudaMemsetAsync(maxabs, 0, sizeof(float) * n_steps, st);
     if (e != cudaSuccess) return (int)e;
     const float scale0 = 1.0f / (float)(1 << n_steps);
     constexpr int RF = 2;
+    const int tiles = ((d.W + TILE_X - 1) / TILE_X) * ((d.H + TILE_Y - 1) / TILE_Y);
+    const bool tma = irs_tma_field_ok(v, d.W) && irs_tma_field_ok(hist, d.W) && (F % 4) == 0;
+    if (tma) {
+        const size_t smem = zmax(svf_fwd_tma_smem(), svf_fwd_tile_smem(RF));
+        static bool configured = false;
+        if (!configured) {
+            e = cudaFuncSetAttribute(svf_step_fwd_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return (int)e;
+            configured = true;
+        }
+        static int slots = 0;
+        if (slots == 0) slots = resident_ctas(svf_step_fwd_tma_kernel, smem);
+        const int seg_len = svf_seg_len(d, C, slots, 3);
+        dim3 tgrid(tiles * ((d.D + seg_len - 1) / seg_len), C);
+        for (int k = 0; k < n_steps; ++k) {
+            const float* in = (k == 0) ? v : hist + (size_t)(k - 1) * F;
+            CUtensorMap map;
+            if (irs_tma_encode_field(&map, in, 3 * C, d.D, d.H, d.W, FWD_BW, TMA_EY) != 0) return IRS_ERR_UNSUPPORTED;
+            svf_step_fwd_tma_kernel<<<tgrid, TILE_T, smem, st>>>(map, in, k == 0 ? scale0 : 1.0f, hist + (size_t)k * F,
+                                                                 k == 0 ? nullptr : maxabs + k - 1, maxabs + k, seg_len, d);
+        }
+        return (int)cudaGetLastError();
+    }
     static int slots = 0;
     if (slots == 0) slots = resident_ctas(svf_step_fwd_tile_kernel<RF>, svf_fwd_tile_smem(RF));
     const int seg_len = svf_seg_len(d, C, slots, 2 * RF + 2);
-    const int tiles = ((d.W + TILE_X - 1) / TILE_X) * ((d.H + TILE_Y - 1) / TILE_Y);
     dim3 tgrid(tiles * ((d.D + seg_len - 1) / seg_len), C);
     for (int k = 0; k < n_steps; ++k) {
         const float* in = (k == 0) ? v : hist + (size_t)(k - 1) * F;
@@ -552,21 +979,40 @@ int irs_launch_svf_bwd(const float* v, const float* hist, const float* maxabs, f
         configured = true;
     }
     const int tiles = ((d.W + TILE_X - 1) / TILE_X) * ((d.H + TILE_Y - 1) / TILE_Y);
-    static int slots = 0;
-    if (slots == 0) slots = resident_ctas(svf_step_bwd_tile_kernel, smem);
-    const int seg_len = svf_seg_len(d, C, slots, 6);
-    const int nseg = (d.D + seg_len - 1) / seg_len;
-    dim3 tgrid(tiles * nseg, C);
     const long long vblocks = (d.V() + 255) / 256;
     dim3 vgrid((unsigned)(vblocks < 1184 ? vblocks : 1184), 1);   // persistent: see svf_step_bwd_scatter_kernel
+    const bool tma = irs_tma_field_ok(v, d.W) && irs_tma_field_ok(hist, d.W) && irs_tma_field_ok(g_u, d.W) &&
+                     irs_tma_field_ok(g_work, d.W) && (F % 4) == 0;
+    const size_t smem_tma = zmax(svf_bwd_tma_smem(), smem);
+    static bool configured_tma = false;
+    if (tma && !configured_tma) {
+        cudaError_t e = cudaFuncSetAttribute(svf_step_bwd_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tma);
+        if (e != cudaSuccess) return (int)e;
+        configured_tma = true;
+    }
+    static int slots = 0, slots_tma = 0;
+    if (slots == 0) slots = resident_ctas(svf_step_bwd_tile_kernel, smem);
+    if (tma && slots_tma == 0) slots_tma = resident_ctas(svf_step_bwd_tma_kernel, smem_tma);
+    const int seg_len = tma ? svf_seg_len(d, C, slots_tma, 4) : svf_seg_len(d, C, slots, 6);
+    const int nseg = (d.D + seg_len - 1) / seg_len;
+    dim3 tgrid(tiles * nseg, C);
     // ping-pong between g_work and the caller's g_u buffer (g_u is only read by the first adjoint step)
     const float* gp = g_u;
     for (int k = n_steps - 1; k >= 0; --k) {
         const float* in = (k == 0) ? v : hist + (size_t)(k - 1) * F;
         float* out = (k == 0) ? g_v : (((n_steps - 1 - k) & 1) ? g_u : g_work);
         const float in_scale = (k == 0) ? scale0 : 1.0f;
-        svf_step_bwd_tile_kernel<<<tgrid, TILE_T, smem, st>>>(in, in_scale, gp, out, maxabs + k, gather_radius_max,
-                                                                  in_scale, seg_len, d);
+        if (tma) {
+            CUtensorMap map_u, map_g;
+            if (irs_tma_encode_field(&map_u, in, 3 * C, d.D, d.H, d.W, BWD_BW, TMA_EY) != 0 ||
+                irs_tma_encode_field(&map_g, gp, 3 * C, d.D, d.H, d.W, BWD_BW, TMA_EY) != 0)
+                return IRS_ERR_UNSUPPORTED;
+            svf_step_bwd_tma_kernel<<<tgrid, TILE_T, smem_tma, st>>>(map_u, map_g, in, in_scale, gp, out, maxabs + k,
+                                                                     gather_radius_max, in_scale, seg_len, d);
+        } else {
+            svf_step_bwd_tile_kernel<<<tgrid, TILE_T, smem, st>>>(in, in_scale, gp, out, maxabs + k, gather_radius_max,
+                                                                      in_scale, seg_len, d);
+        }
         svf_step_bwd_scatter_kernel<<<vgrid, 256, 0, st>>>(in, in_scale, gp, out, maxabs + k, gather_radius_max,
                                                            in_scale, C, d);
         gp = out;

@@ -1,0 +1,15 @@
+#!/bin/bash
+# one GPU-box visit: tests, bench, ncu launch list, full captures of the SVF kernels (outputs under gpurun_out/)
+set -x
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,clocks.max.sm --format=csv,noheader > gpurun_out/gpu.txt
+python -m pytest tests -m gpu -x -q > gpurun_out/t_all.log 2>&1; echo "pytest exit $?" >> gpurun_out/t_all.log
+tail -3 gpurun_out/t_all.log
+python bench.py > gpurun_out/bench_default.log 2>&1; echo "exit $?" >> gpurun_out/bench_default.log
+tail -2 gpurun_out/bench_default.log | cut -c1-1500
+if [ "$1" != "noprof" ]; then
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
+    python bench.py --steps 3 --warmup 3 --no-graph --no-cpu-baseline > gpurun_out/ncu.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:svf_step -s 96 -c 26 -o gpurun_out/prof_svf -f \
+    python bench.py --steps 3 --warmup 3 --no-graph --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
+fi
