@@ -25,6 +25,24 @@
         if (e__ != cudaSuccess) return (int)e__;       \
     } while (0)
 
+// Launch with programmatic stream serialisation (PDL): the kernel may be scheduled while its predecessor in the stream
+// is still draining, so it MUST call irs_pdl_wait() (irs_tma.cuh) before it touches anything a predecessor wrote or reads.
+template <typename... KArgs, typename... Args>
+inline cudaError_t irs_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                  Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 #define IRS_TRY(expr)                  \
     do {                               \
         int r__ = (expr);              \

@@ -52,6 +52,8 @@ __global__ void __launch_bounds__(256)
 svf_step_bwd_scatter_kernel(const float* __restrict__ in, float in_scale, const float* __restrict__ gp_all,
                             float* __restrict__ g_all, const float* __restrict__ maxabs, int radius_max,
                             float out_scale, int C, IrsDims d) {
+    irs_pdl_wait();
+    irs_pdl_launch_dependents();
     const int R = (int)floorf(__ldg(maxabs) + 1e-3f) + 1;   // = svf_gather_radius
     if (R <= radius_max) return;
     const long long V = d.V();
@@ -288,6 +290,8 @@ __global__ void __launch_bounds__(TILE_T)
 svf_step_fwd_tile_kernel(const float* __restrict__ in_all, float in_scale, float* __restrict__ out_all,
                          float* __restrict__ maxabs, int seg_len, IrsDims d) {
     extern __shared__ __align__(128) float smem[];
+    irs_pdl_wait();
+    irs_pdl_launch_dependents();
     const long long V = d.V();
     const int tiles_x = (d.W + TILE_X - 1) / TILE_X, tiles_y = (d.H + TILE_Y - 1) / TILE_Y;
     const int bx = blockIdx.x % tiles_x, by = (blockIdx.x / tiles_x) % tiles_y, bz = blockIdx.x / (tiles_x * tiles_y);
@@ -483,6 +487,8 @@ svf_step_bwd_tile_kernel(const float* __restrict__ in, float in_scale, const flo
                          float* __restrict__ g_all, const float* __restrict__ maxabs, int radius_max, float out_scale,
                          int seg_len, IrsDims d) {
     extern __shared__ __align__(128) float smem[];
+    irs_pdl_wait();
+    irs_pdl_launch_dependents();
     const int R = svf_gather_radius(__ldg(maxabs));
     const long long V = d.V();
     const size_t off = (size_t)blockIdx.y * 3 * V;
@@ -599,6 +605,8 @@ svf_step_fwd_tma_kernel(const __grid_constant__ CUtensorMap tmap, const float* _
                         float* __restrict__ out_all, const float* __restrict__ maxabs_prev, float* __restrict__ maxabs,
                         int seg_len, IrsDims d) {
     extern __shared__ __align__(128) float smem[];
+    irs_pdl_wait();
+    irs_pdl_launch_dependents();
     const long long V = d.V();
     const int tiles_x = (d.W + TILE_X - 1) / TILE_X, tiles_y = (d.H + TILE_Y - 1) / TILE_Y;
     const int bx = blockIdx.x % tiles_x, by = (blockIdx.x / tiles_x) % tiles_y, bz = blockIdx.x / (tiles_x * tiles_y);
@@ -614,29 +622,23 @@ svf_step_fwd_tma_kernel(const __grid_constant__ CUtensorMap tmap, const float* _
 
 // ---- adjoint step ------------------------------------------------------------------------------------------------------
 // Per source plane s the CTA first turns every source voxel of the tile + halo into a RECORD
-//     { cx, cy, wz_b * g_c  (b = 0..2, c = 0..2), - }            12 floats = three 128-bit shared-memory words
+//     { cx, cy, g0, g1 } { g2, wz_0, wz_1, wz_2 }                 two 128-bit shared-memory words (in two arrays)
 // where (cx, cy, cz) = clamp(s + u(s)) - s is the source's sub-voxel offset, g = dL/du_{k+1}(s), and wz_b is its hat
 // weight onto the target plane whose index is congruent to b modulo 3 (planes s-1, s, s+1 in rotating order).  A target
-// then needs, per in-plane neighbour, three LDS.128, two weight ops, one product and five packed FMAs -- the z weights,
-// the border clamps and the products with g are paid once per source instead of nine times.  The nine accumulators
-// (3 target planes x 3 components) never move: the loop is unrolled by three and the plane that completes is selected
-// at compile time.
-constexpr int REC_F = 12;   // floats per record
+// then needs, per in-plane neighbour, two LDS.128, two weight ops, four products and six FMAs (three of them packed) -- the
+// z weights and the border clamps are paid once per source instead of nine times.  The nine accumulators (3 target
+// planes x 3 components) never move: the loop is unrolled by three and the plane that completes is selected at compile
+// time.  (A 12-float record holding the nine products wz_b * g_c saves four instructions per neighbour but costs a third
+// LDS.128: measured shared-memory bound, 61 % of the LSU data pipe vs 50 % issue.)
+constexpr int REC_F = 8;    // floats per record
 constexpr int BWD_NG = 3;   // ring slots of the incoming gradient: plane s and two in flight (slot = plane mod 3, static)
 
 struct BwdAcc {
-    float2 p[4];   // slots 0..7
-    float s8;      // slot 8        slot = 3 * bank + component
+    float2 xy[3];   // components x, y of bank b (packed: updated with FFMA2)
+    float z[3];     // component z of bank b
     __device__ __forceinline__ void clear() {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) p[i] = make_float2(0.f, 0.f);
-        s8 = 0.f;
-    }
-    template <int I> __device__ __forceinline__ float& slot() {
-        static_assert(I >= 0 && I <= 8, "slot");
-        if constexpr (I == 8) return s8;
-        else if constexpr (I & 1) return p[I >> 1].y;
-        else return p[I >> 1].x;
+        for (int i = 0; i < 3; ++i) { xy[i] = make_float2(0.f, 0.f); z[i] = 0.f; }
     }
 };
 
@@ -737,10 +739,9 @@ __device__ __forceinline__ void svf_bwd_tma_body(const BwdTmaCtx& c) {
                 const float wm = fmaxf(-cz, 0.f), w0 = 1.f - fabsf(cz), wp = fmaxf(cz, 0.f);
                 float wb[3];
                 wb[B0] = w0; wb[BP] = wp; wb[BM] = wm;
-                float4* r = reinterpret_cast<float4*>(c.REC + rec_e[k] * REC_F);
-                r[0] = make_float4(cx, cy, wb[0] * g0, wb[0] * g1);
-                r[1] = make_float4(wb[0] * g2, wb[1] * g0, wb[1] * g1, wb[1] * g2);
-                r[2] = make_float4(wb[2] * g0, wb[2] * g1, wb[2] * g2, 0.f);
+                float4* r = reinterpret_cast<float4*>(c.REC) + rec_e[k];   // two planes of float4: conflict-free LDS.128
+                r[0] = make_float4(cx, cy, g0, g1);
+                r[TMA_EX * TMA_EY] = make_float4(g2, wb[0], wb[1], wb[2]);
                 if (g0 != 0.f || g1 != 0.f || g2 != 0.f) c.row_nz[cur * TMA_EY + rec_row[k]] = 1;
             }
         }
@@ -753,15 +754,14 @@ __device__ __forceinline__ void svf_bwd_tma_body(const BwdTmaCtx& c) {
                 constexpr int OY = decltype(oy_tag)::value;
                 auto source = [&](auto ox_tag) {
                     constexpr int OX = decltype(ox_tag)::value;
-                    const float4* r = reinterpret_cast<const float4*>(c.REC + (lr + OY * TMA_EX + OX) * REC_F);
-                    const float4 r0 = r[0], r1 = r[1], r2 = r[2];
+                    const float4* r = reinterpret_cast<const float4*>(c.REC) + (lr + OY * TMA_EX + OX);
+                    const float4 r0 = r[0], r1 = r[TMA_EX * TMA_EY];
                     const float w = hat_small<OX>(r0.x) * hat_small<OY>(r0.y);
-                    const float2 ww = make_float2(w, w);
-                    acc.p[0] = ffma2(ww, make_float2(r0.z, r0.w), acc.p[0]);
-                    acc.p[1] = ffma2(ww, make_float2(r1.x, r1.y), acc.p[1]);
-                    acc.p[2] = ffma2(ww, make_float2(r1.z, r1.w), acc.p[2]);
-                    acc.p[3] = ffma2(ww, make_float2(r2.x, r2.y), acc.p[3]);
-                    acc.s8 = fmaf(w, r2.z, acc.s8);
+                    const float w0 = w * r1.y, w1 = w * r1.z, w2 = w * r1.w;
+                    const float2 g01 = make_float2(r0.z, r0.w);
+                    acc.xy[0] = ffma2(make_float2(w0, w0), g01, acc.xy[0]); acc.z[0] = fmaf(w0, r1.x, acc.z[0]);
+                    acc.xy[1] = ffma2(make_float2(w1, w1), g01, acc.xy[1]); acc.z[1] = fmaf(w1, r1.x, acc.z[1]);
+                    acc.xy[2] = ffma2(make_float2(w2, w2), g01, acc.xy[2]); acc.z[2] = fmaf(w2, r1.x, acc.z[2]);
                 };
                 if (nz[OY + 1] != 0) {   // a source row without gradient contributes nothing (warp-uniform)
                     source(std::integral_constant<int, -1>{});
@@ -784,20 +784,19 @@ __device__ __forceinline__ void svf_bwd_tma_body(const BwdTmaCtx& c) {
                 float fx, fy, fz, jx, jy, jz;
                 tma_ring_cell<BW>(px, py, pz, c.x0t, c.y0t, s, it + 1, i000, sz, fx, fy, fz);
                 ring_interp_grad_dot<BW>(c.U, RG::CS, i000, sz, g0, g1, g2, fx, fy, fz, jx, jy, jz);
-                acc.template slot<3 * B0 + 0>() += g0 + mx * jx;
-                acc.template slot<3 * B0 + 1>() += g1 + my * jy;
-                acc.template slot<3 * B0 + 2>() += g2 + mz * jz;
+                acc.xy[B0].x += g0 + mx * jx;
+                acc.xy[B0].y += g1 + my * jy;
+                acc.z[B0] += g2 + mz * jz;
             }
         }
         // ---- target plane s-1 is complete ----
         if (active && s - 1 >= zs && s - 1 < ze) {
-            c.g[gi] = acc.template slot<3 * BM + 0>() * c.out_scale;
-            c.g[Vi + gi] = acc.template slot<3 * BM + 1>() * c.out_scale;
-            c.g[2 * Vi + gi] = acc.template slot<3 * BM + 2>() * c.out_scale;
+            c.g[gi] = acc.xy[BM].x * c.out_scale;
+            c.g[Vi + gi] = acc.xy[BM].y * c.out_scale;
+            c.g[2 * Vi + gi] = acc.z[BM] * c.out_scale;
         }
-        acc.template slot<3 * BM + 0>() = 0.f;
-        acc.template slot<3 * BM + 1>() = 0.f;
-        acc.template slot<3 * BM + 2>() = 0.f;
+        acc.xy[BM] = make_float2(0.f, 0.f);
+        acc.z[BM] = 0.f;
         gi += HW;
         __syncthreads();   // U plane s-1, G plane s and the records are free
         if (tid == 0) {
@@ -833,6 +832,8 @@ svf_step_bwd_tma_kernel(const __grid_constant__ CUtensorMap tmap_u, const __grid
                         float* __restrict__ g_all, const float* __restrict__ maxabs, int radius_max, float out_scale,
                         int seg_len, IrsDims d) {
     extern __shared__ __align__(128) float smem[];
+    irs_pdl_wait();
+    irs_pdl_launch_dependents();
     const int R = svf_gather_radius(__ldg(maxabs));
     const long long V = d.V();
     const size_t off = (size_t)blockIdx.y * 3 * V;
@@ -868,8 +869,10 @@ constexpr size_t svf_fwd_tile_smem(int R) {
 
 // z-segment length: the (tiles x segments x chains) CTAs should fill whole waves of the 148 SMs, while each segment
 // pays `halo` extra plane-iterations.  Picks the segment count with the lowest modelled time.
-static int svf_seg_len(IrsDims d, int C, int slots, int halo) {
-    if (const char* e = getenv("IRS_SVF_SEG")) {   // development override
+// `dynamic`: the TMA kernels' CTAs differ in cost (zero-gradient rows are skipped), so more CTAs than resident slots let
+// the hardware scheduler even the SMs out; measured at 128^3, one chain: 10 (adjoint) / 8 (forward) planes beat 15.
+static int svf_seg_len(IrsDims d, int C, int slots, int halo, const char* env_name = "IRS_SVF_SEG", bool dynamic = false) {
+    if (const char* e = getenv(env_name)) {   // development override
         const int v = atoi(e);
         if (v >= 1) return v < d.D ? v : d.D;
     }
@@ -884,7 +887,8 @@ static int svf_seg_len(IrsDims d, int C, int slots, int halo) {
         const int nseg_eff = (d.D + len - 1) / len;
         const long long ctas = tiles * nseg_eff;
         const long long waves = (ctas + slots - 1) / slots;
-        const double cost = (double)waves * (len + halo);
+        const double fill = (double)ctas / slots;
+        const double cost = dynamic ? ((fill > 1.0 ? fill : 1.0) + 0.35) * (len + halo) : (double)waves * (len + halo);
         if (cost < best_cost - 1e-9) { best_cost = cost; best_len = len; }
     }
     return best_len;
@@ -944,14 +948,15 @@ int irs_launch_svf_fwd(const float* v, float* hist, float* maxabs, int n_steps, 
         }
         static int slots = 0;
         if (slots == 0) slots = resident_ctas(svf_step_fwd_tma_kernel, smem);
-        const int seg_len = svf_seg_len(d, C, slots, 3);
+        const int seg_len = svf_seg_len(d, C, slots, 3, "IRS_SVF_SEG_FWD", true);
         dim3 tgrid(tiles * ((d.D + seg_len - 1) / seg_len), C);
         for (int k = 0; k < n_steps; ++k) {
             const float* in = (k == 0) ? v : hist + (size_t)(k - 1) * F;
             CUtensorMap map;
             if (irs_tma_encode_field(&map, in, 3 * C, d.D, d.H, d.W, FWD_BW, TMA_EY) != 0) return IRS_ERR_UNSUPPORTED;
-            svf_step_fwd_tma_kernel<<<tgrid, TILE_T, smem, st>>>(map, in, k == 0 ? scale0 : 1.0f, hist + (size_t)k * F,
-                                                                 k == 0 ? nullptr : maxabs + k - 1, maxabs + k, seg_len, d);
+            e = irs_launch_pdl(svf_step_fwd_tma_kernel, tgrid, dim3(TILE_T), smem, st, map, in, k == 0 ? scale0 : 1.0f,
+                               hist + (size_t)k * F, k == 0 ? nullptr : maxabs + k - 1, maxabs + k, seg_len, d);
+            if (e != cudaSuccess) return (int)e;
         }
         return (int)cudaGetLastError();
     }
@@ -961,8 +966,9 @@ int irs_launch_svf_fwd(const float* v, float* hist, float* maxabs, int n_steps, 
     dim3 tgrid(tiles * ((d.D + seg_len - 1) / seg_len), C);
     for (int k = 0; k < n_steps; ++k) {
         const float* in = (k == 0) ? v : hist + (size_t)(k - 1) * F;
-        svf_step_fwd_tile_kernel<RF><<<tgrid, TILE_T, svf_fwd_tile_smem(RF), st>>>(in, k == 0 ? scale0 : 1.0f,
-                                                                                 hist + (size_t)k * F, maxabs + k, seg_len, d);
+        e = irs_launch_pdl(svf_step_fwd_tile_kernel<RF>, tgrid, dim3(TILE_T), svf_fwd_tile_smem(RF), st, in,
+                           k == 0 ? scale0 : 1.0f, hist + (size_t)k * F, maxabs + k, seg_len, d);
+        if (e != cudaSuccess) return (int)e;
     }
     return (int)cudaGetLastError();
 }
@@ -993,11 +999,12 @@ int irs_launch_svf_bwd(const float* v, const float* hist, const float* maxabs, f
     static int slots = 0, slots_tma = 0;
     if (slots == 0) slots = resident_ctas(svf_step_bwd_tile_kernel, smem);
     if (tma && slots_tma == 0) slots_tma = resident_ctas(svf_step_bwd_tma_kernel, smem_tma);
-    const int seg_len = tma ? svf_seg_len(d, C, slots_tma, 4) : svf_seg_len(d, C, slots, 6);
+    const int seg_len = tma ? svf_seg_len(d, C, slots_tma, 4, "IRS_SVF_SEG_BWD", true) : svf_seg_len(d, C, slots, 6);
     const int nseg = (d.D + seg_len - 1) / seg_len;
     dim3 tgrid(tiles * nseg, C);
     // ping-pong between g_work and the caller's g_u buffer (g_u is only read by the first adjoint step)
     const float* gp = g_u;
+    cudaError_t le = cudaSuccess;
     for (int k = n_steps - 1; k >= 0; --k) {
         const float* in = (k == 0) ? v : hist + (size_t)(k - 1) * F;
         float* out = (k == 0) ? g_v : (((n_steps - 1 - k) & 1) ? g_u : g_work);
@@ -1007,14 +1014,16 @@ int irs_launch_svf_bwd(const float* v, const float* hist, const float* maxabs, f
             if (irs_tma_encode_field(&map_u, in, 3 * C, d.D, d.H, d.W, BWD_BW, TMA_EY) != 0 ||
                 irs_tma_encode_field(&map_g, gp, 3 * C, d.D, d.H, d.W, BWD_BW, TMA_EY) != 0)
                 return IRS_ERR_UNSUPPORTED;
-            svf_step_bwd_tma_kernel<<<tgrid, TILE_T, smem_tma, st>>>(map_u, map_g, in, in_scale, gp, out, maxabs + k,
-                                                                     gather_radius_max, in_scale, seg_len, d);
+            le = irs_launch_pdl(svf_step_bwd_tma_kernel, tgrid, dim3(TILE_T), smem_tma, st, map_u, map_g, in, in_scale, gp,
+                                out, maxabs + k, gather_radius_max, in_scale, seg_len, d);
         } else {
-            svf_step_bwd_tile_kernel<<<tgrid, TILE_T, smem, st>>>(in, in_scale, gp, out, maxabs + k, gather_radius_max,
-                                                                      in_scale, seg_len, d);
+            le = irs_launch_pdl(svf_step_bwd_tile_kernel, tgrid, dim3(TILE_T), smem, st, in, in_scale, gp, out, maxabs + k,
+                                gather_radius_max, in_scale, seg_len, d);
         }
-        svf_step_bwd_scatter_kernel<<<vgrid, 256, 0, st>>>(in, in_scale, gp, out, maxabs + k, gather_radius_max,
-                                                           in_scale, C, d);
+        if (le != cudaSuccess) return (int)le;
+        le = irs_launch_pdl(svf_step_bwd_scatter_kernel, vgrid, dim3(256), 0, st, in, in_scale, gp, (float*)out, maxabs + k,
+                            gather_radius_max, in_scale, C, d);
+        if (le != cudaSuccess) return (int)le;
         gp = out;
     }
     return (int)cudaGetLastError();
