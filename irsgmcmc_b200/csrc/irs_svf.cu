@@ -650,7 +650,7 @@ __device__ __forceinline__ float hat_small(float c) {   // |c| < 1; weight of a 
 struct BwdTmaCtx {
     const CUtensorMap *tmap_u, *tmap_g;
     float *U, *G, *REC;
-    int* row_nz;          // [2][TMA_EY]
+    int* row_nz;          // [3][TMA_EY]: "this source row has a non-zero gradient", per plane modulo 3
     uint64_t *bar_u, *bar_g;
     float in_scale, out_scale;
     IrsDims d;
@@ -696,7 +696,7 @@ __device__ __forceinline__ void svf_bwd_tma_body(const BwdTmaCtx& c) {
         for (int i = 0; i < BWD_NG; ++i) irs_mbar_init(&c.bar_g[i], 1);
         irs_mbar_fence_init();
     }
-    if (tid < 2 * TMA_EY) c.row_nz[tid] = 0;
+    if (tid < 3 * TMA_EY) c.row_nz[tid] = 0;
     __syncthreads();
     if (tid == 0) {
         for (int q = 0; q < TMA_NS && q < n_u; ++q) {
@@ -709,52 +709,70 @@ __device__ __forceinline__ void svf_bwd_tma_body(const BwdTmaCtx& c) {
         }
     }
 
+    // Records of source plane s_first + itp (its U and G planes must have landed) into record buffer itp & 1 and row
+    // flags itp mod 3.  MP = itp mod 3: target plane s -> bank MP, s+1 -> bank MP+1, s-1 -> bank MP+2 (mod 3).
+    auto produce = [&](auto m_tag, int itp) {
+        constexpr int MP = decltype(m_tag)::value;
+        constexpr int B0 = MP, BP = (MP + 1) % 3, BM = (MP + 2) % 3;
+        const int s = s_first + itp;
+        if (s < 0 || s >= d.D) return;   // nobody reads the records of a plane outside the volume
+        const float* Us = c.U + ((itp + 1) & 3) * RG::SS;
+        const float* Gs = c.G + MP * RG::SS;
+        float4* rec = reinterpret_cast<float4*>(c.REC) + (itp & 1) * (2 * TMA_EX * TMA_EY);
+        const float sf = (float)s;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            if (rec_e[k] < 0) continue;
+            const int po = rec_po[k];
+            const float g0 = Gs[po], g1 = Gs[RG::CS + po], g2 = Gs[2 * RG::CS + po];
+            const float cx = irs_clampf(Us[po] * c.in_scale, rec_lox[k], rec_hix[k]);
+            const float cy = irs_clampf(Us[RG::CS + po] * c.in_scale, rec_loy[k], rec_hiy[k]);
+            const float cz = irs_clampf(Us[2 * RG::CS + po] * c.in_scale, -sf, zmax - sf);
+            const float wm = fmaxf(-cz, 0.f), w0 = 1.f - fabsf(cz), wp = fmaxf(cz, 0.f);
+            float wb[3];
+            wb[B0] = w0; wb[BP] = wp; wb[BM] = wm;
+            float4* r = rec + rec_e[k];   // two arrays of float4: conflict-free LDS.128
+            r[0] = make_float4(cx, cy, g0, g1);
+            r[TMA_EX * TMA_EY] = make_float4(g2, wb[0], wb[1], wb[2]);
+            if (g0 != 0.f || g1 != 0.f || g2 != 0.f) c.row_nz[MP * TMA_EY + rec_row[k]] = 1;
+        }
+    };
+
     BwdAcc acc;
     acc.clear();
     int gi = ((s_first - 1) * d.H + y) * d.W + x;   // index of target (x, y, s-1)
     irs_mbar_wait(&c.bar_u[0], 0);
     irs_mbar_wait(&c.bar_u[1], 0);
+    irs_mbar_wait(&c.bar_g[0], 0);
+    produce(std::integral_constant<int, 0>{}, 0);
+    __syncthreads();
+    if (tid == 0 && BWD_NG < n_g) {   // G plane s_first has been turned into records: its slot takes sequence number 3
+        irs_mbar_expect_tx(&c.bar_g[0], RG::BYTES);
+        irs_tma_load_plane(c.G, c.tmap_g, &c.bar_g[0], c.x0t - TMA_XO, c.y0t - 1, zs - 1 + BWD_NG, 3 * c.chain);
+    }
 
-    // one source plane; M = (s - s_first) mod 3: target plane s -> bank M, s+1 -> bank M+1, s-1 -> bank M+2 (mod 3)
+    // one source plane; M = (s - s_first) mod 3
     auto iteration = [&](auto m_tag, int it) {
         constexpr int M = decltype(m_tag)::value;
         constexpr int B0 = M, BP = (M + 1) % 3, BM = (M + 2) % 3;
-        const int s = s_first + it, cur = it & 1;
+        const int s = s_first + it;
         irs_mbar_wait(&c.bar_u[(it + 2) & 3], ((it + 2) >> 2) & 1);   // U plane s+1
-        irs_mbar_wait(&c.bar_g[M], (it / 3) & 1);                     // G plane s (ring of 3: slot = it mod 3 = M)
-        const float* Us = c.U + ((it + 1) & 3) * RG::SS;              // U plane s
-        const float* Gs = c.G + M * RG::SS;
-        const bool s_in = s >= 0 && s < d.D;
-        // ---- records of source plane s ----
-        if (s_in) {
-            const float sf = (float)s;
-#pragma unroll
-            for (int k = 0; k < 2; ++k) {
-                if (rec_e[k] < 0) continue;
-                const int po = rec_po[k];
-                const float g0 = Gs[po], g1 = Gs[RG::CS + po], g2 = Gs[2 * RG::CS + po];
-                const float cx = irs_clampf(Us[po] * c.in_scale, rec_lox[k], rec_hix[k]);
-                const float cy = irs_clampf(Us[RG::CS + po] * c.in_scale, rec_loy[k], rec_hiy[k]);
-                const float cz = irs_clampf(Us[2 * RG::CS + po] * c.in_scale, -sf, zmax - sf);
-                const float wm = fmaxf(-cz, 0.f), w0 = 1.f - fabsf(cz), wp = fmaxf(cz, 0.f);
-                float wb[3];
-                wb[B0] = w0; wb[BP] = wp; wb[BM] = wm;
-                float4* r = reinterpret_cast<float4*>(c.REC) + rec_e[k];   // two planes of float4: conflict-free LDS.128
-                r[0] = make_float4(cx, cy, g0, g1);
-                r[TMA_EX * TMA_EY] = make_float4(g2, wb[0], wb[1], wb[2]);
-                if (g0 != 0.f || g1 != 0.f || g2 != 0.f) c.row_nz[cur * TMA_EY + rec_row[k]] = 1;
-            }
+        if (tid < TMA_EY) c.row_nz[BM * TMA_EY + tid] = 0;            // flags of plane s+2: last read in the previous iteration
+        if (it + 1 < n_it) {
+            irs_mbar_wait(&c.bar_g[BP], ((it + 1) / 3) & 1);          // G plane s+1 (ring of 3: slot = (it + 1) mod 3)
+            produce(std::integral_constant<int, BP>{}, it + 1);      // records of the NEXT plane: one barrier per plane
         }
-        __syncthreads();
-        if (tid < TMA_EY) c.row_nz[(cur ^ 1) * TMA_EY + tid] = 0;   // read last in the previous iteration
-        if (active && s_in) {
+        const float* Us = c.U + ((it + 1) & 3) * RG::SS;              // U plane s
+        const float4* rec = reinterpret_cast<const float4*>(c.REC) + (it & 1) * (2 * TMA_EX * TMA_EY);
+        if (active && s >= 0 && s < d.D) {
             // ---- interpolation transpose: 9 in-plane neighbours x 3 target planes ----
-            const int* nz = c.row_nz + cur * TMA_EY + ly;
+            const int* nz = c.row_nz + M * TMA_EY + ly;
+            float g0 = 0.f, g1 = 0.f, g2 = 0.f;   // the target's own incoming gradient (from its record)
             auto source_row = [&](auto oy_tag) {
                 constexpr int OY = decltype(oy_tag)::value;
                 auto source = [&](auto ox_tag) {
                     constexpr int OX = decltype(ox_tag)::value;
-                    const float4* r = reinterpret_cast<const float4*>(c.REC) + (lr + OY * TMA_EX + OX);
+                    const float4* r = rec + (lr + OY * TMA_EX + OX);
                     const float4 r0 = r[0], r1 = r[TMA_EX * TMA_EY];
                     const float w = hat_small<OX>(r0.x) * hat_small<OY>(r0.y);
                     const float w0 = w * r1.y, w1 = w * r1.z, w2 = w * r1.w;
@@ -762,6 +780,7 @@ __device__ __forceinline__ void svf_bwd_tma_body(const BwdTmaCtx& c) {
                     acc.xy[0] = ffma2(make_float2(w0, w0), g01, acc.xy[0]); acc.z[0] = fmaf(w0, r1.x, acc.z[0]);
                     acc.xy[1] = ffma2(make_float2(w1, w1), g01, acc.xy[1]); acc.z[1] = fmaf(w1, r1.x, acc.z[1]);
                     acc.xy[2] = ffma2(make_float2(w2, w2), g01, acc.xy[2]); acc.z[2] = fmaf(w2, r1.x, acc.z[2]);
+                    if (OX == 0 && OY == 0) { g0 = r0.z; g1 = r0.w; g2 = r1.x; }
                 };
                 if (nz[OY + 1] != 0) {   // a source row without gradient contributes nothing (warp-uniform)
                     source(std::integral_constant<int, -1>{});
@@ -774,7 +793,6 @@ __device__ __forceinline__ void svf_bwd_tma_body(const BwdTmaCtx& c) {
             source_row(std::integral_constant<int, 1>{});
             // ---- direct + position term of target (x, y, s) ----
             if (s >= zs && s < ze && nz[1] != 0) {
-                const float g0 = Gs[lc], g1 = Gs[RG::CS + lc], g2 = Gs[2 * RG::CS + lc];
                 float px = xf + Us[lc] * c.in_scale, py = yf + Us[RG::CS + lc] * c.in_scale,
                       pz = (float)s + Us[2 * RG::CS + lc] * c.in_scale;
                 const float mx = irs_inside(px, d.W) * c.in_scale, my = irs_inside(py, d.H) * c.in_scale,
@@ -798,16 +816,16 @@ __device__ __forceinline__ void svf_bwd_tma_body(const BwdTmaCtx& c) {
         acc.xy[BM] = make_float2(0.f, 0.f);
         acc.z[BM] = 0.f;
         gi += HW;
-        __syncthreads();   // U plane s-1, G plane s and the records are free
+        __syncthreads();   // U plane s-1, G plane s+1 and the records of plane s are free; those of plane s+1 are complete
         if (tid == 0) {
             if (it + 4 < n_u) {
                 irs_mbar_expect_tx(&c.bar_u[it & 3], RG::BYTES);
                 irs_tma_load_plane(c.U + (it & 3) * RG::SS, c.tmap_u, &c.bar_u[it & 3], c.x0t - TMA_XO, c.y0t - 1,
                                    zs + 2 + it, 3 * c.chain);
             }
-            if (it + BWD_NG < n_g) {
-                irs_mbar_expect_tx(&c.bar_g[M], RG::BYTES);
-                irs_tma_load_plane(c.G + M * RG::SS, c.tmap_g, &c.bar_g[M], c.x0t - TMA_XO, c.y0t - 1, zs + 2 + it,
+            if (it + 1 + BWD_NG < n_g) {   // G plane s+1 (sequence number it + 1, slot BP) was consumed by produce()
+                irs_mbar_expect_tx(&c.bar_g[BP], RG::BYTES);
+                irs_tma_load_plane(c.G + BP * RG::SS, c.tmap_g, &c.bar_g[BP], c.x0t - TMA_XO, c.y0t - 1, zs + 3 + it,
                                    3 * c.chain);
             }
         }
@@ -822,8 +840,8 @@ __device__ __forceinline__ void svf_bwd_tma_body(const BwdTmaCtx& c) {
 
 constexpr int BWD_BW = 40;
 constexpr size_t svf_bwd_tma_smem() {
-    return sizeof(float) * ((TMA_NS + BWD_NG) * TmaRing<BWD_BW>::SS + TMA_EX * TMA_EY * REC_F) + 8 * (TMA_NS + BWD_NG) +
-           4 * 2 * TMA_EY + 8;
+    return sizeof(float) * ((TMA_NS + BWD_NG) * TmaRing<BWD_BW>::SS + 2 * TMA_EX * TMA_EY * REC_F) + 8 * (TMA_NS + BWD_NG) +
+           4 * 3 * TMA_EY + 8;
 }
 
 __global__ void __launch_bounds__(TILE_T, 4)
@@ -847,7 +865,7 @@ svf_step_bwd_tma_kernel(const __grid_constant__ CUtensorMap tmap_u, const __grid
         c.U = smem;
         c.G = smem + TMA_NS * RG::SS;
         c.REC = smem + (TMA_NS + BWD_NG) * RG::SS;
-        c.bar_u = reinterpret_cast<uint64_t*>(c.REC + TMA_EX * TMA_EY * REC_F);
+        c.bar_u = reinterpret_cast<uint64_t*>(c.REC + 2 * TMA_EX * TMA_EY * REC_F);
         c.bar_g = c.bar_u + TMA_NS;
         c.row_nz = reinterpret_cast<int*>(c.bar_g + BWD_NG);
         c.in_scale = in_scale; c.out_scale = out_scale; c.d = d;
