@@ -145,6 +145,41 @@ def test_graph_replay_matches_eager(built):
     assert outs[0][1][56] == 5  # Philox offset advanced once per transition
 
 
+def test_prefetched_images_match_direct_load(built):
+    """the double-buffered input pipeline (prefetch_images on a copy stream + commit_images) is bit-identical to
+    load_images on the compute stream, also when the pair changes between steps"""
+    from irsgmcmc_b200.sampler import SGLDSampler, SGLDConfig
+    from irsgmcmc_b200.data_loader.synthetic import make_pair
+    n, C = 16, 2
+    fixed, moving, vp = make_pair(n)
+    pin = lambda x: x.contiguous().pin_memory()
+    pairs = []
+    for k in range(3):   # three different pairs: scaled intensities, shifted mask
+        pairs.append((pin(fixed['im'] * (1.0 - 0.1 * k)), pin(moving['im'] * (1.0 + 0.05 * k)),
+                      pin(torch.roll(fixed['mask'], k, dims=-1).view(torch.uint8))))
+    outs = []
+    for pipelined in (False, True):
+        torch.manual_seed(0)
+        s = SGLDSampler(fixed, moving, C, SGLDConfig(), device=DEV)
+        s.set_state(0.5 * torch.randn(C, 3, n, n, n), torch.exp(0.5 * vp['log_var']))
+        s.init_gmm(sigma_hat=0.7)
+        if pipelined:
+            s.prefetch_images(*pairs[0])
+        for k in range(3):
+            if pipelined:
+                s.commit_images()
+                if k + 1 < 3:
+                    s.prefetch_images(*pairs[k + 1])
+            else:
+                s.load_images(*pairs[k])
+            s.step(2, use_graph=True)
+        torch.cuda.synchronize()
+        outs.append((s.v.clone(), s.hyper.clone(), s.stats.clone()))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][2], outs[1][2])
+    with pytest.raises(RuntimeError):
+        SGLDSampler(fixed, moving, C, SGLDConfig(), device=DEV).commit_images()
+
+
 def test_gmm_init_matches_oracle(built):
     from irsgmcmc_b200.sampler import SGLDSampler, SGLDConfig
     from irsgmcmc_b200.data_loader.synthetic import make_pair
