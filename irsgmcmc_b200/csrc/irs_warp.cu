@@ -72,10 +72,12 @@ warp_nearest_kernel(const T_* __restrict__ seg, long long seg_cs, const float* _
 
 
 // ---- voxel-unit variants used inside the fused step: position = index + u (+ jitter in voxels) ----------------------
+// 32-bit index arithmetic throughout (3 V < 2^31 is checked at the ABI): 64-bit divisions cost more than the gather.
 __device__ __forceinline__ void position_from_u(const float* __restrict__ u, const IrsRng& jit, float alpha,
-                                                int use_jitter, long long V, long long i, int c, IrsDims d, float& px,
-                                                float& py, float& pz) {
-    const int x = (int)(i % d.W), y = (int)((i / d.W) % d.H), z = (int)(i / ((long long)d.W * d.H));
+                                                int use_jitter, int V, int i, int c, IrsDims d, float& px, float& py,
+                                                float& pz) {
+    const unsigned q = (unsigned)i / (unsigned)d.W, x = (unsigned)i - q * (unsigned)d.W;
+    const unsigned z = q / (unsigned)d.H, y = q - z * (unsigned)d.H;
     px = (float)x + u[i];
     py = (float)y + u[V + i];
     pz = (float)z + u[2 * V + i];
@@ -97,8 +99,8 @@ __device__ __forceinline__ void position_from_u(const float* __restrict__ u, con
 __global__ void __launch_bounds__(256)
 warp_vox_fwd_kernel(const float* __restrict__ img, const float* __restrict__ u, IrsRng jit, float alpha, int use_jitter,
                     float* __restrict__ out, IrsDims d) {
-    const long long V = d.V();
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int V = (int)d.V();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= V) return;
     const int c = blockIdx.y;
     float px, py, pz;
@@ -109,8 +111,8 @@ warp_vox_fwd_kernel(const float* __restrict__ img, const float* __restrict__ u, 
 __global__ void __launch_bounds__(256)
 warp_vox_bwd_kernel(const float* __restrict__ img, const float* __restrict__ u, IrsRng jit, float alpha, int use_jitter,
                     const float* __restrict__ g_out, float g_sign, float* __restrict__ g_u, IrsDims d) {
-    const long long V = d.V();
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int V = (int)d.V();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= V) return;
     const int c = blockIdx.y;
     float px, py, pz;
