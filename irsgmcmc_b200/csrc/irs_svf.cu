@@ -230,10 +230,10 @@ __device__ __forceinline__ void block_max_to_global(float m, float* __restrict__
     }
 }
 
-template <int R>
+template <int R, bool PAD = true>
 __device__ __forceinline__ float svf_fwd_tile_body(const float* __restrict__ in, float in_scale, float* __restrict__ out,
                                                    IrsDims d, int x0t, int y0t, int zs, int ze, float* smem) {
-    using T = Tile<R, true>;
+    using T = Tile<R, PAD>;
     float* U = smem;  // [3][NP][PS]
     const long long V = d.V();
     const int lx = threadIdx.x % TILE_X, ly = threadIdx.x / TILE_X, x = x0t + lx, y = y0t + ly;
@@ -530,6 +530,12 @@ __device__ __forceinline__ void tma_ring_cell(float px, float py, float pz, int 
     sz = (s1 - s0) * RG::SS;
 }
 
+// exact global gather for one voxel, out of line: its register pressure stays out of the TMA kernels' main path
+__device__ __noinline__ void svf_fwd_voxel_cold(const float* __restrict__ in, float in_scale, float* __restrict__ out,
+                                                long long V, long long i, IrsDims d) {
+    irs_body_svf_fwd(in, in_scale, out, V, i, d);
+}
+
 // ---- forward step ------------------------------------------------------------------------------------------------------
 // voxels with |u| >= 0.999 (rare; only the last steps of a large deformation) take the exact global gather
 template <int BW>
@@ -582,7 +588,7 @@ __device__ __forceinline__ float svf_fwd_tma_body(const CUtensorMap* tmap, const
                 out[Vi + gi] = uy + in_scale * ring_interp<BW>(U + RG::CS, i000, sz, fx, fy, fz);
                 out[2 * Vi + gi] = uz + in_scale * ring_interp<BW>(U + 2 * RG::CS, i000, sz, fx, fy, fz);
             } else {
-                irs_body_svf_fwd(in, in_scale, out, V, gi, d);
+                svf_fwd_voxel_cold(in, in_scale, out, V, gi, d);
             }
         }
         __syncthreads();   // everyone is done with plane z-1: its slot takes plane z+3
@@ -598,9 +604,21 @@ __device__ __forceinline__ float svf_fwd_tma_body(const CUtensorMap* tmap, const
 constexpr int FWD_BW = 40;
 constexpr size_t svf_fwd_tma_smem() { return sizeof(float) * TMA_NS * TmaRing<FWD_BW>::SS + 8 * TMA_NS; }
 
+// out-of-line fallbacks of the TMA forward kernel: their register pressure stays out of the main path
+__device__ __noinline__ float svf_fwd_tile_body_cold(const float* __restrict__ in, float in_scale, float* __restrict__ out,
+                                                     IrsDims d, int x0t, int y0t, int zs, int ze, float* smem) {
+    return svf_fwd_tile_body<2, false>(in, in_scale, out, d, x0t, y0t, zs, ze, smem);   // compact ring (no row padding)
+}
+
+constexpr size_t svf_fwd_tile_smem_compact(int R) {
+    return sizeof(float) * (size_t)(3 * (2 * R + 1)) * (TILE_X + 2 * R) * (TILE_Y + 2 * R);
+}
+
 // maxabs_prev = max |u_{k-1}| of the previous step (nullptr for the first): |u_k| <= 2 max |u_{k-1}|, so the TMA ring is
 // taken when that bound is below 1, the wider non-TMA ring otherwise
-__global__ void __launch_bounds__(TILE_T, 4)
+// CTAS = resident CTAs per SM the kernel is compiled for (register cap 65536 / 256 / CTAS)
+template <int CTAS>
+__global__ void __launch_bounds__(TILE_T, CTAS)
 svf_step_fwd_tma_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restrict__ in_all, float in_scale,
                         float* __restrict__ out_all, const float* __restrict__ maxabs_prev, float* __restrict__ maxabs,
                         int seg_len, IrsDims d) {
@@ -616,7 +634,7 @@ svf_step_fwd_tma_kernel(const __grid_constant__ CUtensorMap tmap, const float* _
     const bool small = maxabs_prev == nullptr || 2.f * __ldg(maxabs_prev) < 0.999f;
     float m;
     if (small) m = svf_fwd_tma_body<FWD_BW>(&tmap, in, in_scale, out, d, blockIdx.y, x0t, y0t, zs, ze, smem);
-    else m = svf_fwd_tile_body<2>(in, in_scale, out, d, x0t, y0t, zs, ze, smem);
+    else m = svf_fwd_tile_body_cold(in, in_scale, out, d, x0t, y0t, zs, ze, smem);
     block_max_to_global(m, maxabs);
 }
 
@@ -957,23 +975,26 @@ int irs_launch_svf_fwd(const float* v, float* hist, float* maxabs, int n_steps, 
     const int tiles = ((d.W + TILE_X - 1) / TILE_X) * ((d.H + TILE_Y - 1) / TILE_Y);
     const bool tma = irs_tma_field_ok(v, d.W) && irs_tma_field_ok(hist, d.W) && (F % 4) == 0;
     if (tma) {
-        const size_t smem = zmax(svf_fwd_tma_smem(), svf_fwd_tile_smem(RF));
-        static bool configured = false;
-        if (!configured) {
-            e = cudaFuncSetAttribute(svf_step_fwd_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) return (int)e;
-            configured = true;
-        }
+        const size_t smem = zmax(svf_fwd_tma_smem(), svf_fwd_tile_smem_compact(RF));
+        using Kern = void (*)(CUtensorMap, const float*, float, float*, const float*, float*, int, IrsDims);
+        static Kern kern = nullptr;
         static int slots = 0;
-        if (slots == 0) slots = resident_ctas(svf_step_fwd_tma_kernel, smem);
+        if (kern == nullptr) {
+            int ctas = 5;   // measured at 128^3: 4 -> 0.212 ms, 5 -> 0.200 ms, 6 -> 0.208 ms for the 12 forward steps
+            if (const char* ev = getenv("IRS_FWD_CTAS")) ctas = atoi(ev);   // development override
+            kern = ctas <= 4 ? (Kern)svf_step_fwd_tma_kernel<4> : (ctas == 5 ? (Kern)svf_step_fwd_tma_kernel<5> : (Kern)svf_step_fwd_tma_kernel<6>);
+            e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return (int)e;
+            slots = resident_ctas(kern, smem);
+        }
         const int seg_len = svf_seg_len(d, C, slots, 3, "IRS_SVF_SEG_FWD", true);
         dim3 tgrid(tiles * ((d.D + seg_len - 1) / seg_len), C);
         for (int k = 0; k < n_steps; ++k) {
             const float* in = (k == 0) ? v : hist + (size_t)(k - 1) * F;
             CUtensorMap map;
             if (irs_tma_encode_field(&map, in, 3 * C, d.D, d.H, d.W, FWD_BW, TMA_EY) != 0) return IRS_ERR_UNSUPPORTED;
-            e = irs_launch_pdl(svf_step_fwd_tma_kernel, tgrid, dim3(TILE_T), smem, st, map, in, k == 0 ? scale0 : 1.0f,
-                               hist + (size_t)k * F, k == 0 ? nullptr : maxabs + k - 1, maxabs + k, seg_len, d);
+            e = irs_launch_pdl(kern, tgrid, dim3(TILE_T), smem, st, map, in, k == 0 ? scale0 : 1.0f, hist + (size_t)k * F,
+                               k == 0 ? nullptr : maxabs + k - 1, maxabs + k, seg_len, d);
             if (e != cudaSuccess) return (int)e;
         }
         return (int)cudaGetLastError();
