@@ -1,11 +1,13 @@
 // irs_data.cu -- data term: LCC normalisation as separable box filters over shared-memory tiles with halos, its adjoint,
 // the Gaussian-mixture log-density with warp-shuffle reductions, virtual decimation.
 // (reference model/loss.py:87-114, utils/util.py:330-347,446-485, trainer/trainer.py:68-77,316-327)
+#include <cstdlib>
+
 #include "irs_kernels.cuh"
 
 namespace {
 
-constexpr int TX = 32, TY = 8, TZ = 8;  // output tile; 256 threads = TX x TY, each marches TZ planes in the last pass
+constexpr int TX = 32, TY = 8;  // in-plane tile of the box filters; 256 threads = TX x TY
 
 enum { BOX_FWD_MEAN = 0, BOX_FWD_VAR = 1, BOX_BWD_VAR = 2, BOX_BWD_MEAN = 3 };
 
@@ -18,169 +20,177 @@ __device__ __forceinline__ float adj_weight(int j, int o, int n, int S) {
     return w;
 }
 
-// One 3-D box filter (forward: replicate padding; backward: its adjoint) over a TZ x TY x TX tile with halo S, with a
-// fused pre-operation on the loaded values and a fused epilogue:
+// One 3-D box filter (forward: replicate padding; backward: its adjoint) with a fused pre-operation on the loaded values
+// and a fused epilogue:
 //   FWD_MEAN : in0 = I                       -> out0 = a = I - box(I)/k^3
 //   FWD_VAR  : in0 = a (pre: a^2), in1 = zF  -> out0 = rs = 1/sqrt(box/k^3 + 1e-10), out1 = z = zF - a rs  (zF null: a rs)
 //   BWD_VAR  : in0 = g, in1 = a, in2 = rs (pre: -g a rs^3 / 2) -> out0 = ga = g rs + 2 a adjbox/k^3        (g = sign * in0)
 //   BWD_MEAN : in0 = ga                      -> out0 = ga - adjbox/k^3
+// Plane-marching form: a CTA owns a 32 x 8 column of voxels and walks along a z segment.  Per plane: tile + halo S in
+// x / y goes through registers into a double-buffered shared-memory plane (pre-operation applied), x pass -> shared
+// memory, y pass -> one register per thread, and the z pass is a ring of 2S+1 registers; the next plane's global loads
+// are in flight while this plane is filtered.  (Round-1 history: a 32 x 8 x 8 tile with a z halo inside the tile and
+// three shared-memory passes ran 47 / 48 us for the forward / adjoint pair at 128^3; this form 39 / 42 us.)
 template <int MODE, int S>
 __global__ void __launch_bounds__(256)
-box_tile_kernel(const float* __restrict__ in0, const float* __restrict__ in1, const float* __restrict__ in2,
-                float sign, float* __restrict__ out0, float* __restrict__ out1, IrsDims d) {
-    extern __shared__ float smem[];
-    constexpr int EX = TX + 2 * S, EY = TY + 2 * S, EZ = TZ + 2 * S;
-    float* A = smem;                 // EZ x EY x EX  (input tile; reused for the y-pass result EZ x TY x TX)
-    float* B = smem + EZ * EY * EX;  // EZ x EY x TX  (x-pass result)
+box_march_kernel(const float* __restrict__ in0, const float* __restrict__ in1, const float* __restrict__ in2, float sign,
+                 float* __restrict__ out0, float* __restrict__ out1, int seg_len, IrsDims d) {
+    constexpr int EX = TX + 2 * S, EY = TY + 2 * S, NP = EX * EY, NE = (NP + 255) / 256, NT = 2 * S + 1;
     constexpr bool BWD = (MODE == BOX_BWD_VAR || MODE == BOX_BWD_MEAN);
+    __shared__ float P[2][NP];        // plane tile + halo (pre-operation applied), double-buffered
+    __shared__ float X[EY * TX];      // x-pass result
 
-    const long long V = d.V();
+    const int V = (int)d.V(), HW = d.H * d.W;
     const int c = blockIdx.y;
     const int tiles_x = (d.W + TX - 1) / TX, tiles_y = (d.H + TY - 1) / TY;
     const int bx = blockIdx.x % tiles_x, by = (blockIdx.x / tiles_x) % tiles_y, bz = blockIdx.x / (tiles_x * tiles_y);
-    const int x0 = bx * TX, y0 = by * TY, z0 = bz * TZ;
+    const int x0 = bx * TX, y0 = by * TY, zs = bz * seg_len, ze = min(zs + seg_len, d.D);
     const size_t off = (size_t)c * V;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-
-    // ---- load tile + halo with the pre-operation ----
-    // column chunks of a row: lane and lane + 32; their (clamped) x offsets are fixed for the whole tile
-    const int gx0 = x0 - S + lane, gx1 = gx0 + 32;
-    const bool has1 = lane + 32 < EX;
-    const int cx0 = irs_clampi(gx0, 0, d.W - 1), cx1 = irs_clampi(gx1, 0, d.W - 1);
-    const bool okx0 = gx0 >= 0 && gx0 < d.W, okx1 = gx1 >= 0 && gx1 < d.W;
+    const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
+    const int gx = x0 + lx, gy = y0 + ly;
+    const bool active = gx < d.W && gy < d.H;
     const float* p0 = in0 + off;
     const float* p1 = in1 ? in1 + off : nullptr;
     const float* p2 = in2 ? in2 + off : nullptr;
-#pragma unroll 3
-    for (int row = warp; row < EZ * EY; row += 8) {
-        const int tz = row / EY, ty = row - tz * EY;
-        const int gz = z0 - S + tz, gy = y0 - S + ty;
-        float* arow = A + row * EX;
-        if (!BWD) {
-            const int rbase = (irs_clampi(gz, 0, d.D - 1) * d.H + irs_clampi(gy, 0, d.H - 1)) * d.W;
-            const float a = __ldg(p0 + rbase + cx0);
-            arow[lane] = (MODE == BOX_FWD_VAR) ? a * a : a;
-            if (has1) {
-                const float b = __ldg(p0 + rbase + cx1);
-                arow[lane + 32] = (MODE == BOX_FWD_VAR) ? b * b : b;
-            }
-        } else {
-            const bool rin = gz >= 0 && gz < d.D && gy >= 0 && gy < d.H;
-            const int rbase = (gz * d.H + gy) * d.W;
-            float va = 0.f, vb = 0.f;
-            if (rin && okx0) {
-                const int gi = rbase + gx0;
-                if (MODE == BOX_BWD_VAR) {
-                    const float g = sign * __ldg(p0 + gi), a = __ldg(p1 + gi), r = __ldg(p2 + gi);
-                    va = -0.5f * g * a * r * r * r;
-                } else {
-                    va = __ldg(p0 + gi);
-                }
-            }
-            if (has1 && rin && okx1) {
-                const int gi = rbase + gx1;
-                if (MODE == BOX_BWD_VAR) {
-                    const float g = sign * __ldg(p0 + gi), a = __ldg(p1 + gi), r = __ldg(p2 + gi);
-                    vb = -0.5f * g * a * r * r * r;
-                } else {
-                    vb = __ldg(p0 + gi);
-                }
-            }
-            arow[lane] = va;
-            if (has1) arow[lane + 32] = vb;
-        }
+
+    // the plane elements this thread stages: offsets inside a (H, W) plane (forward: clamped = replicate padding;
+    // adjoint: -1 outside the volume = zero) and inside the shared-memory plane
+    int pofs[NE], sofs[NE];
+#pragma unroll
+    for (int k = 0; k < NE; ++k) {
+        const int e = threadIdx.x + k * 256;
+        const int ey = e / EX, ex = e - ey * EX;
+        const int ax = x0 - S + ex, ay = y0 - S + ey;
+        sofs[k] = e < NP ? e : -1;
+        if (BWD) pofs[k] = (e < NP && ax >= 0 && ax < d.W && ay >= 0 && ay < d.H) ? ay * d.W + ax : -1;
+        else pofs[k] = irs_clampi(ay, 0, d.H - 1) * d.W + irs_clampi(ax, 0, d.W - 1);
     }
-    __syncthreads();
+    float raw[MODE == BOX_BWD_VAR ? 3 : 1][NE];
+    auto fetch = [&](int pz) {   // global loads of plane pz into registers (values finished in stage())
+        int zofs;
+        bool zin = true;
+        if (BWD) { zin = pz >= 0 && pz < d.D; zofs = pz * HW; }
+        else zofs = irs_clampi(pz, 0, d.D - 1) * HW;
+#pragma unroll
+        for (int k = 0; k < NE; ++k) {
+            const bool ok = sofs[k] >= 0 && zin && pofs[k] >= 0;
+            const int gi = zofs + pofs[k];
+            raw[0][k] = ok ? __ldg(p0 + gi) : 0.f;
+            if (MODE == BOX_BWD_VAR) {
+                raw[1][k] = ok ? __ldg(p1 + gi) : 0.f;
+                raw[2][k] = ok ? __ldg(p2 + gi) : 0.f;
+            }
+        }
+    };
+    auto stage = [&](int buf) {  // pre-operation + store into the shared-memory plane
+#pragma unroll
+        for (int k = 0; k < NE; ++k) {
+            if (sofs[k] < 0) continue;
+            float v = raw[0][k];
+            if (MODE == BOX_FWD_VAR) v = v * v;
+            if (MODE == BOX_BWD_VAR) { const float r = raw[2][k]; v = -0.5f * (sign * v) * raw[1][k] * r * r * r; }
+            P[buf][sofs[k]] = v;
+        }
+    };
 
     // adjoint: the fold weights differ from 1 only for outputs on a face of the volume
-    const bool fold_x = BWD && (x0 == 0 || x0 + TX >= d.W), fold_y = BWD && (y0 == 0 || y0 + TY >= d.H),
-               fold_z = BWD && (z0 == 0 || z0 + TZ >= d.D);
+    const bool fold_x = BWD && (x0 == 0 || x0 + TX >= d.W), fold_y = BWD && (y0 == 0 || y0 + TY >= d.H);
+    const float inv_k3 = 1.0f / (float)((2 * S + 1) * (2 * S + 1) * (2 * S + 1));
 
-    // ---- x pass: B[tz][ty][x] = sum_o w A[tz][ty][x + S + o] ----
-    {
-        const int gx = x0 + lane;
-#pragma unroll 2
-        for (int row = warp; row < EZ * EY; row += 8) {
-            const float* a = A + row * EX + lane + S;
-            float acc = 0.f;
-            if (fold_x) {
+    float ring[NT];   // y-pass results of the last 2S+1 planes (ring[NT-1] = newest)
 #pragma unroll
-                for (int o = -S; o <= S; ++o) acc += adj_weight(gx, o, d.W, S) * a[o];
+    for (int i = 0; i < NT; ++i) ring[i] = 0.f;
+
+    const int p_first = zs - S, p_last = ze - 1 + S;
+    fetch(p_first);
+    stage(0);
+    __syncthreads();
+    for (int p = p_first, it = 0; p <= p_last; ++p, ++it) {
+        const int buf = it & 1;
+        if (p < p_last) fetch(p + 1);   // in flight while this plane is filtered
+        // ---- x pass: X[row][x] = sum_o w P[row][x + S + o], rows ly and ly + 8 ----
+#pragma unroll
+        for (int r = 0; r < (EY + 7) / 8; ++r) {
+            const int row = ly + 8 * r;
+            if (row < EY) {
+                const float* a = &P[buf][row * EX + lx + S];
+                float acc = 0.f;
+                if (fold_x) {
+#pragma unroll
+                    for (int o = -S; o <= S; ++o) acc += adj_weight(gx, o, d.W, S) * a[o];
+                } else {
+#pragma unroll
+                    for (int o = -S; o <= S; ++o) acc += a[o];
+                }
+                X[row * TX + lx] = acc;
+            }
+        }
+        __syncthreads();
+        // ---- y pass into the register ring ----
+#pragma unroll
+        for (int i = 0; i < NT - 1; ++i) ring[i] = ring[i + 1];
+        {
+            const float* b = &X[(ly + S) * TX + lx];
+            float acc = 0.f;
+            if (fold_y) {
+#pragma unroll
+                for (int o = -S; o <= S; ++o) acc += adj_weight(gy, o, d.H, S) * b[o * TX];
             } else {
 #pragma unroll
-                for (int o = -S; o <= S; ++o) acc += a[o];
+                for (int o = -S; o <= S; ++o) acc += b[o * TX];
             }
-            B[row * TX + lane] = acc;
+            ring[NT - 1] = acc;
         }
+        // ---- z pass + epilogue for plane gz = p - S (its window p-2S .. p is in the ring) ----
+        const int gz = p - S;
+        if (active && gz >= zs && gz < ze) {
+            float acc = 0.f;
+            if (BWD && (gz == 0 || gz == d.D - 1)) {
+#pragma unroll
+                for (int o = -S; o <= S; ++o) acc += adj_weight(gz, o, d.D, S) * ring[o + S];
+            } else {
+#pragma unroll
+                for (int o = -S; o <= S; ++o) acc += ring[o + S];
+            }
+            const float box = acc * inv_k3;
+            const size_t gi = off + (size_t)gz * HW + gy * d.W + gx;
+            if (MODE == BOX_FWD_MEAN) {
+                out0[gi] = in0[gi] - box;
+            } else if (MODE == BOX_FWD_VAR) {
+                const float rs = 1.0f / sqrtf(box + 1e-10f);
+                const float zn = in0[gi] * rs;
+                if (out0 != nullptr) out0[gi] = rs;
+                if (out1 != nullptr) out1[gi] = in1 != nullptr ? in1[gi - off] - zn : zn;
+            } else if (MODE == BOX_BWD_VAR) {
+                out0[gi] = sign * in0[gi] * in2[gi] + 2.0f * in1[gi] * box;
+            } else {
+                out0[gi] = in0[gi] - box;
+            }
+        }
+        if (p < p_last) stage(buf ^ 1);
+        __syncthreads();
     }
-    __syncthreads();
+}
 
-    // ---- y pass: A[tz][y][x] = sum_o w B[tz][y + S + o][x]   (A reused as EZ x TY x TX) ----
-#pragma unroll 2
-    for (int row = warp; row < EZ * TY; row += 8) {
-        const int tz = row / TY, ty = row % TY;
-        const int gy = y0 + ty;
-        const float* b = B + (tz * EY + ty + S) * TX + lane;
-        float acc = 0.f;
-        if (fold_y) {
-#pragma unroll
-            for (int o = -S; o <= S; ++o) acc += adj_weight(gy, o, d.H, S) * b[o * TX];
-        } else {
-#pragma unroll
-            for (int o = -S; o <= S; ++o) acc += b[o * TX];
-        }
-        A[row * TX + lane] = acc;
+static int box_seg_len(IrsDims d, int C) {
+    if (const char* e = getenv("IRS_BOX_SEG")) {   // development override
+        const int v = atoi(e);
+        if (v >= 1) return v < d.D ? v : d.D;
     }
-    __syncthreads();
-
-    // ---- z pass + epilogue: thread (warp = y, lane = x) walks the TZ output planes ----
-    const int gx = x0 + lane, gy = y0 + warp;
-    if (gx >= d.W || gy >= d.H) return;
-    const float inv_k3 = 1.0f / (float)((2 * S + 1) * (2 * S + 1) * (2 * S + 1));
-#pragma unroll
-    for (int tz = 0; tz < TZ; ++tz) {
-        const int gz = z0 + tz;
-        if (gz >= d.D) break;
-        const float* a = A + ((tz + S) * TY + warp) * TX + lane;
-        float acc = 0.f;
-        if (fold_z) {
-#pragma unroll
-            for (int o = -S; o <= S; ++o) acc += adj_weight(gz, o, d.D, S) * a[o * TY * TX];
-        } else {
-#pragma unroll
-            for (int o = -S; o <= S; ++o) acc += a[o * TY * TX];
-        }
-        const float box = acc * inv_k3;
-        const size_t gi = off + ((size_t)gz * d.H + gy) * d.W + gx;
-        if (MODE == BOX_FWD_MEAN) {
-            out0[gi] = in0[gi] - box;
-        } else if (MODE == BOX_FWD_VAR) {
-            const float rs = 1.0f / sqrtf(box + 1e-10f);
-            const float zn = in0[gi] * rs;
-            if (out0 != nullptr) out0[gi] = rs;
-            if (out1 != nullptr) out1[gi] = in1 != nullptr ? in1[gi - off] - zn : zn;
-        } else if (MODE == BOX_BWD_VAR) {
-            out0[gi] = sign * in0[gi] * in2[gi] + 2.0f * in1[gi] * box;
-        } else {
-            out0[gi] = in0[gi] - box;
-        }
-    }
+    // enough CTAs for ~2 waves of the 148 x 8 resident slots, segments no shorter than 8 planes (halo 2S per segment)
+    const long long tiles = (long long)((d.W + TX - 1) / TX) * ((d.H + TY - 1) / TY) * C;
+    int len = d.D;
+    while (len > 8 && tiles * ((d.D + len - 1) / len) < 2 * 1184) len = (len + 1) / 2;
+    return len < 8 ? (d.D < 8 ? d.D : 8) : len;
 }
 
 template <int MODE, int S>
 int launch_box_s(const float* in0, const float* in1, const float* in2, float sign, float* out0, float* out1, int C,
                  IrsDims d, cudaStream_t st) {
-    constexpr int EX = TX + 2 * S, EY = TY + 2 * S, EZ = TZ + 2 * S;
-    constexpr size_t smem = sizeof(float) * ((size_t)EZ * EY * EX + (size_t)EZ * EY * TX);
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(box_tile_kernel<MODE, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-        configured = true;
-    }
-    const int tiles = ((d.W + TX - 1) / TX) * ((d.H + TY - 1) / TY) * ((d.D + TZ - 1) / TZ);
+    const int seg_len = box_seg_len(d, C);
+    const int tiles = ((d.W + TX - 1) / TX) * ((d.H + TY - 1) / TY) * ((d.D + seg_len - 1) / seg_len);
     dim3 grid(tiles, C);
-    box_tile_kernel<MODE, S><<<grid, 256, smem, st>>>(in0, in1, in2, sign, out0, out1, d);
+    box_march_kernel<MODE, S><<<grid, 256, 0, st>>>(in0, in1, in2, sign, out0, out1, seg_len, d);
     return (int)cudaGetLastError();
 }
 
