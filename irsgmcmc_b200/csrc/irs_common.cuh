@@ -181,19 +181,25 @@ struct IrsGmm {
 #define IRS_LOG_SQRT_2PI 0.9189385332046727f
 
 // returns log pdf(z); rho[k] = responsibilities; wprec = sum_k rho_k prec_k  (so dNLL/dz = z*wprec, VD residual = z^2*wprec)
-IRS_HD float irs_gmm_eval(const IrsGmm& g, float z, float* rho, float& wprec) {
-    float e[IRS_MAX_K];
+// KK = compile-time bound on the component loop (g.K <= KK): the kernels instantiate KK = 4 for the usual mixture so that
+// no issue slots go to predicated-off components; same operations in the same order for every KK >= g.K.
+template <int KK>
+IRS_HD float irs_gmm_eval_t(const IrsGmm& g, float z, float* rho, float& wprec) {
+    float e[KK];
     float hz2 = 0.5f * z * z, m = -INFINITY;
 #pragma unroll
-    for (int k = 0; k < IRS_MAX_K; ++k) if (k < g.K) { e[k] = g.lw[k] - hz2 * g.prec[k]; m = fmaxf(m, e[k]); }
+    for (int k = 0; k < KK; ++k) if (k < g.K) { e[k] = g.lw[k] - hz2 * g.prec[k]; m = fmaxf(m, e[k]); }
     float S = 0.0f;
 #pragma unroll
-    for (int k = 0; k < IRS_MAX_K; ++k) if (k < g.K) { e[k] = expf(e[k] - m); S += e[k]; }
+    for (int k = 0; k < KK; ++k) if (k < g.K) { e[k] = expf(e[k] - m); S += e[k]; }
     float inv = 1.0f / S;
     wprec = 0.0f;
 #pragma unroll
-    for (int k = 0; k < IRS_MAX_K; ++k) if (k < g.K) { rho[k] = e[k] * inv; wprec += rho[k] * g.prec[k]; }
+    for (int k = 0; k < KK; ++k) if (k < g.K) { rho[k] = e[k] * inv; wprec += rho[k] * g.prec[k]; }
     return m + logf(S) - IRS_LOG_SQRT_2PI;
+}
+IRS_HD float irs_gmm_eval(const IrsGmm& g, float z, float* rho, float& wprec) {
+    return irs_gmm_eval_t<IRS_MAX_K>(g, z, rho, wprec);
 }
 
 // precision-weighted squared residual used by virtual decimation (reference utils/util.py:330-347, closed form)

@@ -2,6 +2,7 @@
 // the Gaussian-mixture log-density with warp-shuffle reductions, virtual decimation.
 // (reference model/loss.py:87-114, utils/util.py:330-347,446-485, trainer/trainer.py:68-77,316-327)
 #include <cstdlib>
+#include <type_traits>
 
 #include "irs_kernels.cuh"
 
@@ -299,40 +300,47 @@ gmm_stats_a_kernel(const float* __restrict__ z, const unsigned char* __restrict_
     float acc[IRS_SUM_COUNT];
 #pragma unroll
     for (int k = 0; k < IRS_SUM_COUNT; ++k) acc[k] = 0.f;
-    auto one = [&](float zi) {
-        float rho[IRS_MAX_K], wp;
-        const float lp = irs_gmm_eval(gl, zi, rho, wp);
-        const float z2 = zi * zi, r = z2 * wp;
-        acc[IRS_SUM_NLL] -= lp;
+    // one voxel; `on` = inside the mask.  Branch-free: the four voxels of a 128-bit load are evaluated side by side (the
+    // loop is latency-bound on the exp / log chains), off-mask results are discarded by selects (adding 0 is exact).
+    auto one = [&](auto kk_tag, float zi, bool on) {
+        constexpr int KK = decltype(kk_tag)::value;
+        float rho[KK], wp;
+        const float lp = irs_gmm_eval_t<KK>(gl, zi, rho, wp);
+        const float z2 = zi * zi, r = on ? z2 * wp : 0.f;
+        acc[IRS_SUM_NLL] -= on ? lp : 0.f;
         acc[IRS_SUM_RR] += r * r;
 #pragma unroll
-        for (int k = 0; k < IRS_MAX_K; ++k) if (k < gl.K) {
-            acc[IRS_SUM_RHO + k] += rho[k];
-            acc[IRS_SUM_Q + k] += rho[k] * z2 * gl.prec[k];
+        for (int k = 0; k < KK; ++k) if (k < gl.K) {
+            acc[IRS_SUM_RHO + k] += on ? rho[k] : 0.f;
+            acc[IRS_SUM_Q + k] += on ? rho[k] * z2 * gl.prec[k] : 0.f;
         }
         return r;
     };
     const bool vec = (V % 4 == 0) && ((reinterpret_cast<uintptr_t>(z) | reinterpret_cast<uintptr_t>(mask) |
                                        reinterpret_cast<uintptr_t>(r_out)) & 15) == 0;
-    if (vec) {   // 128-bit loads, four voxels per thread and iteration
-        for (int i = (blockIdx.x * blockDim.x + threadIdx.x) * 4; i < V; i += gridDim.x * blockDim.x * 4) {
-            const uchar4 m4 = *reinterpret_cast<const uchar4*>(mask + i);
-            float4 r4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (m4.x | m4.y | m4.z | m4.w) {
-                const float4 z4 = __ldg(reinterpret_cast<const float4*>(z + i));
-                if (m4.x) r4.x = one(z4.x);
-                if (m4.y) r4.y = one(z4.y);
-                if (m4.z) r4.z = one(z4.z);
-                if (m4.w) r4.w = one(z4.w);
+    auto sweep = [&](auto kk_tag) {
+        if (vec) {   // 128-bit loads, four voxels per thread and iteration
+            for (int i = (blockIdx.x * blockDim.x + threadIdx.x) * 4; i < V; i += gridDim.x * blockDim.x * 4) {
+                const uchar4 m4 = *reinterpret_cast<const uchar4*>(mask + i);
+                float4 r4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (m4.x | m4.y | m4.z | m4.w) {
+                    const float4 z4 = __ldg(reinterpret_cast<const float4*>(z + i));
+                    r4.x = one(kk_tag, z4.x, m4.x != 0);
+                    r4.y = one(kk_tag, z4.y, m4.y != 0);
+                    r4.z = one(kk_tag, z4.z, m4.z != 0);
+                    r4.w = one(kk_tag, z4.w, m4.w != 0);
+                }
+                if (!FINALIZE) *reinterpret_cast<float4*>(r_out + i) = r4;
             }
-            if (!FINALIZE) *reinterpret_cast<float4*>(r_out + i) = r4;
+        } else {
+            for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < V; i += gridDim.x * blockDim.x) {
+                const float r = mask[i] ? one(kk_tag, z[i], true) : 0.f;
+                if (!FINALIZE) r_out[i] = r;
+            }
         }
-    } else {
-        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < V; i += gridDim.x * blockDim.x) {
-            const float r = mask[i] ? one(z[i]) : 0.f;
-            if (!FINALIZE) r_out[i] = r;
-        }
-    }
+    };
+    if (gl.K <= 4) sweep(std::integral_constant<int, 4>{});
+    else sweep(std::integral_constant<int, IRS_MAX_K>{});
     double blk[IRS_SUM_COUNT];
     irs_block_sum<IRS_SUM_COUNT>(acc, blk, sh);
     if (!irs_grid_sum<IRS_SUM_COUNT>(blk, partials, counter, total)) return;
@@ -417,28 +425,36 @@ gmm_grad_kernel(const float* __restrict__ z_all, const unsigned char* __restrict
     const float* z = z_all + (size_t)c * V;
     float* go = g_all + (size_t)c * V;
     float nll = 0.f;
-    auto one = [&](float zi) {
-        float rho[IRS_MAX_K], wp;
-        nll -= irs_gmm_eval(g, zi, rho, wp);
-        return alpha * zi * wp;
+    auto one = [&](auto kk_tag, float zi, bool on) {   // branch-free like gmm_stats_a_kernel
+        constexpr int KK = decltype(kk_tag)::value;
+        float rho[KK], wp;
+        const float lp = irs_gmm_eval_t<KK>(g, zi, rho, wp);
+        nll -= on ? lp : 0.f;
+        return on ? alpha * zi * wp : 0.f;
     };
-    if (V % 4 == 0 && ((reinterpret_cast<uintptr_t>(z) | reinterpret_cast<uintptr_t>(mask) | reinterpret_cast<uintptr_t>(go)) & 15) == 0) {
-        for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < V; i += (long long)gridDim.x * blockDim.x * 4) {
-            const uchar4 m4 = *reinterpret_cast<const uchar4*>(mask + i);
-            float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (m4.x | m4.y | m4.z | m4.w) {
-                const float4 z4 = __ldg(reinterpret_cast<const float4*>(z + i));
-                if (m4.x) g4.x = one(z4.x);
-                if (m4.y) g4.y = one(z4.y);
-                if (m4.z) g4.z = one(z4.z);
-                if (m4.w) g4.w = one(z4.w);
+    const bool vec = V % 4 == 0 && ((reinterpret_cast<uintptr_t>(z) | reinterpret_cast<uintptr_t>(mask) | reinterpret_cast<uintptr_t>(go)) & 15) == 0;
+    auto sweep = [&](auto kk_tag) {
+        if (vec) {
+            const int Vi = (int)V;
+            for (int i = (blockIdx.x * blockDim.x + threadIdx.x) * 4; i < Vi; i += gridDim.x * blockDim.x * 4) {
+                const uchar4 m4 = *reinterpret_cast<const uchar4*>(mask + i);
+                float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (m4.x | m4.y | m4.z | m4.w) {
+                    const float4 z4 = __ldg(reinterpret_cast<const float4*>(z + i));
+                    g4.x = one(kk_tag, z4.x, m4.x != 0);
+                    g4.y = one(kk_tag, z4.y, m4.y != 0);
+                    g4.z = one(kk_tag, z4.z, m4.z != 0);
+                    g4.w = one(kk_tag, z4.w, m4.w != 0);
+                }
+                *reinterpret_cast<float4*>(go + i) = g4;
             }
-            *reinterpret_cast<float4*>(go + i) = g4;
+        } else {
+            for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < V; i += (long long)gridDim.x * blockDim.x)
+                go[i] = mask[i] ? one(kk_tag, z[i], true) : 0.f;
         }
-    } else {
-        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < V; i += (long long)gridDim.x * blockDim.x)
-            go[i] = mask[i] ? one(z[i]) : 0.f;
-    }
+    };
+    if (K <= 4) sweep(std::integral_constant<int, 4>{});
+    else sweep(std::integral_constant<int, IRS_MAX_K>{});
     double blk[1];
     irs_block_sum<1>(&nll, blk, sh);
     if (irs_grid_sum<1>(blk, partials + (size_t)c * gridDim.x, counters + c, total)) {
