@@ -111,7 +111,8 @@ extern "C" int irs_sgld_launches_per_step(const irs_sgld_config* c) {
     n += c->data_term == IRS_DATA_LCC ? 2 : 0;   // LCC adjoint boxes
     n += 1;                                      // warp grid gradient
     n += 1;                                      // regulariser hyper step
-    n += 2 * c->svf_steps;                       // SVF adjoint (tiled gather + large-displacement scatter, early exit)
+    n += c->svf_steps + (c->svf_steps < 4 ? c->svf_steps : 4);   // SVF adjoint (gather; the last four steps carry the
+                                                                 // early-exit large-displacement scatter companion)
     n += 1;                                      // regulariser gradient + SGD update
     return n;
 }

@@ -1048,21 +1048,28 @@ int irs_launch_svf_bwd(const float* v, const float* hist, const float* maxabs, f
         const float* in = (k == 0) ? v : hist + (size_t)(k - 1) * F;
         float* out = (k == 0) ? g_v : (((n_steps - 1 - k) & 1) ? g_u : g_work);
         const float in_scale = (k == 0) ? scale0 : 1.0f;
+        // Only the last four steps can reach displacements beyond the gather limit for |v| < 32 voxels (|u_k| <= |v| /
+        // 2^(n-k)); they get the early-exit scatter companion.  Earlier steps gather with whatever radius their max |u_k|
+        // asks for (exact; slow only for absurd fields), which saves eight empty launches per transition.
+        const bool companion = k >= n_steps - 4;
+        const int radius_max_k = companion ? gather_radius_max : 0x7fffffff;
         if (tma) {
             CUtensorMap map_u, map_g;
             if (irs_tma_encode_field(&map_u, in, 3 * C, d.D, d.H, d.W, BWD_BW, TMA_EY) != 0 ||
                 irs_tma_encode_field(&map_g, gp, 3 * C, d.D, d.H, d.W, BWD_BW, TMA_EY) != 0)
                 return IRS_ERR_UNSUPPORTED;
             le = irs_launch_pdl(svf_step_bwd_tma_kernel, tgrid, dim3(TILE_T), smem_tma, st, map_u, map_g, in, in_scale, gp,
-                                out, maxabs + k, gather_radius_max, in_scale, seg_len, d);
+                                out, maxabs + k, radius_max_k, in_scale, seg_len, d);
         } else {
             le = irs_launch_pdl(svf_step_bwd_tile_kernel, tgrid, dim3(TILE_T), smem, st, in, in_scale, gp, out, maxabs + k,
-                                gather_radius_max, in_scale, seg_len, d);
+                                radius_max_k, in_scale, seg_len, d);
         }
         if (le != cudaSuccess) return (int)le;
-        le = irs_launch_pdl(svf_step_bwd_scatter_kernel, vgrid, dim3(256), 0, st, in, in_scale, gp, (float*)out, maxabs + k,
-                            gather_radius_max, in_scale, C, d);
-        if (le != cudaSuccess) return (int)le;
+        if (companion) {
+            le = irs_launch_pdl(svf_step_bwd_scatter_kernel, vgrid, dim3(256), 0, st, in, in_scale, gp, (float*)out, maxabs + k,
+                                gather_radius_max, in_scale, C, d);
+            if (le != cudaSuccess) return (int)le;
+        }
         gp = out;
     }
     return (int)cudaGetLastError();
