@@ -76,7 +76,11 @@ int irs_launch_warp_vox_bwd(const float* img, const float* u, IrsRng jit, float 
                             const float* g_out, float g_sign, float* g_u, int C, IrsDims d, cudaStream_t st);
 
 // --- irs_svf.cu -------------------------------------------------------------------------------------------------------
-int irs_launch_svf_fwd(const float* v, float* hist, float* maxabs, int n_steps, int C, IrsDims d, cudaStream_t st);
+// energy != nullptr: the first step may also reduce the regulariser energy of v (one double per chain at energy[c *
+// energy_stride]; partials: C * irs_svf_fwd_max_blocks(d) doubles; counters: C zeroed uints); *energy_done tells whether it did
+int irs_launch_svf_fwd(const float* v, float* hist, float* maxabs, int n_steps, int C, IrsDims d, cudaStream_t st,
+                       double* energy, long long energy_stride, double* partials, unsigned int* counters, int* energy_done);
+size_t irs_svf_fwd_max_blocks(IrsDims d);
 int irs_launch_svf_bwd(const float* v, const float* hist, const float* maxabs, float* g_u, float* g_work, float* g_v,
                        int n_steps, int gather_radius_max, int C, IrsDims d, cudaStream_t st);
 

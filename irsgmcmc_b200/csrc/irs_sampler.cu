@@ -94,7 +94,9 @@ int check_config(const irs_sgld_config* c) {
 extern "C" size_t irs_sgld_partials_doubles(const irs_sgld_config* cfg) {
     if (!cfg) return 0;
     IrsDims d{cfg->D, cfg->H, cfg->W};
-    const size_t per_chain = (size_t)irs_data_blocks(d) * IRS_SUM_COUNT;
+    size_t per_chain = (size_t)irs_data_blocks(d) * IRS_SUM_COUNT;
+    const size_t fwd = irs_svf_fwd_max_blocks(d);   // the first squaring step reduces the regulariser energy
+    if (fwd > per_chain) per_chain = fwd;
     return (size_t)cfg->C * per_chain;
 }
 
@@ -102,7 +104,7 @@ extern "C" int irs_sgld_launches_per_step(const irs_sgld_config* c) {
     if (check_config(c) != IRS_OK) return -1;
     int n = 1;                                   // langevin
     n += c->n_taps > 0 ? 3 : 0;                  // Sobolev z, y, x
-    n += 1;                                      // regulariser energy
+    n += (c->W % 4 == 0) ? 0 : 1;                // regulariser energy (an epilogue of the first squaring step otherwise)
     n += c->svf_steps;                           // scaling and squaring
     n += 1;                                      // warp
     n += c->data_term == IRS_DATA_LCC ? 2 : 1;   // LCC boxes / SSD residual
@@ -159,13 +161,16 @@ static int sgld_step_impl(const irs_sgld_config* cfg, const irs_sgld_buffers* b,
     }
 
     mark(tm, st);
-    // (2) regulariser energy y_c                                                  trainer.py:311
-    IRS_TRY(irs_launch_reg_energy(b->css, b->stats + IRS_STAT_ENERGY, IRS_STAT_SIZE, b->partials, b->counters, C, d, st));
-
-    mark(tm, st);
-    // (3) scaling and squaring                                                    trainer.py:294
-    IRS_TRY(irs_launch_svf_fwd(b->css, b->hist, b->maxabs, cfg->svf_steps, C, d, st));
+    // (2) + (3) scaling and squaring; its first step also reduces the regulariser energy y_c of css from the planes it
+    // holds in shared memory (trainer.py:294, 311).  When that kernel cannot run (row pitch not addressable by the TMA
+    // unit) the stand-alone energy kernel follows.
+    int energy_done = 0;
+    IRS_TRY(irs_launch_svf_fwd(b->css, b->hist, b->maxabs, cfg->svf_steps, C, d, st, b->stats + IRS_STAT_ENERGY, IRS_STAT_SIZE,
+                               b->partials, b->counters, &energy_done));
     const float* disp = b->hist + (size_t)(cfg->svf_steps - 1) * F;
+    mark(tm, st);
+    if (!energy_done)
+        IRS_TRY(irs_launch_reg_energy(b->css, b->stats + IRS_STAT_ENERGY, IRS_STAT_SIZE, b->partials, b->counters, C, d, st));
 
     mark(tm, st);
     // (4) warp the moving image at T (+ jitter)                                   trainer.py:296-300
@@ -278,7 +283,7 @@ extern "C" int irs_sgld_gmm_init(const irs_sgld_config* cfg, const irs_sgld_buff
         IRS_TRY(irs_launch_langevin(v_sample, nullptr, 0, 0.f, none, b->css, 1, d, st));
     }
     // hist of a single chain is laid out with stride 3V per step when C = 1
-    IRS_TRY(irs_launch_svf_fwd(b->css, b->hist, b->maxabs, cfg->svf_steps, 1, d, st));
+    IRS_TRY(irs_launch_svf_fwd(b->css, b->hist, b->maxabs, cfg->svf_steps, 1, d, st, nullptr, 0, nullptr, nullptr, nullptr));
     const float* disp = b->hist + (size_t)(cfg->svf_steps - 1) * 3 * V;
     IRS_TRY(irs_launch_warp_vox_fwd(b->moving, disp, none, 0.f, 0, b->im_warped, 1, d, st));
     if (cfg->data_term == IRS_DATA_LCC) {

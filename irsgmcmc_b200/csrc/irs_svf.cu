@@ -538,10 +538,13 @@ __device__ __noinline__ void svf_fwd_voxel_cold(const float* __restrict__ in, fl
 
 // ---- forward step ------------------------------------------------------------------------------------------------------
 // voxels with |u| >= 0.999 (rare; only the last steps of a large deformation) take the exact global gather
-template <int BW>
+// ENERGY: the regulariser energy of the (unscaled) input field -- sum over components and axes of squared forward
+// differences, last difference counted twice (reference model/loss.py:152-161, utils/diff_op.py:83-96) -- accumulated
+// from the ring into `energy_acc`: every neighbour it needs is already in shared memory.
+template <int BW, bool ENERGY>
 __device__ __forceinline__ float svf_fwd_tma_body(const CUtensorMap* tmap, const float* __restrict__ in, float in_scale,
                                                   float* __restrict__ out, IrsDims d, int chain, int x0t, int y0t, int zs,
-                                                  int ze, float* smem) {
+                                                  int ze, float* smem, float& energy_acc) {
     using RG = TmaRing<BW>;
     float* U = smem;                                                           // [4 slots][3][EY][BW]
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + TMA_NS * RG::SS);      // one mbarrier per slot
@@ -574,6 +577,15 @@ __device__ __forceinline__ float svf_fwd_tma_body(const CUtensorMap* tmap, const
         irs_mbar_wait(&bar[(it + 2) & 3], ((it + 2) >> 2) & 1);   // plane z+1 has landed
         if (active) {
             const float* Uz = U + ((it + 1) & 3) * RG::SS + lc;
+            if (ENERGY) {
+                const float* Un = U + ((it + 2) & 3) * RG::SS + lc;   // plane z+1
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch) {
+                    const float c0 = Uz[ch * RG::CS];
+                    energy_acc += irs_diff_energy(c0, Uz[ch * RG::CS + 1], x, d.W) + irs_diff_energy(c0, Uz[ch * RG::CS + BW], y, d.H) +
+                                  irs_diff_energy(c0, Un[ch * RG::CS], z, d.D);
+                }
+            }
             const float ux = Uz[0] * in_scale, uy = Uz[RG::CS] * in_scale, uz = Uz[2 * RG::CS] * in_scale;
             const float amax = fmaxf(fabsf(ux), fmaxf(fabsf(uy), fabsf(uz)));
             m = fmaxf(m, amax);
@@ -616,12 +628,21 @@ constexpr size_t svf_fwd_tile_smem_compact(int R) {
 
 // maxabs_prev = max |u_{k-1}| of the previous step (nullptr for the first): |u_k| <= 2 max |u_{k-1}|, so the TMA ring is
 // taken when that bound is below 1, the wider non-TMA ring otherwise
-// CTAS = resident CTAs per SM the kernel is compiled for (register cap 65536 / 256 / CTAS)
-template <int CTAS>
+// CTAS = resident CTAs per SM the kernel is compiled for (register cap 65536 / 256 / CTAS).  ENERGY (first step only):
+// also reduces the regulariser energy of the input field per chain -- block sums in double, partials[blockIdx.x], the
+// last block of the chain adds them in block order (deterministic) -> energy[chain * energy_stride].
+struct IrsEnergyOut {
+    double* energy;          // nullptr: the caller computes the energy itself
+    long long energy_stride;
+    double* partials;        // gridDim.x doubles per chain
+    unsigned int* counters;  // one per chain, zero on entry, reset on exit
+};
+
+template <int CTAS, bool ENERGY>
 __global__ void __launch_bounds__(TILE_T, CTAS)
 svf_step_fwd_tma_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restrict__ in_all, float in_scale,
                         float* __restrict__ out_all, const float* __restrict__ maxabs_prev, float* __restrict__ maxabs,
-                        int seg_len, IrsDims d) {
+                        int seg_len, IrsDims d, IrsEnergyOut eo) {
     extern __shared__ __align__(128) float smem[];
     irs_pdl_wait();
     irs_pdl_launch_dependents();
@@ -631,11 +652,21 @@ svf_step_fwd_tma_kernel(const __grid_constant__ CUtensorMap tmap, const float* _
     const int x0t = bx * TILE_X, y0t = by * TILE_Y, zs = bz * seg_len, ze = min(zs + seg_len, d.D);
     const float* in = in_all + (size_t)blockIdx.y * 3 * V;
     float* out = out_all + (size_t)blockIdx.y * 3 * V;
-    const bool small = maxabs_prev == nullptr || 2.f * __ldg(maxabs_prev) < 0.999f;
-    float m;
-    if (small) m = svf_fwd_tma_body<FWD_BW>(&tmap, in, in_scale, out, d, blockIdx.y, x0t, y0t, zs, ze, smem);
+    const bool small = maxabs_prev == nullptr || 2.f * __ldg(maxabs_prev) < 0.999f;   // always true for the first step
+    float m, e_acc = 0.f;
+    if (small) m = svf_fwd_tma_body<FWD_BW, ENERGY>(&tmap, in, in_scale, out, d, blockIdx.y, x0t, y0t, zs, ze, smem, e_acc);
     else m = svf_fwd_tile_body_cold(in, in_scale, out, d, x0t, y0t, zs, ze, smem);
     block_max_to_global(m, maxabs);
+    if (ENERGY) {
+        __shared__ double sh[32];
+        __shared__ double total[1];
+        double blk[1];
+        __syncthreads();
+        irs_block_sum<1>(&e_acc, blk, sh);
+        if (irs_grid_sum<1>(blk, eo.partials + (size_t)blockIdx.y * gridDim.x, eo.counters + blockIdx.y, total)) {
+            if (threadIdx.x == 0) eo.energy[(size_t)blockIdx.y * eo.energy_stride] = total[0];
+        }
+    }
 }
 
 // ---- adjoint step ------------------------------------------------------------------------------------------------------
@@ -966,7 +997,15 @@ static int resident_ctas(K kernel, size_t smem) {
 
 static size_t zmax(size_t a, size_t b) { return a > b ? a : b; }
 
-int irs_launch_svf_fwd(const float* v, float* hist, float* maxabs, int n_steps, int C, IrsDims d, cudaStream_t st) {
+// upper bound on the forward grid (x dimension) for a volume: segments are never shorter than 4 planes
+size_t irs_svf_fwd_max_blocks(IrsDims d) {
+    return (size_t)((d.W + TILE_X - 1) / TILE_X) * ((d.H + TILE_Y - 1) / TILE_Y) * ((d.D + 3) / 4);
+}
+
+int irs_launch_svf_fwd(const float* v, float* hist, float* maxabs, int n_steps, int C, IrsDims d, cudaStream_t st,
+                       double* energy, long long energy_stride, double* partials, unsigned int* counters,
+                       int* energy_done) {
+    if (energy_done) *energy_done = 0;
     const size_t F = (size_t)C * 3 * d.V();
     cudaError_t e = cudaMemsetAsync(maxabs, 0, sizeof(float) * n_steps, st);
     if (e != cudaSuccess) return (int)e;
@@ -976,27 +1015,38 @@ int irs_launch_svf_fwd(const float* v, float* hist, float* maxabs, int n_steps, 
     const bool tma = irs_tma_field_ok(v, d.W) && irs_tma_field_ok(hist, d.W) && (F % 4) == 0;
     if (tma) {
         const size_t smem = zmax(svf_fwd_tma_smem(), svf_fwd_tile_smem_compact(RF));
-        using Kern = void (*)(CUtensorMap, const float*, float, float*, const float*, float*, int, IrsDims);
-        static Kern kern = nullptr;
+        using Kern = void (*)(CUtensorMap, const float*, float, float*, const float*, float*, int, IrsDims, IrsEnergyOut);
+        static Kern kern = nullptr, kern_e = nullptr;
         static int slots = 0;
         if (kern == nullptr) {
             int ctas = 5;   // measured at 128^3: 4 -> 0.212 ms, 5 -> 0.200 ms, 6 -> 0.208 ms for the 12 forward steps
             if (const char* ev = getenv("IRS_FWD_CTAS")) ctas = atoi(ev);   // development override
-            kern = ctas <= 4 ? (Kern)svf_step_fwd_tma_kernel<4> : (ctas == 5 ? (Kern)svf_step_fwd_tma_kernel<5> : (Kern)svf_step_fwd_tma_kernel<6>);
+            kern = ctas <= 4 ? (Kern)svf_step_fwd_tma_kernel<4, false>
+                             : (ctas == 5 ? (Kern)svf_step_fwd_tma_kernel<5, false> : (Kern)svf_step_fwd_tma_kernel<6, false>);
+            kern_e = ctas <= 4 ? (Kern)svf_step_fwd_tma_kernel<4, true>
+                               : (ctas == 5 ? (Kern)svf_step_fwd_tma_kernel<5, true> : (Kern)svf_step_fwd_tma_kernel<6, true>);
             e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return (int)e;
+            e = cudaFuncSetAttribute(kern_e, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return (int)e;
             slots = resident_ctas(kern, smem);
         }
         const int seg_len = svf_seg_len(d, C, slots, 3, "IRS_SVF_SEG_FWD", true);
         dim3 tgrid(tiles * ((d.D + seg_len - 1) / seg_len), C);
+        // the first step can reduce the regulariser energy of v on the way (its ring holds every neighbour)
+        const bool with_energy = energy != nullptr && partials != nullptr && counters != nullptr &&
+                                 (size_t)tgrid.x <= irs_svf_fwd_max_blocks(d);
         for (int k = 0; k < n_steps; ++k) {
             const float* in = (k == 0) ? v : hist + (size_t)(k - 1) * F;
             CUtensorMap map;
             if (irs_tma_encode_field(&map, in, 3 * C, d.D, d.H, d.W, FWD_BW, TMA_EY) != 0) return IRS_ERR_UNSUPPORTED;
-            e = irs_launch_pdl(kern, tgrid, dim3(TILE_T), smem, st, map, in, k == 0 ? scale0 : 1.0f, hist + (size_t)k * F,
-                               k == 0 ? nullptr : maxabs + k - 1, maxabs + k, seg_len, d);
+            const bool en = with_energy && k == 0;
+            IrsEnergyOut eo{en ? energy : nullptr, energy_stride, partials, counters};
+            e = irs_launch_pdl(en ? kern_e : kern, tgrid, dim3(TILE_T), smem, st, map, in, k == 0 ? scale0 : 1.0f,
+                               hist + (size_t)k * F, k == 0 ? nullptr : maxabs + k - 1, maxabs + k, seg_len, d, eo);
             if (e != cudaSuccess) return (int)e;
         }
+        if (with_energy && energy_done) *energy_done = 1;
         return (int)cudaGetLastError();
     }
     static int slots = 0;
@@ -1084,7 +1134,8 @@ extern "C" int irs_svf_exp_fwd(const float* v, float* hist, float* maxabs, int n
     IRS_CHECK_DIMS(C, D, H, W);
     IRS_CHECK_CUBE(D, H, W);
     if (!v || !hist || !maxabs || n_steps < 1 || n_steps > IRS_MAX_SVF_STEPS) return IRS_ERR_BAD_ARG;
-    return irs_launch_svf_fwd(v, hist, maxabs, n_steps, C, IrsDims{D, H, W}, (cudaStream_t)stream);
+    return irs_launch_svf_fwd(v, hist, maxabs, n_steps, C, IrsDims{D, H, W}, (cudaStream_t)stream, nullptr, 0, nullptr, nullptr,
+                              nullptr);
 }
 
 extern "C" int irs_svf_outputs(const float* u, const float* lin_x, const float* lin_y, const float* lin_z, float* T,

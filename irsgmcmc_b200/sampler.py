@@ -276,7 +276,7 @@ class SGLDSampler:
             done += 1
         self.iteration += max(n, 0)
 
-    STAGES = ('langevin+sobolev', 'reg_energy', 'svf_fwd', 'warp', 'residual_map', 'mixture_step', 'dL/dz',
+    STAGES = ('langevin+sobolev', 'svf_fwd', 'reg_energy', 'warp', 'residual_map', 'mixture_step', 'dL/dz',
               'map+warp_adjoint', 'reg_hyper', 'svf_adjoint', 'reg_grad+update')
 
     def profile_stages(self):

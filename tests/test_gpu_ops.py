@@ -81,7 +81,9 @@ def test_warp_nearest_bit_exact(ops, dtype):
     assert torch.equal(out.cpu(), O.warp_nearest_aten(seg.expand(C, -1, -1, -1, -1), T))
 
 
-@pytest.mark.parametrize('n,C,amp', [(16, 2, 0.8), (24, 1, 4.0), (20, 2, 9.0)])
+# 16 / 24 / 20 / 40: TMA kernels (40 = several tiles in x and y, partial last tile, several z segments; 4.0 and 9.0 cross
+# |u| = 1, 2 inside the pass and reach the ring / scatter paths); 18 = row pitch the TMA unit cannot address (ring kernels)
+@pytest.mark.parametrize('n,C,amp', [(16, 2, 0.8), (24, 1, 4.0), (20, 2, 9.0), (40, 1, 1.5), (18, 1, 1.0)])
 def test_svf_fwd_bwd(ops, n, C, amp):
     v = smooth_field((C, 3, n, n, n), amp, 11)
     hist, maxabs = ops.svf_exp_fwd(v.to(DEV), 12)
