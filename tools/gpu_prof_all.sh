@@ -1,0 +1,14 @@
+#!/bin/bash
+# final evidence run: tests, smoke, bench (with CPU baseline), reference arm, ncu launch list, two full captures
+mkdir -p gpurun_out
+python -m pytest tests -m gpu -x -q > gpurun_out/t_all.log 2>&1; echo "pytest exit $?" >> gpurun_out/t_all.log; tail -2 gpurun_out/t_all.log
+python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke exit $?" >> gpurun_out/smoke.log; tail -2 gpurun_out/smoke.log
+python bench.py > gpurun_out/bench_default.log 2>&1; echo "exit $?" >> gpurun_out/bench_default.log
+python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
+    python bench.py --steps 3 --warmup 3 --no-graph --no-cpu-baseline > gpurun_out/ncu.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:svf_step -s 96 -c 14 -o gpurun_out/prof_svf -f \
+    python bench.py --steps 3 --warmup 3 --no-graph --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
+ncu --set full --clock-control none -k "regex:langevin|smooth|warp_vox|box_march|gmm_|reg_hyper|sgd_update" -s 150 -c 19 \
+    -o gpurun_out/prof_other -f python bench.py --steps 3 --warmup 3 --no-graph --no-cpu-baseline > gpurun_out/ncu_full2.log 2>&1
+ls -la gpurun_out/*.ncu-rep

@@ -13,3 +13,9 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
 ncu --set full --clock-control none --import-source on -k regex:svf_step -s 96 -c 26 -o gpurun_out/prof_svf -f \
     python bench.py --steps 3 --warmup 3 --no-graph --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
 fi
+if [ "$1" != "noprof" ]; then
+ncu --set full --clock-control none --import-source on -k "regex:langevin|smooth|warp_vox|box_march|gmm_|reg_hyper|sgd_update" -s 150 -c 20 \
+    -o gpurun_out/prof_other -f python bench.py --steps 3 --warmup 3 --no-graph --no-cpu-baseline > gpurun_out/ncu_full2.log 2>&1
+fi
+python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke exit $?" >> gpurun_out/smoke.log; tail -2 gpurun_out/smoke.log
+python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.log 2>&1; tail -1 gpurun_out/bench_ref.log | cut -c1-300

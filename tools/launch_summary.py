@@ -15,8 +15,8 @@ def main(path):
     print(f'# {len(rows)} launches in the list; transitions start at launch ids {idx}')
     if len(idx) < 2:
         s, e = (idx[0] if idx else 0), len(rows)
-    else:
-        s, e = idx[-2], idx[-1]
+    else:   # the shortest slice = a device-resident transition (the end-to-end steps add the image (re)load kernels)
+        s, e = min(zip(idx[1:-1], idx[2:]), key=lambda p: p[1] - p[0]) if len(idx) > 2 else (idx[-2], idx[-1])
     agg = collections.OrderedDict()
     for n, x in zip(names[s:e], t[s:e]):
         a = agg.setdefault(n, [0, 0.0])
