@@ -123,6 +123,16 @@ def test_transition_parity_larger_no_vd(built):
     check(run_pair(32, 3, 'lcc', 'lognormal', True, iters=2, vd=False, jitter=False))
 
 
+def test_transition_parity_row_pitch_not_tma_addressable(built):
+    """W % 4 != 0: the fused step takes the shared-memory ring kernels and the stand-alone energy kernel"""
+    check(run_pair(18, 2, 'lcc', 'lognormal', True, iters=2))
+
+
+def test_transition_parity_multi_tile(built):
+    """40^3: several tiles in x and y (the last ones partial) and several z segments in every marching kernel"""
+    check(run_pair(40, 1, 'lcc', 'l2', False, iters=1))
+
+
 def test_transition_deterministic_no_noise(built):
     check(run_pair(24, 1, 'lcc', 'lognormal', True, iters=2, noise=False, jitter=False, s=1))
 
