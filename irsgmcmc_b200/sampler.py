@@ -303,29 +303,42 @@ class SGLDSampler:
     @torch.no_grad()
     def prefetch_images(self, fixed_im, moving_im, mask):
         """Start uploading the NEXT image pair from (pinned) host memory into staging buffers on a dedicated copy stream
-        and return immediately: the transfer overlaps the transitions running on the compute stream.  The host tensors
-        must stay unchanged until commit_images() has been called.  Double-buffered input pipeline of the sampler."""
+        and return immediately: the transfer -- and the fixed-image side of the LCC map, computed on the same stream once
+        the fixed image has arrived -- overlap the transitions running on the compute stream.  The host tensors must stay
+        unchanged until commit_images() has been called.  Double-buffered input pipeline of the sampler."""
+        lcc = self.cfg.data_loss == 'lcc'
         if getattr(self, '_stage', None) is None:
             self._stage = (torch.empty_like(self.fixed_im), torch.empty_like(self.moving_im), torch.empty_like(self.mask))
+            self._stage_term = torch.empty_like(self.fixed_term) if lcc else None
+            self._stage_a = torch.empty_like(self.fixed_term) if lcc else None
             self._copy_stream = torch.cuda.Stream(device=self.device)
             self._stage_ready, self._stage_free = torch.cuda.Event(), torch.cuda.Event()
         cs = self._copy_stream
         cs.wait_event(self._stage_free)   # the previous commit has read the staging buffers (no-op before the first one)
         with torch.cuda.stream(cs):
             self._stage[0].copy_(fixed_im, non_blocking=True)
+            if lcc:
+                D, H, W = self.dims
+                _lib.check(self.lib.irs_lcc_normalise(_lib.ptr(self._stage[0]), self.cfg.s, _lib.ptr(self._stage_a), None,
+                                                      _lib.ptr(self._stage_term), 1, D, H, W, _lib.stream()))
             self._stage[1].copy_(moving_im, non_blocking=True)
             self._stage[2].copy_(mask.view(torch.uint8) if mask.dtype == torch.bool else mask, non_blocking=True)
             self._stage_ready.record(cs)
 
     @torch.no_grad()
     def commit_images(self):
-        """Make the pair uploaded by prefetch_images() the current one (device-to-device into the resident buffers whose
-        addresses the captured graph holds) and recompute the fixed-image side of the LCC map."""
+        """Make the pair uploaded by prefetch_images() the current one: device-to-device copies into the resident buffers
+        whose addresses the captured graph holds (images, mask, fixed-side LCC terms)."""
         if getattr(self, '_stage', None) is None:
             raise RuntimeError('commit_images() without a preceding prefetch_images()')
-        torch.cuda.current_stream().wait_event(self._stage_ready)
-        self.load_images(*self._stage)
-        self._stage_free.record(torch.cuda.current_stream())
+        cur = torch.cuda.current_stream()
+        cur.wait_event(self._stage_ready)
+        self.fixed_im.copy_(self._stage[0], non_blocking=True)
+        self.moving_im.copy_(self._stage[1], non_blocking=True)
+        self.mask.copy_(self._stage[2], non_blocking=True)
+        if self.cfg.data_loss == 'lcc':
+            self.fixed_term.copy_(self._stage_term, non_blocking=True)
+        self._stage_free.record(cur)
 
     # ------------------------------------------------------------------------------------------------------------------
     # outputs of the last transition (views, no copies: SURVEY K13)
