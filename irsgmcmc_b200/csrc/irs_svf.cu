@@ -927,6 +927,246 @@ svf_step_bwd_tma_kernel(const __grid_constant__ CUtensorMap tmap_u, const __grid
     }
 }
 
+// ---- adjoint step, two targets per thread ----------------------------------------------------------------------------------
+// Same algorithm on a 32 x 16 tile: thread (lx, ly) owns the targets in rows 2 ly and 2 ly + 1, whose neighbourhoods share
+// two of their three source rows -- 12 record loads for two targets instead of 18, half the barriers and TMA issues per
+// voxel, a smaller halo share (34 x 18 records for 512 targets).  128 registers, 2 CTAs per SM.
+constexpr int B2_TY = 16, B2_EY = B2_TY + 2, B2_NR = TMA_EX * B2_EY;                  // 612 records per plane
+constexpr int B2_CS = B2_EY * BWD_BW;                                               // component stride of a plane box
+constexpr uint32_t B2_BYTES = 3u * B2_CS * 4u;
+constexpr int B2_SS = (int)((B2_BYTES + 127u) / 128u * 128u / 4u);                  // slot stride (floats)
+constexpr size_t svf_bwd_tma2_smem() {
+    return sizeof(float) * ((TMA_NS + BWD_NG) * B2_SS + 2 * B2_NR * REC_F) + 8 * (TMA_NS + BWD_NG) + 4 * 3 * B2_EY + 8;
+}
+
+__device__ __forceinline__ float hat_small_rt(float c, int o) {   // hat_small with the offset as a (constant-folded) argument
+    return o < 0 ? fmaxf(c, 0.f) : (o > 0 ? fmaxf(-c, 0.f) : 1.f - fabsf(c));
+}
+
+__device__ __forceinline__ void svf_bwd_tma2_body(const BwdTmaCtx& c) {
+    constexpr int BW = BWD_BW, CS = B2_CS, SS = B2_SS, NRP = (B2_NR + TILE_T - 1) / TILE_T;   // 3 records per thread
+    const int tid = threadIdx.x;
+    const IrsDims d = c.d;
+    const int lx = tid % TILE_X, ly = tid / TILE_X, x = c.x0t + lx;
+    const int ty0 = 2 * ly;                                   // tile row of target 0 (target 1 = ty0 + 1)
+    const int y0 = c.y0t + ty0;
+    const bool act[2] = {x < d.W && y0 < d.H, x < d.W && y0 + 1 < d.H};
+    const int lc0 = (ty0 + 1) * BW + lx + TMA_XO;             // target 0 inside a plane box (target 1: + BW)
+    const int lr0 = (ty0 + 1) * TMA_EX + lx + 1;              // target 0's record (target 1: + TMA_EX)
+    const float xf = (float)x;
+    const float xmax = (float)(d.W - 1), ymax = (float)(d.H - 1), zmax = (float)(d.D - 1);
+    const int Vi = (int)d.V(), HW = d.H * d.W;
+    const int zs = c.zs, ze = c.ze;
+    const int s_first = zs - 1, n_it = (ze - zs) + 2;
+    const int n_u = n_it + 2, n_g = n_it;
+
+    int rec_e[NRP], rec_po[NRP], rec_row[NRP];
+    float rec_lox[NRP], rec_loy[NRP];
+#pragma unroll
+    for (int k = 0; k < NRP; ++k) {
+        const int e = tid + k * TILE_T;
+        const int ey = e / TMA_EX, ex = e - ey * TMA_EX;
+        rec_e[k] = e < B2_NR ? e : -1;
+        rec_po[k] = ey * BW + ex + (TMA_XO - 1);
+        rec_row[k] = ey;
+        rec_lox[k] = -(float)(c.x0t - 1 + ex);
+        rec_loy[k] = -(float)(c.y0t - 1 + ey);
+    }
+
+    if (tid == 0) {
+#pragma unroll
+        for (int i = 0; i < TMA_NS; ++i) irs_mbar_init(&c.bar_u[i], 1);
+#pragma unroll
+        for (int i = 0; i < BWD_NG; ++i) irs_mbar_init(&c.bar_g[i], 1);
+        irs_mbar_fence_init();
+    }
+    if (tid < 3 * B2_EY) c.row_nz[tid] = 0;
+    __syncthreads();
+    if (tid == 0) {
+        for (int q = 0; q < TMA_NS && q < n_u; ++q) {
+            irs_mbar_expect_tx(&c.bar_u[q], B2_BYTES);
+            irs_tma_load_plane(c.U + q * SS, c.tmap_u, &c.bar_u[q], c.x0t - TMA_XO, c.y0t - 1, zs - 2 + q, 3 * c.chain);
+        }
+        for (int q = 0; q < BWD_NG && q < n_g; ++q) {
+            irs_mbar_expect_tx(&c.bar_g[q], B2_BYTES);
+            irs_tma_load_plane(c.G + q * SS, c.tmap_g, &c.bar_g[q], c.x0t - TMA_XO, c.y0t - 1, zs - 1 + q, 3 * c.chain);
+        }
+    }
+
+    auto produce = [&](auto m_tag, int itp) {
+        constexpr int MP = decltype(m_tag)::value;
+        constexpr int B0 = MP, BP = (MP + 1) % 3, BM = (MP + 2) % 3;
+        const int s = s_first + itp;
+        if (s < 0 || s >= d.D) return;
+        const float* Us = c.U + ((itp + 1) & 3) * SS;
+        const float* Gs = c.G + MP * SS;
+        float4* rec = reinterpret_cast<float4*>(c.REC) + (itp & 1) * (2 * B2_NR);
+        const float sf = (float)s;
+#pragma unroll
+        for (int k = 0; k < NRP; ++k) {
+            if (rec_e[k] < 0) continue;
+            const int po = rec_po[k];
+            const float g0 = Gs[po], g1 = Gs[CS + po], g2 = Gs[2 * CS + po];
+            const float cx = irs_clampf(Us[po] * c.in_scale, rec_lox[k], xmax + rec_lox[k]);
+            const float cy = irs_clampf(Us[CS + po] * c.in_scale, rec_loy[k], ymax + rec_loy[k]);
+            const float cz = irs_clampf(Us[2 * CS + po] * c.in_scale, -sf, zmax - sf);
+            const float wm = fmaxf(-cz, 0.f), w0 = 1.f - fabsf(cz), wp = fmaxf(cz, 0.f);
+            float wb[3];
+            wb[B0] = w0; wb[BP] = wp; wb[BM] = wm;
+            float4* r = rec + rec_e[k];
+            r[0] = make_float4(cx, cy, g0, g1);
+            r[B2_NR] = make_float4(g2, wb[0], wb[1], wb[2]);
+            if (g0 != 0.f || g1 != 0.f || g2 != 0.f) c.row_nz[MP * B2_EY + rec_row[k]] = 1;
+        }
+    };
+
+    BwdAcc acc[2];
+    acc[0].clear(); acc[1].clear();
+    int gi = ((s_first - 1) * d.H + y0) * d.W + x;   // index of target 0 in plane s-1 (target 1: + W)
+    irs_mbar_wait(&c.bar_u[0], 0);
+    irs_mbar_wait(&c.bar_u[1], 0);
+    irs_mbar_wait(&c.bar_g[0], 0);
+    produce(std::integral_constant<int, 0>{}, 0);
+    __syncthreads();
+    if (tid == 0 && BWD_NG < n_g) {
+        irs_mbar_expect_tx(&c.bar_g[0], B2_BYTES);
+        irs_tma_load_plane(c.G, c.tmap_g, &c.bar_g[0], c.x0t - TMA_XO, c.y0t - 1, zs - 1 + BWD_NG, 3 * c.chain);
+    }
+
+    auto iteration = [&](auto m_tag, int it) {
+        constexpr int M = decltype(m_tag)::value;
+        constexpr int B0 = M, BP = (M + 1) % 3, BM = (M + 2) % 3;
+        const int s = s_first + it;
+        irs_mbar_wait(&c.bar_u[(it + 2) & 3], ((it + 2) >> 2) & 1);
+        if (tid < B2_EY) c.row_nz[BM * B2_EY + tid] = 0;
+        if (it + 1 < n_it) {
+            irs_mbar_wait(&c.bar_g[BP], ((it + 1) / 3) & 1);
+            produce(std::integral_constant<int, BP>{}, it + 1);
+        }
+        const float* Us = c.U + ((it + 1) & 3) * SS;
+        const float4* rec = reinterpret_cast<const float4*>(c.REC) + (it & 1) * (2 * B2_NR);
+        if ((act[0] || act[1]) && s >= 0 && s < d.D) {
+            const int* nz = c.row_nz + M * B2_EY + ty0;   // flags of record rows ty0 .. ty0 + 3
+            float gown[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
+            // record row rr (0..3) of this thread's neighbourhood: oy = rr - 1 for target 0, rr - 2 for target 1
+#pragma unroll
+            for (int rr = 0; rr < 4; ++rr) {
+                if (nz[rr] == 0) continue;   // warp-uniform: the row holds no gradient
+#pragma unroll
+                for (int ox = -1; ox <= 1; ++ox) {
+                    const float4* r = rec + (lr0 + (rr - 1) * TMA_EX + ox);
+                    const float4 r0 = r[0], r1 = r[B2_NR];
+                    const float wx = hat_small_rt(r0.x, ox);
+                    const float2 g01 = make_float2(r0.z, r0.w);
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        const int oy = rr - 1 - j;
+                        if (oy < -1 || oy > 1) continue;
+                        const float w = wx * hat_small_rt(r0.y, oy);
+                        const float w0 = w * r1.y, w1 = w * r1.z, w2 = w * r1.w;
+                        acc[j].xy[0] = ffma2(make_float2(w0, w0), g01, acc[j].xy[0]); acc[j].z[0] = fmaf(w0, r1.x, acc[j].z[0]);
+                        acc[j].xy[1] = ffma2(make_float2(w1, w1), g01, acc[j].xy[1]); acc[j].z[1] = fmaf(w1, r1.x, acc[j].z[1]);
+                        acc[j].xy[2] = ffma2(make_float2(w2, w2), g01, acc[j].xy[2]); acc[j].z[2] = fmaf(w2, r1.x, acc[j].z[2]);
+                        if (ox == 0 && oy == 0) { gown[j][0] = r0.z; gown[j][1] = r0.w; gown[j][2] = r1.x; }
+                    }
+                }
+            }
+            // ---- direct + position terms ----
+            if (s >= zs && s < ze) {
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    if (!act[j] || nz[1 + j] == 0) continue;
+                    const int lc = lc0 + j * BW;
+                    const float g0 = gown[j][0], g1 = gown[j][1], g2 = gown[j][2];
+                    float px = xf + Us[lc] * c.in_scale, py = (float)(y0 + j) + Us[CS + lc] * c.in_scale,
+                          pz = (float)s + Us[2 * CS + lc] * c.in_scale;
+                    const float mx = irs_inside(px, d.W) * c.in_scale, my = irs_inside(py, d.H) * c.in_scale,
+                                mz = irs_inside(pz, d.D) * c.in_scale;
+                    px = irs_clampf(px, 0.f, xmax); py = irs_clampf(py, 0.f, ymax); pz = irs_clampf(pz, 0.f, zmax);
+                    const float fx0 = floorf(px), fy0 = floorf(py), fz0 = floorf(pz);
+                    const float fx = px - fx0, fy = py - fy0, fz = pz - fz0;
+                    const int ix = (int)fx0, iy = (int)fy0, iz = (int)fz0;
+                    const int s0 = (it + 1 + (iz - s)) & (TMA_NS - 1), s1 = (s0 + 1) & (TMA_NS - 1);
+                    const int i000 = s0 * SS + (iy - (c.y0t - 1)) * BW + (ix - (c.x0t - TMA_XO));
+                    float jx, jy, jz;
+                    ring_interp_grad_dot<BW>(c.U, CS, i000, (s1 - s0) * SS, g0, g1, g2, fx, fy, fz, jx, jy, jz);
+                    acc[j].xy[B0].x += g0 + mx * jx;
+                    acc[j].xy[B0].y += g1 + my * jy;
+                    acc[j].z[B0] += g2 + mz * jz;
+                }
+            }
+        }
+        // ---- target plane s-1 is complete ----
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            if (act[j] && s - 1 >= zs && s - 1 < ze) {
+                const int o = gi + j * d.W;
+                c.g[o] = acc[j].xy[BM].x * c.out_scale;
+                c.g[Vi + o] = acc[j].xy[BM].y * c.out_scale;
+                c.g[2 * Vi + o] = acc[j].z[BM] * c.out_scale;
+            }
+            acc[j].xy[BM] = make_float2(0.f, 0.f);
+            acc[j].z[BM] = 0.f;
+        }
+        gi += HW;
+        __syncthreads();
+        if (tid == 0) {
+            if (it + 4 < n_u) {
+                irs_mbar_expect_tx(&c.bar_u[it & 3], B2_BYTES);
+                irs_tma_load_plane(c.U + (it & 3) * SS, c.tmap_u, &c.bar_u[it & 3], c.x0t - TMA_XO, c.y0t - 1, zs + 2 + it,
+                                   3 * c.chain);
+            }
+            if (it + 1 + BWD_NG < n_g) {
+                irs_mbar_expect_tx(&c.bar_g[BP], B2_BYTES);
+                irs_tma_load_plane(c.G + BP * SS, c.tmap_g, &c.bar_g[BP], c.x0t - TMA_XO, c.y0t - 1, zs + 3 + it, 3 * c.chain);
+            }
+        }
+    };
+
+    for (int it = 0; it < n_it; it += 3) {
+        iteration(std::integral_constant<int, 0>{}, it);
+        if (it + 1 < n_it) iteration(std::integral_constant<int, 1>{}, it + 1);
+        if (it + 2 < n_it) iteration(std::integral_constant<int, 2>{}, it + 2);
+    }
+}
+
+__global__ void __launch_bounds__(TILE_T, 2)
+svf_step_bwd_tma2_kernel(const __grid_constant__ CUtensorMap tmap_u, const __grid_constant__ CUtensorMap tmap_g,
+                         const float* __restrict__ in, float in_scale, const float* __restrict__ gp_all,
+                         float* __restrict__ g_all, const float* __restrict__ maxabs, int radius_max, float out_scale,
+                         int seg_len, IrsDims d) {
+    extern __shared__ __align__(128) float smem[];
+    irs_pdl_wait();
+    irs_pdl_launch_dependents();
+    const int R = svf_gather_radius(__ldg(maxabs));
+    const long long V = d.V();
+    const size_t off = (size_t)blockIdx.y * 3 * V;
+    const int tiles_x = (d.W + TILE_X - 1) / TILE_X, tiles_y = (d.H + B2_TY - 1) / B2_TY;
+    const int bx = blockIdx.x % tiles_x, by = (blockIdx.x / tiles_x) % tiles_y, bz = blockIdx.x / (tiles_x * tiles_y);
+    const int x0t = bx * TILE_X, y0t = by * B2_TY, zs = bz * seg_len, ze = min(zs + seg_len, d.D);
+    if (R == 1 && R <= radius_max) {
+        BwdTmaCtx c;
+        c.tmap_u = &tmap_u; c.tmap_g = &tmap_g;
+        c.U = smem;
+        c.G = smem + TMA_NS * B2_SS;
+        c.REC = smem + (TMA_NS + BWD_NG) * B2_SS;
+        c.bar_u = reinterpret_cast<uint64_t*>(c.REC + 2 * B2_NR * REC_F);
+        c.bar_g = c.bar_u + TMA_NS;
+        c.row_nz = reinterpret_cast<int*>(c.bar_g + BWD_NG);
+        c.in_scale = in_scale; c.out_scale = out_scale; c.d = d;
+        c.x0t = x0t; c.y0t = y0t; c.zs = zs; c.ze = ze; c.chain = blockIdx.y;
+        c.g = g_all + off;
+        svf_bwd_tma2_body(c);
+    } else {   // the 32 x 8 fallbacks, once per half tile
+        svf_bwd_tile_dispatch_cold(R, in + off, in_scale, gp_all + off, g_all + off, radius_max, out_scale, d, x0t, y0t, zs, ze,
+                                   smem);
+        __syncthreads();
+        if (y0t + TILE_Y < d.H)
+            svf_bwd_tile_dispatch_cold(R, in + off, in_scale, gp_all + off, g_all + off, radius_max, out_scale, d, x0t,
+                                       y0t + TILE_Y, zs, ze, smem);
+    }
+}
+
 constexpr size_t svf_bwd_tile_smem(int R) {
     return sizeof(float) * (size_t)(3 * (2 * R + 1) + 3) * (TILE_X + 2 * R) * (TILE_Y + 2 * R);
 }
@@ -938,12 +1178,13 @@ constexpr size_t svf_fwd_tile_smem(int R) {
 // pays `halo` extra plane-iterations.  Picks the segment count with the lowest modelled time.
 // `dynamic`: the TMA kernels' CTAs differ in cost (zero-gradient rows are skipped), so more CTAs than resident slots let
 // the hardware scheduler even the SMs out; measured at 128^3, one chain: 10 (adjoint) / 8 (forward) planes beat 15.
-static int svf_seg_len(IrsDims d, int C, int slots, int halo, const char* env_name = "IRS_SVF_SEG", bool dynamic = false) {
+static int svf_seg_len(IrsDims d, int C, int slots, int halo, const char* env_name = "IRS_SVF_SEG", bool dynamic = false,
+                       int tile_y = TILE_Y) {
     if (const char* e = getenv(env_name)) {   // development override
         const int v = atoi(e);
         if (v >= 1) return v < d.D ? v : d.D;
     }
-    const long long tiles = (long long)((d.W + TILE_X - 1) / TILE_X) * ((d.H + TILE_Y - 1) / TILE_Y) * C;
+    const long long tiles = (long long)((d.W + TILE_X - 1) / TILE_X) * ((d.H + tile_y - 1) / tile_y) * C;
     int best_len = d.D;
     double best_cost = 1e300;
     for (int nseg = 1; nseg <= d.D; ++nseg) {
@@ -1085,12 +1326,23 @@ int irs_launch_svf_bwd(const float* v, const float* hist, const float* maxabs, f
         if (e != cudaSuccess) return (int)e;
         configured_tma = true;
     }
-    static int slots = 0, slots_tma = 0;
+    static int slots = 0, slots_tma = 0, two = -1;
     if (slots == 0) slots = resident_ctas(svf_step_bwd_tile_kernel, smem);
-    if (tma && slots_tma == 0) slots_tma = resident_ctas(svf_step_bwd_tma_kernel, smem_tma);
-    const int seg_len = tma ? svf_seg_len(d, C, slots_tma, 4, "IRS_SVF_SEG_BWD", true) : svf_seg_len(d, C, slots, 6);
+    const size_t smem_tma2 = zmax(svf_bwd_tma2_smem(), smem);
+    if (two < 0) {   // two targets per thread (32 x 16 tiles) unless IRS_BWD_NT=1 (development switch)
+        two = (getenv("IRS_BWD_NT") && atoi(getenv("IRS_BWD_NT")) == 1) ? 0 : 1;
+        if (two) {
+            cudaError_t e = cudaFuncSetAttribute(svf_step_bwd_tma2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tma2);
+            if (e != cudaSuccess) return (int)e;
+        }
+    }
+    const bool tma2 = tma && two == 1;
+    if (tma && slots_tma == 0)
+        slots_tma = tma2 ? resident_ctas(svf_step_bwd_tma2_kernel, smem_tma2) : resident_ctas(svf_step_bwd_tma_kernel, smem_tma);
+    const int seg_len = tma ? svf_seg_len(d, C, slots_tma, 4, "IRS_SVF_SEG_BWD", true, tma2 ? B2_TY : TILE_Y) : svf_seg_len(d, C, slots, 6);
     const int nseg = (d.D + seg_len - 1) / seg_len;
-    dim3 tgrid(tiles * nseg, C);
+    const int tiles2 = ((d.W + TILE_X - 1) / TILE_X) * ((d.H + B2_TY - 1) / B2_TY);
+    dim3 tgrid((tma2 ? tiles2 : tiles) * nseg, C);
     // ping-pong between g_work and the caller's g_u buffer (g_u is only read by the first adjoint step)
     const float* gp = g_u;
     cudaError_t le = cudaSuccess;
@@ -1105,11 +1357,16 @@ int irs_launch_svf_bwd(const float* v, const float* hist, const float* maxabs, f
         const int radius_max_k = companion ? gather_radius_max : 0x7fffffff;
         if (tma) {
             CUtensorMap map_u, map_g;
-            if (irs_tma_encode_field(&map_u, in, 3 * C, d.D, d.H, d.W, BWD_BW, TMA_EY) != 0 ||
-                irs_tma_encode_field(&map_g, gp, 3 * C, d.D, d.H, d.W, BWD_BW, TMA_EY) != 0)
+            const int bh = tma2 ? B2_EY : TMA_EY;
+            if (irs_tma_encode_field(&map_u, in, 3 * C, d.D, d.H, d.W, BWD_BW, bh) != 0 ||
+                irs_tma_encode_field(&map_g, gp, 3 * C, d.D, d.H, d.W, BWD_BW, bh) != 0)
                 return IRS_ERR_UNSUPPORTED;
-            le = irs_launch_pdl(svf_step_bwd_tma_kernel, tgrid, dim3(TILE_T), smem_tma, st, map_u, map_g, in, in_scale, gp,
-                                out, maxabs + k, radius_max_k, in_scale, seg_len, d);
+            if (tma2)
+                le = irs_launch_pdl(svf_step_bwd_tma2_kernel, tgrid, dim3(TILE_T), smem_tma2, st, map_u, map_g, in, in_scale,
+                                    gp, out, maxabs + k, radius_max_k, in_scale, seg_len, d);
+            else
+                le = irs_launch_pdl(svf_step_bwd_tma_kernel, tgrid, dim3(TILE_T), smem_tma, st, map_u, map_g, in, in_scale, gp,
+                                    out, maxabs + k, radius_max_k, in_scale, seg_len, d);
         } else {
             le = irs_launch_pdl(svf_step_bwd_tile_kernel, tgrid, dim3(TILE_T), smem, st, in, in_scale, gp, out, maxabs + k,
                                 radius_max_k, in_scale, seg_len, d);
