@@ -25,9 +25,9 @@ sys.path.insert(0, ROOT)
 BYTES_PER_VOXEL_STEP_LCC = 895.0  # 175 + 60 * n_svf
 BYTES_PER_VOXEL_STEP_SSD = 875.0
 SVF_BWD_BYTES_PER_VOXEL = 36.0    # read g_{k+1} 12 + u_k 12, write g_k 12
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE svf_step_bwd_tma_kernel launch from the committed ncu --set full capture
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE svf_step_bwd_tma2_kernel launch from the committed ncu --set full capture
 # (profiles/r1_ncu_final_summary.txt; 128^3, one chain).  Below the algorithmic 75.5 MB: the 24 MB result stays in the L2.
-NCU_TRAFFIC_BYTES = {(128, 1, 'lcc'): 50.596e6 + 2.211e6}
+NCU_TRAFFIC_BYTES = {(128, 1, 'lcc'): 50.794e6 + 2.081e6}
 
 
 def measured_peaks():
@@ -257,7 +257,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_serial_value = world * C * V * e2e_steps / (float(t.item()) * 1e-3)
 
-    # ---- dominant kernel: one SVF adjoint step (svf_step_bwd_tma_kernel), CUDA events around the 12-step adjoint ----
+    # ---- dominant kernel: one SVF adjoint step (svf_step_bwd_tma2_kernel), CUDA events around the 12-step adjoint ----
     peak, peak_src = measured_peaks()
     stage_ms = {k: 0.0 for k in sampler.STAGES}
     n_prof = 5
@@ -296,7 +296,7 @@ def main():
                         'steps': e2e_steps, 'pipeline': 'double-buffered upload on a copy stream; per-step read-back pipelined by one step',
                         'serial_value': e2e_serial_value},
                 'gpu_launches': sampler.launches_per_step() * args.steps,
-                'roofline': {'bound': 'hbm', 'kernel': 'svf_step_bwd_tma_kernel', 'achieved': achieved, 'peak': peak,
+                'roofline': {'bound': 'hbm', 'kernel': 'svf_step_bwd_tma2_kernel', 'achieved': achieved, 'peak': peak,
                              'unit': 'GB/s', 'frac': achieved / peak,
                              'traffic': NCU_TRAFFIC_BYTES.get((n, C, args.data)), 'peak_source': peak_src,
                              'algorithmic_bytes_per_launch': SVF_BWD_BYTES_PER_VOXEL * C * V, 'kernel_ms': kernel_ms},
