@@ -993,9 +993,11 @@ __device__ __forceinline__ void svf_bwd_tma2_body(const BwdTmaCtx& c) {
         }
     }
 
-    auto produce = [&](auto m_tag, int itp) {
-        constexpr int MP = decltype(m_tag)::value;
-        constexpr int B0 = MP, BP = (MP + 1) % 3, BM = (MP + 2) % 3;
+    // Bank order of a record's z weights is fixed: {target plane s-1, s, s+1}; the accumulators rotate by register moves
+    // once per plane (12 moves) instead of unrolling the plane loop by three -- a third of the code, fewer instruction
+    // cache misses (measured 94 % hit rate / 0.31 stall cycles per issue with the unrolled body).
+    auto produce = [&](int itp) {
+        const int MP = itp % 3;   // ring slot of the gradient plane and of the row flags
         const int s = s_first + itp;
         if (s < 0 || s >= d.D) return;
         const float* Us = c.U + ((itp + 1) & 3) * SS;
@@ -1011,11 +1013,9 @@ __device__ __forceinline__ void svf_bwd_tma2_body(const BwdTmaCtx& c) {
             const float cy = irs_clampf(Us[CS + po] * c.in_scale, rec_loy[k], ymax + rec_loy[k]);
             const float cz = irs_clampf(Us[2 * CS + po] * c.in_scale, -sf, zmax - sf);
             const float wm = fmaxf(-cz, 0.f), w0 = 1.f - fabsf(cz), wp = fmaxf(cz, 0.f);
-            float wb[3];
-            wb[B0] = w0; wb[BP] = wp; wb[BM] = wm;
             float4* r = rec + rec_e[k];
             r[0] = make_float4(cx, cy, g0, g1);
-            r[B2_NR] = make_float4(g2, wb[0], wb[1], wb[2]);
+            r[B2_NR] = make_float4(g2, wm, w0, wp);
             if (g0 != 0.f || g1 != 0.f || g2 != 0.f) c.row_nz[MP * B2_EY + rec_row[k]] = 1;
         }
     };
@@ -1026,22 +1026,22 @@ __device__ __forceinline__ void svf_bwd_tma2_body(const BwdTmaCtx& c) {
     irs_mbar_wait(&c.bar_u[0], 0);
     irs_mbar_wait(&c.bar_u[1], 0);
     irs_mbar_wait(&c.bar_g[0], 0);
-    produce(std::integral_constant<int, 0>{}, 0);
+    produce(0);
     __syncthreads();
     if (tid == 0 && BWD_NG < n_g) {
         irs_mbar_expect_tx(&c.bar_g[0], B2_BYTES);
         irs_tma_load_plane(c.G, c.tmap_g, &c.bar_g[0], c.x0t - TMA_XO, c.y0t - 1, zs - 1 + BWD_NG, 3 * c.chain);
     }
 
-    auto iteration = [&](auto m_tag, int it) {
-        constexpr int M = decltype(m_tag)::value;
-        constexpr int B0 = M, BP = (M + 1) % 3, BM = (M + 2) % 3;
+    for (int it = 0; it < n_it; ++it) {
+        constexpr int B0 = 1, BM = 0;   // accumulator 0 = target plane s-1, 1 = s, 2 = s+1
+        const int M = it % 3, BP = (it + 1) % 3, BMf = (it + 2) % 3;   // ring slots (gradient planes, row flags)
         const int s = s_first + it;
         irs_mbar_wait(&c.bar_u[(it + 2) & 3], ((it + 2) >> 2) & 1);
-        if (tid < B2_EY) c.row_nz[BM * B2_EY + tid] = 0;
+        if (tid < B2_EY) c.row_nz[BMf * B2_EY + tid] = 0;
         if (it + 1 < n_it) {
             irs_mbar_wait(&c.bar_g[BP], ((it + 1) / 3) & 1);
-            produce(std::integral_constant<int, BP>{}, it + 1);
+            produce(it + 1);
         }
         const float* Us = c.U + ((it + 1) & 3) * SS;
         const float4* rec = reinterpret_cast<const float4*>(c.REC) + (it & 1) * (2 * B2_NR);
@@ -1105,8 +1105,9 @@ __device__ __forceinline__ void svf_bwd_tma2_body(const BwdTmaCtx& c) {
                 c.g[Vi + o] = acc[j].xy[BM].y * c.out_scale;
                 c.g[2 * Vi + o] = acc[j].z[BM] * c.out_scale;
             }
-            acc[j].xy[BM] = make_float2(0.f, 0.f);
-            acc[j].z[BM] = 0.f;
+            acc[j].xy[0] = acc[j].xy[1]; acc[j].z[0] = acc[j].z[1];
+            acc[j].xy[1] = acc[j].xy[2]; acc[j].z[1] = acc[j].z[2];
+            acc[j].xy[2] = make_float2(0.f, 0.f); acc[j].z[2] = 0.f;
         }
         gi += HW;
         __syncthreads();
@@ -1121,12 +1122,6 @@ __device__ __forceinline__ void svf_bwd_tma2_body(const BwdTmaCtx& c) {
                 irs_tma_load_plane(c.G + BP * SS, c.tmap_g, &c.bar_g[BP], c.x0t - TMA_XO, c.y0t - 1, zs + 3 + it, 3 * c.chain);
             }
         }
-    };
-
-    for (int it = 0; it < n_it; it += 3) {
-        iteration(std::integral_constant<int, 0>{}, it);
-        if (it + 1 < n_it) iteration(std::integral_constant<int, 1>{}, it + 1);
-        if (it + 2 < n_it) iteration(std::integral_constant<int, 2>{}, it + 2);
     }
 }
 
