@@ -11,6 +11,14 @@
 // (every s with a non-zero hat weight lies inside it), so no atomics are issued -- ATen scatters 24 atomicAdds per
 // voxel here.  Candidates are pruned axis by axis (a zero x-weight skips the y/z loads).  For R above
 // gather_radius_max the exact scatter kernel below takes over (large deformations; still CUDA, no CPU path).
+//
+// Kernels in this file, fastest first; the choice between them is made on the device from max|u_k| (no host sync):
+//   svf_step_fwd_tma_kernel    forward step, TMA plane ring (max|u| < 1 bound; otherwise its in-kernel ring fallback)
+//   svf_step_bwd_tma2_kernel   adjoint step, TMA rings + per-source records, two targets per thread (the default)
+//   svf_step_bwd_tma_kernel    the same with one target per thread (IRS_BWD_NT=1)
+//   svf_step_fwd_tile_kernel / svf_step_bwd_tile_kernel   shared-memory rings fed by ordinary loads: row pitches the TMA
+//                              unit cannot address (W % 4 != 0), and steps with 1 <= max|u| < 2 inside the TMA kernels
+//   svf_step_fwd_kernel, irs_body_svf_bwd, svf_step_bwd_scatter_kernel   global gathers / atomic scatter for larger radii
 #include <cstdlib>
 #include <type_traits>
 
