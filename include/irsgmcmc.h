@@ -58,11 +58,14 @@ int irs_warp3d_nearest_u8(const unsigned char* mask, long long mask_chain_stride
  * autograd (n_steps x grid_sampler_3d_backward), in voxel units.
  *   v        (C,3,D,H,W) velocity in voxels
  *   hist     workspace, n_steps*C*3*D*H*W floats: u_1 .. u_n (u_0 = v / 2^n is not stored); u_n is the displacement
- *   maxabs   n_steps floats: max |u_k| of the input of step k (sizes the adjoint's gather window)
+ *   maxabs   workspace, irs_svf_maxabs_floats() floats: first the n_steps values max |u_k| of the input of step k (they
+ *            size the adjoint's gather window), then per step the same maximum over cells of 32 x 8 x 8 voxels, which lets
+ *            every tile of the adjoint pick its window from the displacements near it
  * Cubic volumes only (D == H == W, else IRS_ERR_UNSUPPORTED): the reference's own coordinate handling is consistent only
  * for cubes (utils/util.py:418-429 scales channel i by shape[2+i]; its data loader pads every image to a cube).
  * ------------------------------------------------------------------------------------------------------------------ */
 size_t irs_svf_hist_floats(int C, int D, int H, int W, int n_steps);
+size_t irs_svf_maxabs_floats(int C, int D, int H, int W, int n_steps);
 int irs_svf_exp_fwd(const float* v, float* hist, float* maxabs, int n_steps, int C, int D, int H, int W, void* stream);
 
 /* T = identity + normalised(u) and/or displacement copy.  lin_x/lin_y/lin_z: the fp32 torch.linspace(-1,1,n) tables of
@@ -235,7 +238,7 @@ typedef struct irs_sgld_buffers {
     float* field_a;              /* (C,3,V) scratch */
     float* field_b;              /* (C,3,V) scratch */
     float* grad_v;               /* (C,3,V) sigma^2 dL/d css: what SGD applies */
-    float* maxabs;               /* svf_steps floats */
+    float* maxabs;               /* irs_svf_maxabs_floats() */
     double* hyper;               /* IRS_HYPER_SIZE doubles (parameters, optimiser state, scratch) */
     double* stats;               /* C * IRS_STAT_SIZE doubles */
     float* gmm_table;            /* C * 16 floats: per chain (lw[8], prec[8]) after that chain's update */

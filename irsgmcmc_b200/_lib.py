@@ -69,6 +69,7 @@ SYMBOLS = {
     'irs_warp3d_nearest_i16': (_i, [_vp, _ll, _vp, _vp, _i, _i, _i, _i, _vp]),
     'irs_warp3d_nearest_u8': (_i, [_vp, _ll, _vp, _vp, _i, _i, _i, _i, _vp]),
     'irs_svf_hist_floats': (_sz, [_i, _i, _i, _i, _i]),
+    'irs_svf_maxabs_floats': (_sz, [_i, _i, _i, _i, _i]),
     'irs_svf_exp_fwd': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     'irs_svf_outputs': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     'irs_svf_exp_bwd': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),

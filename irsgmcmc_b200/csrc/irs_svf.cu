@@ -18,7 +18,7 @@
 //   svf_step_bwd_tma_kernel    the same with one target per thread (IRS_BWD_NT=1)
 //   svf_step_fwd_tile_kernel / svf_step_bwd_tile_kernel   shared-memory rings fed by ordinary loads: row pitches the TMA
 //                              unit cannot address (W % 4 != 0), and steps with 1 <= max|u| < 2 inside the TMA kernels
-//   svf_step_fwd_kernel, irs_body_svf_bwd, svf_step_bwd_scatter_kernel   global gathers / atomic scatter for larger radii
+//   irs_body_svf_fwd / irs_body_svf_bwd, svf_step_bwd_scatter_kernel   global gathers / atomic scatter for larger radii
 #include <cstdlib>
 #include <type_traits>
 
@@ -32,15 +32,69 @@ __device__ __forceinline__ void atomic_max_nonneg(float* addr, float v) {
     atomicMax(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Cell map: besides the global max |u_k| of a step, the forward pass leaves (for steps that reach one voxel) the maximum
+// over cells of 32 x 8 x 8 voxels.  The adjoint of a tile then depends on the displacements NEAR that tile only: a tile
+// whose neighbourhood stays below one voxel takes the TMA kernel even when the field exceeds one voxel elsewhere (typical
+// for a registration: large deformations are local).
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int CELL_X = 32, CELL_Y = 8, CELL_Z = 8;
+struct IrsCells {
+    float* p;          // this step's map, (C, nz, ny, nx) floats, or nullptr
+    int nx, ny, nz;
+};
+__host__ __device__ inline int irs_cells_per_chain(IrsDims d) {
+    return ((d.W + CELL_X - 1) / CELL_X) * ((d.H + CELL_Y - 1) / CELL_Y) * ((d.D + CELL_Z - 1) / CELL_Z);
+}
+static IrsCells make_cells(float* maxabs, int n_steps, int k, int C, IrsDims d) {
+    IrsCells c;
+    c.nx = (d.W + CELL_X - 1) / CELL_X; c.ny = (d.H + CELL_Y - 1) / CELL_Y; c.nz = (d.D + CELL_Z - 1) / CELL_Z;
+    c.p = maxabs + n_steps + (size_t)k * C * c.nx * c.ny * c.nz;
+    return c;
+}
+// maximum of the cell map over the cells that overlap the voxel box [x0,x1] x [y0,y1] x [z0,z1]; all threads get it
+__device__ __forceinline__ float cells_region_max(const IrsCells& cm, int chain, int x0, int x1, int y0, int y1, int z0,
+                                                  int z1) {
+    __shared__ float s_region_max;
+    const int cx0 = max(x0, 0) / CELL_X, cx1 = min(x1 / CELL_X, cm.nx - 1), cy0 = max(y0, 0) / CELL_Y,
+              cy1 = min(y1 / CELL_Y, cm.ny - 1), cz0 = max(z0, 0) / CELL_Z, cz1 = min(z1 / CELL_Z, cm.nz - 1);
+    if (threadIdx.x < 32) {
+        const int nx = cx1 - cx0 + 1, ny = cy1 - cy0 + 1, nz = cz1 - cz0 + 1, n = nx * ny * nz;
+        float m = 0.f;
+        for (int i = threadIdx.x; i < n; i += 32) {
+            const int ix = i % nx, iy = (i / nx) % ny, iz = i / (nx * ny);
+            m = fmaxf(m, __ldg(cm.p + (((size_t)chain * cm.nz + cz0 + iz) * cm.ny + cy0 + iy) * cm.nx + cx0 + ix));
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if (threadIdx.x == 0) s_region_max = m;
+    }
+    __syncthreads();
+    const float r = s_region_max;
+    __syncthreads();
+    return r;
+}
+
+// Cell map of one field, computed only when somebody needs it: the step's max |u| has reached one voxel (the adjoint then
+// picks its window per tile).  One block per cell; launched behind the last forward steps, exits at once otherwise.
 __global__ void __launch_bounds__(256)
-svf_step_fwd_kernel(const float* __restrict__ in, float in_scale, float* __restrict__ out,
-                    float* __restrict__ maxabs, IrsDims d) {
-    const long long V = d.V();
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const int c = blockIdx.y;
+svf_cells_kernel(const float* __restrict__ u_all, float scale, const float* __restrict__ maxabs, IrsCells cm, IrsDims d) {
+    irs_pdl_wait();
+    irs_pdl_launch_dependents();
+    if ((int)floorf(__ldg(maxabs) + 1e-3f) + 1 < 2) return;   // = svf_gather_radius(max |u_k|) < 2: nobody reads the map
+    const int cx = blockIdx.x % cm.nx, cy = (blockIdx.x / cm.nx) % cm.ny, cz = blockIdx.x / (cm.nx * cm.ny), chain = blockIdx.y;
+    const int V = (int)d.V();
+    const float* u = u_all + (size_t)chain * 3 * V;
+    const int lx = threadIdx.x % CELL_X, ly = threadIdx.x / CELL_X;   // 32 x 8 threads = one plane of the cell
+    const int x = cx * CELL_X + lx, y = cy * CELL_Y + ly;
     float m = 0.f;
-    if (i < V) m = irs_body_svf_fwd(in + (size_t)c * 3 * V, in_scale, out + (size_t)c * 3 * V, V, i, d);
-    // block max -> one atomic per block (max is order independent: deterministic)
+    if (x < d.W && y < d.H) {
+        for (int z = cz * CELL_Z; z < min((cz + 1) * CELL_Z, d.D); ++z) {
+            const int i = (z * d.H + y) * d.W + x;
+            m = fmaxf(m, fmaxf(fabsf(__ldg(u + i)), fmaxf(fabsf(__ldg(u + V + i)), fabsf(__ldg(u + 2 * V + i)))));
+        }
+    }
+    m *= scale;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
     __shared__ float sm[8];
@@ -48,8 +102,8 @@ svf_step_fwd_kernel(const float* __restrict__ in, float in_scale, float* __restr
     __syncthreads();
     if (threadIdx.x == 0) {
         float mm = sm[0];
-        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) mm = fmaxf(mm, sm[w]);
-        if (mm > 0.f) atomic_max_nonneg(maxabs, mm);
+        for (int w = 1; w < 8; ++w) mm = fmaxf(mm, sm[w]);
+        cm.p[(((size_t)chain * cm.nz + cz) * cm.ny + cy) * cm.nx + cx] = mm;
     }
 }
 
@@ -486,6 +540,16 @@ __device__ __noinline__ void svf_bwd_tile_dispatch_cold(int R, const float* __re
     svf_bwd_tile_dispatch(R, in, in_scale, gp, g, radius_max, out_scale, d, x0t, y0t, zs, ze, smem);
 }
 
+// Radius a tile may use: the step's global radius R, or 1 when every source within R voxels of the tile's targets moves by
+// less than one voxel (sources farther away cannot reach it: they move by less than R).  Only in the gather regime
+// (2 <= R <= radius_max): beyond it the scatter companion adds the whole transpose and tiles must not do their own.
+__device__ __forceinline__ int svf_local_radius(int R, int radius_max, const IrsCells& cm, int chain, int x0t, int y0t, int ty,
+                                                int zs, int ze) {
+    if (R < 2 || R > radius_max || cm.p == nullptr) return R;
+    const float m = cells_region_max(cm, chain, x0t - R, x0t + TILE_X - 1 + R, y0t - R, y0t + ty - 1 + R, zs - R, ze - 1 + R);
+    return m < 0.999f ? 1 : R;
+}
+
 // gather radius of a step from its max |u|.  The R = 1 kernels assume that x + u never ROUNDS to x +- 1 in fp32, hence the
 // margin (ulp(x) / 2 < 1e-3 for every supported volume size).
 __device__ __forceinline__ int svf_gather_radius(float maxabs) { return (int)floorf(maxabs + 1e-3f) + 1; }
@@ -493,16 +557,17 @@ __device__ __forceinline__ int svf_gather_radius(float maxabs) { return (int)flo
 __global__ void __launch_bounds__(TILE_T, 4)
 svf_step_bwd_tile_kernel(const float* __restrict__ in, float in_scale, const float* __restrict__ gp_all,
                          float* __restrict__ g_all, const float* __restrict__ maxabs, int radius_max, float out_scale,
-                         int seg_len, IrsDims d) {
+                         int seg_len, IrsDims d, IrsCells cm) {
     extern __shared__ __align__(128) float smem[];
     irs_pdl_wait();
     irs_pdl_launch_dependents();
-    const int R = svf_gather_radius(__ldg(maxabs));
+    int R = svf_gather_radius(__ldg(maxabs));
     const long long V = d.V();
     const size_t off = (size_t)blockIdx.y * 3 * V;
     const int tiles_x = (d.W + TILE_X - 1) / TILE_X, tiles_y = (d.H + TILE_Y - 1) / TILE_Y;
     const int bx = blockIdx.x % tiles_x, by = (blockIdx.x / tiles_x) % tiles_y, bz = blockIdx.x / (tiles_x * tiles_y);
     const int x0t = bx * TILE_X, y0t = by * TILE_Y, zs = bz * seg_len, ze = min(zs + seg_len, d.D);
+    R = svf_local_radius(R, radius_max, cm, blockIdx.y, x0t, y0t, TILE_Y, zs, ze);
     svf_bwd_tile_dispatch(R, in + off, in_scale, gp_all + off, g_all + off, radius_max, out_scale, d, x0t, y0t, zs, ze, smem);
 }
 
@@ -905,7 +970,7 @@ __global__ void __launch_bounds__(TILE_T, 4)
 svf_step_bwd_tma_kernel(const __grid_constant__ CUtensorMap tmap_u, const __grid_constant__ CUtensorMap tmap_g,
                         const float* __restrict__ in, float in_scale, const float* __restrict__ gp_all,
                         float* __restrict__ g_all, const float* __restrict__ maxabs, int radius_max, float out_scale,
-                        int seg_len, IrsDims d) {
+                        int seg_len, IrsDims d, IrsCells cm) {
     extern __shared__ __align__(128) float smem[];
     irs_pdl_wait();
     irs_pdl_launch_dependents();
@@ -915,7 +980,8 @@ svf_step_bwd_tma_kernel(const __grid_constant__ CUtensorMap tmap_u, const __grid
     const int tiles_x = (d.W + TILE_X - 1) / TILE_X, tiles_y = (d.H + TILE_Y - 1) / TILE_Y;
     const int bx = blockIdx.x % tiles_x, by = (blockIdx.x / tiles_x) % tiles_y, bz = blockIdx.x / (tiles_x * tiles_y);
     const int x0t = bx * TILE_X, y0t = by * TILE_Y, zs = bz * seg_len, ze = min(zs + seg_len, d.D);
-    if (R == 1 && R <= radius_max) {
+    const int Rl = svf_local_radius(R, radius_max, cm, blockIdx.y, x0t, y0t, TILE_Y, zs, ze);
+    if (Rl == 1 && Rl <= radius_max) {
         using RG = TmaRing<BWD_BW>;
         BwdTmaCtx c;
         c.tmap_u = &tmap_u; c.tmap_g = &tmap_g;
@@ -1137,7 +1203,7 @@ __global__ void __launch_bounds__(TILE_T, 2)
 svf_step_bwd_tma2_kernel(const __grid_constant__ CUtensorMap tmap_u, const __grid_constant__ CUtensorMap tmap_g,
                          const float* __restrict__ in, float in_scale, const float* __restrict__ gp_all,
                          float* __restrict__ g_all, const float* __restrict__ maxabs, int radius_max, float out_scale,
-                         int seg_len, IrsDims d) {
+                         int seg_len, IrsDims d, IrsCells cm) {
     extern __shared__ __align__(128) float smem[];
     irs_pdl_wait();
     irs_pdl_launch_dependents();
@@ -1147,7 +1213,8 @@ svf_step_bwd_tma2_kernel(const __grid_constant__ CUtensorMap tmap_u, const __gri
     const int tiles_x = (d.W + TILE_X - 1) / TILE_X, tiles_y = (d.H + B2_TY - 1) / B2_TY;
     const int bx = blockIdx.x % tiles_x, by = (blockIdx.x / tiles_x) % tiles_y, bz = blockIdx.x / (tiles_x * tiles_y);
     const int x0t = bx * TILE_X, y0t = by * B2_TY, zs = bz * seg_len, ze = min(zs + seg_len, d.D);
-    if (R == 1 && R <= radius_max) {
+    const int Rl = svf_local_radius(R, radius_max, cm, blockIdx.y, x0t, y0t, B2_TY, zs, ze);
+    if (Rl == 1 && Rl <= radius_max) {
         BwdTmaCtx c;
         c.tmap_u = &tmap_u; c.tmap_g = &tmap_g;
         c.U = smem;
@@ -1251,9 +1318,18 @@ int irs_launch_svf_fwd(const float* v, float* hist, float* maxabs, int n_steps, 
                        int* energy_done) {
     if (energy_done) *energy_done = 0;
     const size_t F = (size_t)C * 3 * d.V();
-    cudaError_t e = cudaMemsetAsync(maxabs, 0, sizeof(float) * n_steps, st);
+    cudaError_t e = cudaMemsetAsync(maxabs, 0, sizeof(float) * n_steps, st);   // the cell maps are written, not accumulated
     if (e != cudaSuccess) return (int)e;
     const float scale0 = 1.0f / (float)(1 << n_steps);
+    // Cell map of the input of step k (= the field the adjoint of step k gathers from).  Only the last four steps can reach one
+    // voxel for |v| < 16 voxels (|u_k| <= |v| / 2^(n-k)); earlier steps keep the step-wide radius.  The kernel exits at once
+    // unless max |u_k| >= 1, and with programmatic dependent launch it is invisible in graph replay.
+    auto launch_cells = [&](int k, const float* in, float in_scale) -> cudaError_t {
+        if (k < n_steps - 4 || k == 0) return cudaSuccess;
+        IrsCells cm = make_cells(maxabs, n_steps, k, C, d);
+        dim3 grid((unsigned)(cm.nx * cm.ny * cm.nz), C);
+        return irs_launch_pdl(svf_cells_kernel, grid, dim3(256), 0, st, in, in_scale, (const float*)(maxabs + k), cm, d);
+    };
     constexpr int RF = 2;
     const int tiles = ((d.W + TILE_X - 1) / TILE_X) * ((d.H + TILE_Y - 1) / TILE_Y);
     const bool tma = irs_tma_field_ok(v, d.W) && irs_tma_field_ok(hist, d.W) && (F % 4) == 0;
@@ -1289,6 +1365,8 @@ int irs_launch_svf_fwd(const float* v, float* hist, float* maxabs, int n_steps, 
             e = irs_launch_pdl(en ? kern_e : kern, tgrid, dim3(TILE_T), smem, st, map, in, k == 0 ? scale0 : 1.0f,
                                hist + (size_t)k * F, k == 0 ? nullptr : maxabs + k - 1, maxabs + k, seg_len, d, eo);
             if (e != cudaSuccess) return (int)e;
+            e = launch_cells(k, in, k == 0 ? scale0 : 1.0f);
+            if (e != cudaSuccess) return (int)e;
         }
         if (with_energy && energy_done) *energy_done = 1;
         return (int)cudaGetLastError();
@@ -1301,6 +1379,8 @@ int irs_launch_svf_fwd(const float* v, float* hist, float* maxabs, int n_steps, 
         const float* in = (k == 0) ? v : hist + (size_t)(k - 1) * F;
         e = irs_launch_pdl(svf_step_fwd_tile_kernel<RF>, tgrid, dim3(TILE_T), svf_fwd_tile_smem(RF), st, in,
                            k == 0 ? scale0 : 1.0f, hist + (size_t)k * F, maxabs + k, seg_len, d);
+        if (e != cudaSuccess) return (int)e;
+        e = launch_cells(k, in, k == 0 ? scale0 : 1.0f);
         if (e != cudaSuccess) return (int)e;
     }
     return (int)cudaGetLastError();
@@ -1356,6 +1436,9 @@ int irs_launch_svf_bwd(const float* v, const float* hist, const float* maxabs, f
         // Only the last four steps can reach displacements beyond the gather limit for |v| < 32 voxels (|u_k| <= |v| /
         // 2^(n-k)); they get the early-exit scatter companion.  Earlier steps gather with whatever radius their max |u_k|
         // asks for (exact; slow only for absurd fields), which saves eight empty launches per transition.
+        // the forward pass left the cell map of u_k behind the n_steps global maxima for the last four steps (read-only here)
+        IrsCells cm = make_cells(const_cast<float*>(maxabs), n_steps, k, C, d);
+        if (k < n_steps - 4 || k == 0) cm.p = nullptr;
         const bool companion = k >= n_steps - 4;
         const int radius_max_k = companion ? gather_radius_max : 0x7fffffff;
         if (tma) {
@@ -1366,13 +1449,13 @@ int irs_launch_svf_bwd(const float* v, const float* hist, const float* maxabs, f
                 return IRS_ERR_UNSUPPORTED;
             if (tma2)
                 le = irs_launch_pdl(svf_step_bwd_tma2_kernel, tgrid, dim3(TILE_T), smem_tma2, st, map_u, map_g, in, in_scale,
-                                    gp, out, maxabs + k, radius_max_k, in_scale, seg_len, d);
+                                    gp, out, maxabs + k, radius_max_k, in_scale, seg_len, d, cm);
             else
                 le = irs_launch_pdl(svf_step_bwd_tma_kernel, tgrid, dim3(TILE_T), smem_tma, st, map_u, map_g, in, in_scale, gp,
-                                    out, maxabs + k, radius_max_k, in_scale, seg_len, d);
+                                    out, maxabs + k, radius_max_k, in_scale, seg_len, d, cm);
         } else {
             le = irs_launch_pdl(svf_step_bwd_tile_kernel, tgrid, dim3(TILE_T), smem, st, in, in_scale, gp, out, maxabs + k,
-                                radius_max_k, in_scale, seg_len, d);
+                                radius_max_k, in_scale, seg_len, d, cm);
         }
         if (le != cudaSuccess) return (int)le;
         if (companion) {
@@ -1383,6 +1466,12 @@ int irs_launch_svf_bwd(const float* v, const float* hist, const float* maxabs, f
         gp = out;
     }
     return (int)cudaGetLastError();
+}
+
+// n_steps global maxima followed by n_steps cell maps (C x cells of 32 x 8 x 8 voxels)
+extern "C" size_t irs_svf_maxabs_floats(int C, int D, int H, int W, int n_steps) {
+    if (C < 1 || D < 1 || H < 1 || W < 1 || n_steps < 1) return 0;
+    return (size_t)n_steps * (1 + (size_t)C * irs_cells_per_chain(IrsDims{D, H, W}));
 }
 
 extern "C" size_t irs_svf_hist_floats(int C, int D, int H, int W, int n_steps) {

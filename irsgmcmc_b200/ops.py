@@ -68,7 +68,10 @@ def svf_exp_fwd(v, n_steps=12):
     _f32(v)
     C, D, H, W = _dims(v)
     hist = torch.empty(n_steps, C, 3, D, H, W, device=v.device, dtype=torch.float32)
-    maxabs = torch.zeros(n_steps, device=v.device, dtype=torch.float32)
+    # per-step max |u_k| followed by the per-cell maxima the adjoint reads (irs_svf_maxabs_floats); the returned tensor is
+    # the first n_steps entries, a view that keeps the whole block alive
+    mbuf = torch.zeros(int(lib.irs_svf_maxabs_floats(C, D, H, W, n_steps)), device=v.device, dtype=torch.float32)
+    maxabs = mbuf[:n_steps]
     _lib.check(lib.irs_svf_exp_fwd(_lib.ptr(v), _lib.ptr(hist), _lib.ptr(maxabs), n_steps, C, D, H, W, _lib.stream()))
     return hist, maxabs
 

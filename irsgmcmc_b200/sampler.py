@@ -100,7 +100,7 @@ class SGLDSampler:
         self._field_a = torch.empty(C, 3, D, H, W, **f32)
         self._field_b = torch.empty(C, 3, D, H, W, **f32)
         self.grad_v = torch.zeros(C, 3, D, H, W, **f32)
-        self._maxabs = torch.zeros(cfg.svf_steps, **f32)
+        self._maxabs = torch.zeros(int(self.lib.irs_svf_maxabs_floats(C, D, H, W, cfg.svf_steps)), **f32)
         self.hyper = torch.zeros(_lib.HYPER_SIZE, device=dev, dtype=torch.float64)
         self.stats = torch.zeros(C, _lib.STAT_SIZE, device=dev, dtype=torch.float64)
         self._gmm_table = torch.zeros(C, 16, **f32)

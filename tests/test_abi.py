@@ -48,6 +48,9 @@ def test_argument_validation_without_gpu(built):
     assert lib.irs_sgld_step(ctypes.byref(cfg), None, None) == -1
     assert lib.irs_sgld_launches_per_step(ctypes.byref(cfg)) == -1
     assert lib.irs_svf_hist_floats(2, 4, 5, 6, 12) == 12 * 2 * 3 * 4 * 5 * 6
+    # 12 global maxima + 12 cell maps of 2 chains x (1 x 1 x 1) cells of 32 x 8 x 8 voxels
+    assert lib.irs_svf_maxabs_floats(2, 4, 5, 6, 12) == 12 * (1 + 2 * 1)
+    assert lib.irs_svf_maxabs_floats(1, 128, 128, 128, 12) == 12 * (1 + 4 * 16 * 16)
 
 
 def test_config_struct_layout_matches_c(built):

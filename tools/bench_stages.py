@@ -21,6 +21,6 @@ e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=Tr
 e0.record(); s.step(a.steps, use_graph=True); e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / a.steps
 print(f'{n}^3 x {C} chains: {ms:.3f} ms/step, {C * n ** 3 / ms / 1e6:.3f} G voxel-steps/s')
-print('maxabs per step', [round(float(x), 3) for x in s._maxabs.tolist()])
+print('maxabs per step', [round(float(x), 3) for x in s._maxabs[:12].tolist()])
 st = s.profile_stages()
 print({k: round(v, 4) for k, v in st.items()})
