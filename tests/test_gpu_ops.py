@@ -107,6 +107,32 @@ def test_svf_fwd_bwd(ops, n, C, amp):
         assert grad_ok(g, g32, g64, f'svf bwd amp={amp} radius_max={radius_max}')
 
 
+@pytest.mark.parametrize('n,bump', [(48, 3.0), (40, 7.0)])
+def test_svf_adjoint_window_per_tile(ops, n, bump):
+    """a deformation that exceeds one voxel only inside a local bump: tiles far from it keep the TMA kernel (window 1) while
+    the tiles around it take the wider ring (3.0: |u| < 2, gather regime) or everything falls back (7.0: scatter regime
+    in the last step, per-tile windows in the one before) -- forward and adjoint must stay exact in every mix"""
+    C = 1
+    v = smooth_field((C, 3, n, n, n), 0.6, 21)
+    z, y, x = torch.meshgrid(torch.arange(n), torch.arange(n), torch.arange(n), indexing='ij')
+    c = torch.tensor([0.72 * n, 0.3 * n, 0.25 * n])
+    w = torch.exp(-((z - c[0]) ** 2 + (y - c[1]) ** 2 + (x - c[2]) ** 2) / (2 * (0.09 * n) ** 2))
+    v = v + bump * w * torch.tensor([1.0, -0.7, 0.5]).view(1, 3, 1, 1, 1)
+    hist, maxabs = ops.svf_exp_fwd(v.to(DEV), 12)
+    assert float(maxabs[-1]) > 1.0 and float(maxabs[0]) < 0.01
+    v64 = v.double().requires_grad_(True)
+    T64, d64 = O.svf_exp_aten(v64, 12, exact_grid=True)
+    v32 = v.clone().requires_grad_(True)
+    T32, d32 = O.svf_exp_aten(v32, 12)
+    assert three_numbers(hist[-1], d32, d64)[0] < 1e-5
+    G = torch.randn(C, 3, n, n, n, generator=torch.Generator().manual_seed(6))
+    g64, = torch.autograd.grad((d64 * G.double()).sum(), v64)
+    g32, = torch.autograd.grad((d32 * G).sum(), v32)
+    for radius_max in (2, 3):
+        g = ops.svf_exp_bwd(v.to(DEV), hist, maxabs, G.to(DEV), radius_max)
+        assert grad_ok(g, g32, g64, f'svf bwd local bump {bump} radius_max={radius_max}')
+
+
 @pytest.mark.parametrize('s', [1, 2, 3])
 def test_langevin_sobolev(ops, s):
     from irsgmcmc_b200.utils.functions import langevin_sobolev, Sobolev_kernel_1D
