@@ -106,6 +106,7 @@ extern "C" int irs_sgld_launches_per_step(const irs_sgld_config* c) {
     n += c->n_taps > 0 ? 3 : 0;                  // Sobolev z, y, x
     n += (c->W % 4 == 0) ? 0 : 1;                // regulariser energy (an epilogue of the first squaring step otherwise)
     n += c->svf_steps;                           // scaling and squaring
+    n += c->svf_steps > 4 ? 4 : c->svf_steps - 1; // cell maps behind the last four steps (exit at once below one voxel)
     n += 1;                                      // warp
     n += c->data_term == IRS_DATA_LCC ? 2 : 1;   // LCC boxes / SSD residual
     n += c->C * (c->virtual_decimation ? 2 : 1); // per-chain mixture statistics (+ VD lag sums) + Adam
