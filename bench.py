@@ -27,7 +27,7 @@ BYTES_PER_VOXEL_STEP_SSD = 875.0
 SVF_BWD_BYTES_PER_VOXEL = 36.0    # read g_{k+1} 12 + u_k 12, write g_k 12
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE svf_step_bwd_tma2_kernel launch from the committed ncu --set full capture
 # (profiles/r1_ncu_final_summary.txt; 128^3, one chain).  Below the algorithmic 75.5 MB: the 24 MB result stays in the L2.
-NCU_TRAFFIC_BYTES = {(128, 1, 'lcc'): 50.569e6 + 3.268e6}
+NCU_TRAFFIC_BYTES = {(128, 1, 'lcc'): 50.777e6 + 3.067e6}
 
 
 def measured_peaks():
