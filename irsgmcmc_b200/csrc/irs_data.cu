@@ -556,8 +556,16 @@ masked_moments_kernel(const float* __restrict__ z, const unsigned char* __restri
 }  // namespace
 
 int irs_data_blocks(IrsDims d) {
+    static int cap = 0;   // development override
+    if (cap == 0) {
+        cap = -1;
+        if (const char* e = getenv("IRS_DATA_BLOCKS")) { const int v = atoi(e); if (v >= 1) cap = v; }
+    }
+    // 4 CTAs per SM x 148 SMs: enough loads in flight, short final reduction; 2 per SM up to 128^3, where the final
+    // reduction over the blocks is a visible part of these latency-bound kernels (measured 48 vs 51 us for the mixture step)
+    const int limit = cap > 0 ? cap : (d.V() <= 128ll * 128 * 128 ? 296 : 592);
     long long b = (d.V() + 255) / 256;
-    return (int)(b < 592 ? b : 592);  // 4 CTAs per SM x 148 SMs: enough loads in flight, short final reduction
+    return (int)(b < limit ? b : limit);
 }
 
 int irs_launch_lcc_fwd(const float* im, const float* zF, int s, float* a, float* rs, float* z, int C, IrsDims d,
