@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define IRS_ABI_VERSION 1
+#define IRS_ABI_VERSION 2   /* 2: irs_svf_maxabs_floats() sizes the maxabs workspace (per-cell maxima behind the per-step ones) */
 
 #define IRS_OK 0
 #define IRS_ERR_BAD_ARG (-1)

@@ -111,7 +111,7 @@ def load():
     for name, (restype, argtypes) in SYMBOLS.items():
         fn = getattr(lib, name)
         fn.restype, fn.argtypes = restype, argtypes
-    if lib.irs_abi_version() != 1:
+    if lib.irs_abi_version() != 2:
         raise RuntimeError('libirsgmcmc.so ABI version mismatch')
     _lib = lib
     return lib
