@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define IRS_ABI_VERSION 2   /* 2: irs_svf_maxabs_floats() sizes the maxabs workspace (per-cell maxima behind the per-step ones) */
+#define IRS_ABI_VERSION 3   /* 2: irs_svf_maxabs_floats() sizes the maxabs workspace; 3: cubic B-spline FFD entry points */
 
 #define IRS_OK 0
 #define IRS_ERR_BAD_ARG (-1)
@@ -78,6 +78,29 @@ int irs_svf_outputs(const float* u, const float* lin_x, const float* lin_y, cons
  * radius exceeds gather_radius_max use an exact atomic scatter kernel instead. */
 int irs_svf_exp_bwd(const float* v, const float* hist, const float* maxabs, float* g_u, float* g_work, float* g_v,
                     int n_steps, int gather_radius_max, int C, int D, int H, int W, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------ *
+ * Cubic B-spline free-form deformation -- replaces Cubic_B_spline_FFD_3D.forward (utils/transformation.py:132-152: per
+ * axis conv1D(transpose=True) = F.conv_transpose1d with stride s, the 4 s - 1 taps of B_spline_1D_kernel(s) :95-103 and
+ * padding 2 s - 1, then the crop [s, s + n)) and its autograd.  SVFFD_3D (:155-164) is this followed by irs_svf_exp_fwd.
+ *   cp      (C,3,gD,gH,gW) control-point velocities, g = get_control_grid_size(dims, cps) (utils/util.py:61-69) or any
+ *           size whose un-cropped result (g-1) s + 1 covers the crop
+ *   dense   (C,3,D,H,W)
+ *   kernel_*_host  HOST arrays: the reference's B_spline_1D_kernel(s) for the D, H and W axis (4 s - 1 floats, s <= 8)
+ *   work    irs_ffd_work_floats() floats
+ * irs_bspline_axis is one axis of it on an (outer, len, inner) array -- conv1D(x, kernel, dim, stride, padding = 2 s - 1,
+ * transpose=True) with crop_start = 0 and n = (g-1) s + 1; adjoint != 0 maps (outer, n, inner) back to (outer, g, inner).
+ * ------------------------------------------------------------------------------------------------------------------ */
+size_t irs_ffd_work_floats(int C, int gD, int gH, int gW, int D, int H, int W);
+int irs_ffd_fwd(const float* cp, const float* kernel_d_host, const float* kernel_h_host, const float* kernel_w_host,
+                int sD, int sH, int sW, float* work, float* dense, int C, int gD, int gH, int gW, int D, int H, int W,
+                void* stream);
+/* adjoint: g_dense (C,3,D,H,W) -> g_cp (C,3,gD,gH,gW); gathers over each control point's support, no atomics */
+int irs_ffd_bwd(const float* g_dense, const float* kernel_d_host, const float* kernel_h_host,
+                const float* kernel_w_host, int sD, int sH, int sW, float* work, float* g_cp, int C, int gD, int gH,
+                int gW, int D, int H, int W, void* stream);
+int irs_bspline_axis(const float* in, float* out, int adjoint, long long outer, int g, int n, long long inner,
+                     const float* kernel_host, int stride, int crop_start, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------ *
  * Langevin proposal + Sobolev smoothing -- replaces SGLD.forward (utils/functions.py:76-80, utils/util.py:48-58) and

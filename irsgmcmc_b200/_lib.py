@@ -73,6 +73,10 @@ SYMBOLS = {
     'irs_svf_exp_fwd': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     'irs_svf_outputs': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     'irs_svf_exp_bwd': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    'irs_ffd_work_floats': (_sz, [_i, _i, _i, _i, _i, _i, _i]),
+    'irs_ffd_fwd': (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    'irs_ffd_bwd': (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    'irs_bspline_axis': (_i, [_vp, _vp, _i, _ll, _i, _i, _ll, _vp, _i, _i, _vp]),
     'irs_langevin_sobolev': (_i, [_vp, _vp, _ll, _f, _vp, _ull, _ull, _i, _vp, _i, _vp, _vp, _i, _i, _i, _i, _vp]),
     'irs_diff_fwd': (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     'irs_diff_bwd': (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
@@ -111,7 +115,7 @@ def load():
     for name, (restype, argtypes) in SYMBOLS.items():
         fn = getattr(lib, name)
         fn.restype, fn.argtypes = restype, argtypes
-    if lib.irs_abi_version() != 2:
+    if lib.irs_abi_version() != 3:
         raise RuntimeError('libirsgmcmc.so ABI version mismatch')
     _lib = lib
     return lib

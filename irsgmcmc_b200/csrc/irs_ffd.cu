@@ -1,0 +1,115 @@
+// irs_ffd.cu -- cubic B-spline free-form deformation: control-point velocities -> dense velocity field and its adjoint
+// (SURVEY.md section 8f, N3).  Replaces Cubic_B_spline_FFD_3D.forward / conv1D(transpose=True) and their autograd,
+// reference utils/transformation.py:106-152.
+//
+// The tensor product is evaluated like the reference does, one axis at a time (z, y, x), so the two intermediates live on
+// the coarse grid along the axes not yet expanded: at cps 4 and 128^3 they are 0.6 MB and 6.9 MB per chain next to the
+// 25 MB result, i.e. the op moves about 18 B per voxel instead of the 12 B minimum, with 4 multiply-adds per output
+// element and pass.  The adjoint runs the same three passes in reverse as gathers over each control point's support
+// (4 s - 1 elements): deterministic, no atomics.  Arithmetic: csrc/irs_ffd_body.cuh.
+#include "irs_ffd_body.cuh"
+#include "irs_kernels.cuh"
+
+namespace {
+
+template <int VEC, bool ADJOINT>
+__global__ void __launch_bounds__(256)
+ffd_axis_kernel(const float* __restrict__ in, float* __restrict__ out, long long total, int g, int n, long long inner,
+                const __grid_constant__ IrsFfdAxis ax) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total / VEC; i += stride) {
+        float r[VEC];
+#pragma unroll
+        for (int k = 0; k < VEC; ++k)
+            r[k] = ADJOINT ? irs_body_ffd_axis_bwd(in, i * VEC + k, g, n, inner, ax)
+                           : irs_body_ffd_axis_fwd(in, i * VEC + k, g, n, inner, ax);
+        if constexpr (VEC == 4) reinterpret_cast<float4*>(out)[i] = make_float4(r[0], r[1], r[2], r[3]);
+        else out[i] = r[0];
+    }
+}
+
+int make_axis(IrsFfdAxis& ax, const float* kernel_host, int s, int off) {
+    if (!kernel_host || s < 1 || s > IRS_FFD_MAX_STRIDE || off < 0) return IRS_ERR_BAD_ARG;
+    ax.s = s;
+    ax.off = off;
+    for (int j = 0; j <= IRS_FFD_MAX_KERNEL; ++j) ax.k[j] = j < 4 * s - 1 ? kernel_host[j] : 0.f;
+    return IRS_OK;
+}
+
+// one axis pass; `adjoint` maps (outer, n, inner) -> (outer, g, inner), otherwise (outer, g, inner) -> (outer, n, inner)
+int launch_axis(const float* in, float* out, bool adjoint, long long outer, int g, int n, long long inner,
+                const IrsFfdAxis& ax, cudaStream_t st) {
+    // every dense element must exist in the un-cropped result of the transposed convolution: (g - 1) s + 1 elements
+    if (g < 1 || n < 1 || outer < 1 || inner < 1 || (long long)ax.off + n > (long long)(g - 1) * ax.s + 1)
+        return IRS_ERR_BAD_ARG;
+    const long long total = outer * (adjoint ? g : n) * inner;
+    const bool vec = total % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+    const long long work = vec ? total / 4 : total;
+    long long blocks = (work + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks < 1) blocks = 1;
+    if (vec) {
+        if (adjoint) ffd_axis_kernel<4, true><<<(unsigned)blocks, 256, 0, st>>>(in, out, total, g, n, inner, ax);
+        else ffd_axis_kernel<4, false><<<(unsigned)blocks, 256, 0, st>>>(in, out, total, g, n, inner, ax);
+    } else {
+        if (adjoint) ffd_axis_kernel<1, true><<<(unsigned)blocks, 256, 0, st>>>(in, out, total, g, n, inner, ax);
+        else ffd_axis_kernel<1, false><<<(unsigned)blocks, 256, 0, st>>>(in, out, total, g, n, inner, ax);
+    }
+    IRS_LAUNCH_CHECK();
+    return IRS_OK;
+}
+
+int check_ffd(int C, int gD, int gH, int gW, int D, int H, int W) {
+    IRS_CHECK_DIMS(C, D, H, W);
+    if (gD < 1 || gH < 1 || gW < 1) return IRS_ERR_BAD_ARG;
+    return IRS_OK;
+}
+
+}  // namespace
+
+extern "C" size_t irs_ffd_work_floats(int C, int gD, int gH, int gW, int D, int H, int W) {
+    if (C < 1 || gD < 1 || gH < 1 || gW < 1 || D < 1 || H < 1 || W < 1) return 0;
+    return (size_t)C * 3 * ((size_t)D * gH * gW + (size_t)D * H * gW);
+}
+
+extern "C" int irs_bspline_axis(const float* in, float* out, int adjoint, long long outer, int g, int n, long long inner,
+                                const float* kernel_host, int stride, int crop_start, void* stream) {
+    if (!in || !out) return IRS_ERR_BAD_ARG;
+    IrsFfdAxis ax;
+    IRS_TRY(make_axis(ax, kernel_host, stride, crop_start));
+    return launch_axis(in, out, adjoint != 0, outer, g, n, inner, ax, (cudaStream_t)stream);
+}
+
+extern "C" int irs_ffd_fwd(const float* cp, const float* kernel_d_host, const float* kernel_h_host,
+                           const float* kernel_w_host, int sD, int sH, int sW, float* work, float* dense, int C, int gD,
+                           int gH, int gW, int D, int H, int W, void* stream) {
+    IRS_TRY(check_ffd(C, gD, gH, gW, D, H, W));
+    if (!cp || !work || !dense) return IRS_ERR_BAD_ARG;
+    IrsFfdAxis az, ay, ax;
+    IRS_TRY(make_axis(az, kernel_d_host, sD, sD));
+    IRS_TRY(make_axis(ay, kernel_h_host, sH, sH));
+    IRS_TRY(make_axis(ax, kernel_w_host, sW, sW));
+    cudaStream_t st = (cudaStream_t)stream;
+    float* t1 = work;                                    // (C 3, D, gH, gW)
+    float* t2 = work + (size_t)C * 3 * D * gH * gW;      // (C 3, D, H, gW)
+    IRS_TRY(launch_axis(cp, t1, false, (long long)C * 3, gD, D, (long long)gH * gW, az, st));
+    IRS_TRY(launch_axis(t1, t2, false, (long long)C * 3 * D, gH, H, gW, ay, st));
+    return launch_axis(t2, dense, false, (long long)C * 3 * D * H, gW, W, 1, ax, st);
+}
+
+extern "C" int irs_ffd_bwd(const float* g_dense, const float* kernel_d_host, const float* kernel_h_host,
+                           const float* kernel_w_host, int sD, int sH, int sW, float* work, float* g_cp, int C, int gD,
+                           int gH, int gW, int D, int H, int W, void* stream) {
+    IRS_TRY(check_ffd(C, gD, gH, gW, D, H, W));
+    if (!g_dense || !work || !g_cp) return IRS_ERR_BAD_ARG;
+    IrsFfdAxis az, ay, ax;
+    IRS_TRY(make_axis(az, kernel_d_host, sD, sD));
+    IRS_TRY(make_axis(ay, kernel_h_host, sH, sH));
+    IRS_TRY(make_axis(ax, kernel_w_host, sW, sW));
+    cudaStream_t st = (cudaStream_t)stream;
+    float* t1 = work;
+    float* t2 = work + (size_t)C * 3 * D * gH * gW;
+    IRS_TRY(launch_axis(g_dense, t2, true, (long long)C * 3 * D * H, gW, W, 1, ax, st));
+    IRS_TRY(launch_axis(t2, t1, true, (long long)C * 3 * D, gH, H, gW, ay, st));
+    return launch_axis(t1, g_cp, true, (long long)C * 3, gD, D, (long long)gH * gW, az, st);
+}

@@ -97,6 +97,70 @@ def svf_exp_bwd(v, hist, maxabs, g_u, gather_radius_max=2):
     return g_v
 
 
+def _ffd_args(cp, kernels, cps, dims):
+    lib = _lib.load()
+    _lib.require_cuda(cp)
+    _f32(cp)
+    if cp.dim() != 5 or cp.shape[1] != 3 or len(kernels) != 3 or len(cps) != 3 or len(dims) != 3:
+        raise RuntimeError('cubic B-spline FFD: expected a (C,3,gD,gH,gW) field, three kernels, spacings and sizes')
+    for k, s in zip(kernels, cps):
+        if len(k) != 4 * int(s) - 1:
+            raise RuntimeError('cubic B-spline FFD: a kernel of 4 * cps - 1 taps per axis is expected')
+    return lib, [_lib.host_floats([float(x) for x in k]) for k in kernels], [int(s) for s in cps]
+
+
+def ffd_fwd(cp, kernels, cps, dims):
+    """dense (C,3,D,H,W) velocity field of control-point velocities cp (C,3,gD,gH,gW); kernels: the three
+    B_spline_1D_kernel(s) as host sequences (reference utils/transformation.py:132-152)"""
+    lib, hk, st = _ffd_args(cp, kernels, cps, dims)
+    C, (gD, gH, gW), (D, H, W) = cp.shape[0], cp.shape[2:], [int(n) for n in dims]
+    work = torch.empty(int(lib.irs_ffd_work_floats(C, gD, gH, gW, D, H, W)), device=cp.device, dtype=torch.float32)
+    dense = torch.empty(C, 3, D, H, W, device=cp.device, dtype=torch.float32)
+    _lib.check(lib.irs_ffd_fwd(_lib.ptr(cp), hk[0], hk[1], hk[2], st[0], st[1], st[2], _lib.ptr(work), _lib.ptr(dense),
+                               C, gD, gH, gW, D, H, W, _lib.stream()))
+    return dense
+
+
+def ffd_bwd(g_dense, kernels, cps, grid_size):
+    """adjoint of ffd_fwd: (C,3,D,H,W) -> (C,3,gD,gH,gW)"""
+    lib, hk, st = _ffd_args(g_dense, kernels, cps, grid_size)
+    C, (D, H, W), (gD, gH, gW) = g_dense.shape[0], g_dense.shape[2:], [int(n) for n in grid_size]
+    work = torch.empty(int(lib.irs_ffd_work_floats(C, gD, gH, gW, D, H, W)), device=g_dense.device, dtype=torch.float32)
+    g_cp = torch.empty(C, 3, gD, gH, gW, device=g_dense.device, dtype=torch.float32)
+    _lib.check(lib.irs_ffd_bwd(_lib.ptr(g_dense), hk[0], hk[1], hk[2], st[0], st[1], st[2], _lib.ptr(work),
+                               _lib.ptr(g_cp), C, gD, gH, gW, D, H, W, _lib.stream()))
+    return g_cp
+
+
+def bspline_axis(x, kernel, dim, stride, adjoint=False, crop_start=0, out_len=None):
+    """one axis of the FFD on an arbitrary contiguous fp32 tensor: conv1D(x, kernel, dim, stride, padding=2 stride - 1,
+    transpose=True) (reference utils/transformation.py:106-129) when adjoint is False, its transpose otherwise"""
+    lib = _lib.load()
+    _lib.require_cuda(x)
+    _f32(x)
+    stride = int(stride)
+    if len(kernel) != 4 * stride - 1:
+        raise RuntimeError('bspline_axis: a kernel of 4 * stride - 1 taps is expected')
+    dim = dim % x.dim()
+    outer = 1
+    for n in x.shape[:dim]:
+        outer *= int(n)
+    inner = 1
+    for n in x.shape[dim + 1:]:
+        inner *= int(n)
+    if adjoint:
+        n, g = int(x.shape[dim]), int(out_len)
+    else:
+        g = int(x.shape[dim])
+        n = (g - 1) * stride + 1 - int(crop_start) if out_len is None else int(out_len)
+    shape = list(x.shape)
+    shape[dim] = g if adjoint else n
+    out = torch.empty(shape, device=x.device, dtype=torch.float32)
+    _lib.check(lib.irs_bspline_axis(_lib.ptr(x), _lib.ptr(out), int(bool(adjoint)), outer, g, n, inner,
+                                    _lib.host_floats([float(v) for v in kernel]), stride, int(crop_start), _lib.stream()))
+    return out
+
+
 def diff_fwd(v, transformation=False):
     lib = _lib.load()
     _lib.require_cuda(v)

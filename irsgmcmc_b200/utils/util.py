@@ -31,6 +31,11 @@ def add_noise_Langevin(field, sigma, tau):
     return field + get_noise_Langevin(sigma, tau)
 
 
+def get_control_grid_size(dims, cps):
+    """control grid size of a B-spline FFD with control point spacing cps (reference utils/util.py:61-69)"""
+    return tuple([int(math.ceil((sz - 1) / c) + 1 + 2) for sz, c in zip(dims, cps)])
+
+
 def transform_coordinates(field):
     """voxel units -> normalised units: channel i times 2 / (shape[2 + i] - 1)  (reference :418-429)"""
     scale = torch.tensor([2.0 / float(n - 1) for n in field.shape[2:]], device=field.device, dtype=field.dtype)

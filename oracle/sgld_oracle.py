@@ -114,6 +114,68 @@ def svf_exp_aten(v, no_steps=12, exact_grid=False):
     return grid.permute(0, 4, 1, 2, 3) + d, to_voxels(d)
 
 
+# ----------------------------------------------------------------------------------------------------------------------
+# cubic B-spline FFD
+# ----------------------------------------------------------------------------------------------------------------------
+
+def control_grid_size(dims, cps):
+    """reference utils/util.py:61-69 (get_control_grid_size): ceil((n - 1) / cps) + 1 control points + 2 outside"""
+    return tuple(int(math.ceil((n - 1) / c) + 1 + 2) for n, c in zip(dims, cps))
+
+
+def bspline_taps(stride, dtype=torch.float32):
+    """
+    reference utils/transformation.py:79-103 (cubic_B_spline_1D_value, B_spline_1D_kernel): the cubic B-spline
+    B(t) = 2/3 + (t/2 - 1) t^2 for t < 1, -(t - 2)^3 / 6 for 1 <= t < 2, sampled at (i - (2 s - 1)) / s, i = 0 .. 4 s - 2;
+    evaluated in Python doubles and stored in an fp32 tensor like the reference does
+    """
+    taps = torch.ones(4 * stride - 1)
+    r = taps.shape[0] // 2
+    for i in range(taps.shape[0]):
+        t = abs((i - r) / stride)
+        taps[i] = 0.0 if t >= 2 else (2.0 / 3.0 + (0.5 * t - 1.0) * t ** 2 if t < 1 else -1.0 * ((t - 2.0) ** 3) / 6.0)
+    return taps.to(dtype)
+
+
+def bspline_axis(x, axis, s, n=None, crop_start=0):
+    """
+    one axis of the FFD = reference conv1D(x, B_spline_1D_kernel(s), dim=axis, stride=s, padding=2 s - 1, transpose=True)
+    (utils/transformation.py:106-129), restated without a convolution: element p = j + crop_start of the transposed
+    convolution is sum_i x[i] B(p / s - i), i.e. with p + 2 s - 1 = q s + r the four inputs i = q - m (m = 0..3) weighted
+    by taps[r + m s]; n elements from crop_start on (default: all (g - 1) s + 1 of them)
+    """
+    taps = bspline_taps(s, x.dtype)
+    g = x.shape[axis]
+    n = (g - 1) * s + 1 - crop_start if n is None else n
+    t = torch.arange(n) + crop_start + 2 * s - 1
+    q, r = t // s, t % s
+    shape = [1] * x.dim()
+    shape[axis] = n
+    acc = 0
+    for m in range(3, -1, -1):
+        i, j = q - m, r + m * s
+        ok = (i >= 0) & (i < g) & (j <= 4 * s - 2)
+        w = torch.where(ok, taps[j.clamp(max=4 * s - 2)], torch.zeros((), dtype=x.dtype))
+        acc = acc + x.index_select(axis, i.clamp(0, g - 1)) * w.view(shape)
+    return acc
+
+
+def ffd_dense(cp, dims, cps):
+    """
+    reference utils/transformation.py:132-152 (Cubic_B_spline_FFD_3D.forward): the transposed convolution per axis (D, H,
+    W in that order), then the crop [s, s + n): dense[x] = sum_i cp[i] B((x + s) / s - i) along each axis
+    """
+    out = cp
+    for a, (n, s) in enumerate(zip(dims, cps)):
+        out = bspline_axis(out, a + 2, s, n, crop_start=s)
+    return out
+
+
+def svffd_exp_aten(cp, dims, cps, no_steps=12):
+    """reference utils/transformation.py:155-164 (SVFFD_3D): SVF_3D of the dense B-spline velocity field"""
+    return svf_exp_aten(ffd_dense(cp, dims, cps), no_steps)
+
+
 def warp_aten(im, T):
     """reference utils/registration.py:29-30 (float images)"""
     return F.grid_sample(im, T.permute(0, 2, 3, 4, 1), mode='bilinear', padding_mode='border', align_corners=True)

@@ -164,8 +164,68 @@ def op_vectors(ref):
     print('wrote ops')
 
 
+def ffd_vectors(ref):
+    """Cubic_B_spline_FFD_3D / SVFFD_3D (utils/transformation.py:79-164), get_control_grid_size (utils/util.py:61-69)"""
+    out = {}
+    torch.manual_seed(17)
+    T = ref.transformation
+    for tag, dims, cps in (('a', (16, 16, 16), (4, 4, 4)), ('b', (13, 13, 13), (2, 3, 5))):
+        g = ref.util.get_control_grid_size(dims, cps)
+        cp = torch.randn(2, 3, *g)
+        G = torch.randn(2, 3, *dims)
+        ffd = T.Cubic_B_spline_FFD_3D(dims, cps)
+        cp32 = cp.clone().requires_grad_(True)
+        dense = ffd(cp32)
+        (dense * G).sum().backward()
+        out[f'{tag}_dims'], out[f'{tag}_cps'], out[f'{tag}_grid'] = np.array(dims), np.array(cps), np.array(g)
+        out[f'{tag}_cp'], out[f'{tag}_G'] = np32(cp), np32(G)
+        out[f'{tag}_dense'], out[f'{tag}_grad'] = np32(dense), np32(cp32.grad)
+        for i, s in enumerate(cps):
+            out[f'{tag}_kernel{i}'] = np32(T.B_spline_1D_kernel(s))
+        # one un-cropped axis of it: conv1D(transpose=True) along H
+        out[f'{tag}_conv1d_dim3'] = np32(T.conv1D(cp, ffd.kernels[1], dim=3, stride=cps[1], padding=ffd.padding[1],
+                                                  transpose=True))
+    # SVFFD_3D: smooth control-point velocities of a few voxels, fp32 and fp64 with the gradient of sum(disp * G)
+    dims, cps = (16, 16, 16), (4, 4, 4)
+    g = ref.util.get_control_grid_size(dims, cps)
+    cp = 2.0 * torch.randn(2, 3, *g)
+    G = torch.randn(2, 3, *dims)
+    m = T.SVFFD_3D(dims, cps)
+    # the gradient w.r.t. the dense velocity field is kept too: trilinear kink flips (SURVEY surprise 9) are isolated
+    # voxels there, whereas one flipped voxel reaches the 64 control points around it
+    def run(module, cp_in, G_in):
+        dense = []
+        def keep(mod, inp, res):
+            res.retain_grad()
+            dense.append(res)
+
+        hook = module.cubic_B_spline_FFD.register_forward_hook(keep)
+        Tr, disp = module(cp_in)
+        (disp * G_in).sum().backward()
+        hook.remove()
+        return Tr, disp, dense[0].grad
+
+    cp32 = cp.clone().requires_grad_(True)
+    Tr, disp, g_dense = run(m, cp32, G)
+    out['svffd_cp'], out['svffd_G'] = np32(cp), np32(G)
+    out['svffd_T'], out['svffd_disp'], out['svffd_grad'] = np32(Tr), np32(disp), np32(cp32.grad)
+    out['svffd_grad_dense'] = np32(g_dense)
+    m64 = T.SVFFD_3D(dims, cps).double()
+    cp64 = cp.double().requires_grad_(True)
+    _, disp64, g_dense64 = run(m64, cp64, G.double())
+    out['svffd_disp_f64'], out['svffd_grad_f64'] = np32(disp64), np32(cp64.grad)
+    out['svffd_grad_dense_f64'] = np32(g_dense64)
+    np.savez_compressed(os.path.join(HERE, 'ffd.npz'), **out)
+    print('wrote ffd')
+
+
 if __name__ == '__main__':
     ref = ref_import.load()
-    op_vectors(ref)
-    transition_vectors(ref, 12, 2, 'RegLoss_LogNormal', True, 1.6, 'lcc_lognormal')
-    transition_vectors(ref, 12, 2, 'RegLoss_L2', True, 1.4, 'lcc_l2')
+    which = sys.argv[1:] or ['ops', 'transitions', 'ffd']
+    if 'ops' in which:
+        op_vectors(ref)
+    if 'transitions' in which:
+        transition_vectors(ref, 12, 2, 'RegLoss_LogNormal', True, 1.6, 'lcc_lognormal')
+        transition_vectors(ref, 12, 2, 'RegLoss_L2', True, 1.4, 'lcc_l2')
+    if 'ffd' in which:
+        ffd_vectors(ref)

@@ -179,3 +179,36 @@ void emul_philox(unsigned int c0, unsigned int c1, unsigned int c2, unsigned int
 }
 
 }  // extern "C"
+
+// cubic B-spline FFD (csrc/irs_ffd_body.cuh): the three axis passes of irs_ffd_fwd / irs_ffd_bwd in the same order
+#include "../../irsgmcmc_b200/csrc/irs_ffd_body.cuh"
+
+static IrsFfdAxis emul_axis(const float* kernel, int s, int off) {
+    IrsFfdAxis ax;
+    ax.s = s;
+    ax.off = off;
+    for (int j = 0; j <= IRS_FFD_MAX_KERNEL; ++j) ax.k[j] = j < 4 * s - 1 ? kernel[j] : 0.f;
+    return ax;
+}
+
+extern "C" void emul_bspline_axis(const float* in, float* out, int adjoint, long long outer, int g, int n,
+                                  long long inner, const float* kernel, int s, int off) {
+    const IrsFfdAxis ax = emul_axis(kernel, s, off);
+    const long long total = outer * (adjoint ? g : n) * inner;
+    for (long long i = 0; i < total; ++i)
+        out[i] = adjoint ? irs_body_ffd_axis_bwd(in, i, g, n, inner, ax) : irs_body_ffd_axis_fwd(in, i, g, n, inner, ax);
+}
+
+extern "C" void emul_ffd(const float* in, float* out, int adjoint, const float* kd, const float* kh, const float* kw,
+                         int sD, int sH, int sW, int C, int gD, int gH, int gW, int D, int H, int W) {
+    std::vector<float> t1((size_t)C * 3 * D * gH * gW), t2((size_t)C * 3 * D * H * gW);
+    if (!adjoint) {
+        emul_bspline_axis(in, t1.data(), 0, (long long)C * 3, gD, D, (long long)gH * gW, kd, sD, sD);
+        emul_bspline_axis(t1.data(), t2.data(), 0, (long long)C * 3 * D, gH, H, gW, kh, sH, sH);
+        emul_bspline_axis(t2.data(), out, 0, (long long)C * 3 * D * H, gW, W, 1, kw, sW, sW);
+    } else {
+        emul_bspline_axis(in, t2.data(), 1, (long long)C * 3 * D * H, gW, W, 1, kw, sW, sW);
+        emul_bspline_axis(t2.data(), t1.data(), 1, (long long)C * 3 * D, gH, H, gW, kh, sH, sH);
+        emul_bspline_axis(t1.data(), out, 1, (long long)C * 3, gD, D, (long long)gH * gW, kd, sD, sD);
+    }
+}
