@@ -239,6 +239,13 @@ typedef struct irs_sgld_config {
     double w_reg_prior_shape, w_reg_prior_rate;
     double n_mask;               /* number of true voxels of the fixed mask */
     unsigned long long seed;
+    /* SVFFD_3D as the transformation model (utils/transformation.py:155-164): ffd_cps[0] > 0 turns it on.  The chain
+     * state v, sigma, eps, css and grad_v then live on the control grid (C,3,gD,gH,gW) = ffd_grid; Langevin proposal,
+     * Sobolev smoothing, regulariser and update act there, the dense velocity field is ffd_dense.  dof stays 3 D H W
+     * (model/loss.py:134 takes the image size). */
+    int ffd_cps[3];              /* control point spacing along D, H, W (each <= 8); all 0 = plain SVF_3D */
+    int ffd_grid[3];             /* gD, gH, gW */
+    float ffd_kernel[3][32];     /* B_spline_1D_kernel(cps) per axis: 4 cps - 1 taps */
 } irs_sgld_config;
 
 typedef struct irs_sgld_buffers {
@@ -267,11 +274,16 @@ typedef struct irs_sgld_buffers {
     float* gmm_table;            /* C * 16 floats: per chain (lw[8], prec[8]) after that chain's update */
     double* partials;            /* irs_sgld_partials_doubles() doubles */
     unsigned int* counters;      /* C + 8 zero-initialised unsigned ints */
+    /* only with cfg->ffd_cps[0] > 0 */
+    float* ffd_dense;            /* (C,3,V) dense velocity field of the control points */
+    float* ffd_grad;             /* (C,3,V) its gradient */
+    float* ffd_scratch;          /* (C,3,gD gH gW) scratch of the smoothing passes */
+    float* ffd_work;             /* irs_ffd_work_floats() floats */
 } irs_sgld_buffers;
 
 size_t irs_sgld_partials_doubles(const irs_sgld_config* cfg);
 
-/* enqueue one transition on `stream` (about 60 + 2 C kernel launches; capturable in a CUDA graph) */
+/* enqueue one transition on `stream` (about 45 + 2 C kernel launches, 7 more with the FFD; capturable in a CUDA graph) */
 int irs_sgld_step(const irs_sgld_config* cfg, const irs_sgld_buffers* buf, void* stream);
 
 /* Profiling aid: one eager transition with a CUDA event between stages; synchronises the stream and writes the

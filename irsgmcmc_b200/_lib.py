@@ -43,7 +43,8 @@ class SgldConfig(ctypes.Structure):
                 ('dirichlet_alpha', ctypes.c_double),
                 ('reg_scale_prior_loc', ctypes.c_double), ('reg_scale_prior_scale', ctypes.c_double),
                 ('w_reg_prior_shape', ctypes.c_double), ('w_reg_prior_rate', ctypes.c_double),
-                ('n_mask', ctypes.c_double), ('seed', ctypes.c_ulonglong)]
+                ('n_mask', ctypes.c_double), ('seed', ctypes.c_ulonglong),
+                ('ffd_cps', ctypes.c_int * 3), ('ffd_grid', ctypes.c_int * 3), ('ffd_kernel', (ctypes.c_float * 32) * 3)]
 
 
 class SgldBuffers(ctypes.Structure):
@@ -55,7 +56,9 @@ class SgldBuffers(ctypes.Structure):
                 ('scratch1', ctypes.c_void_p), ('scratch2', ctypes.c_void_p),
                 ('field_a', ctypes.c_void_p), ('field_b', ctypes.c_void_p), ('grad_v', ctypes.c_void_p),
                 ('maxabs', ctypes.c_void_p), ('hyper', ctypes.c_void_p), ('stats', ctypes.c_void_p),
-                ('gmm_table', ctypes.c_void_p), ('partials', ctypes.c_void_p), ('counters', ctypes.c_void_p)]
+                ('gmm_table', ctypes.c_void_p), ('partials', ctypes.c_void_p), ('counters', ctypes.c_void_p),
+                ('ffd_dense', ctypes.c_void_p), ('ffd_grad', ctypes.c_void_p), ('ffd_scratch', ctypes.c_void_p),
+                ('ffd_work', ctypes.c_void_p)]
 
 
 # name -> (restype, argtypes); every symbol include/irsgmcmc.h declares

@@ -67,6 +67,24 @@ int check_ffd(int C, int gD, int gH, int gW, int D, int H, int W) {
 
 }  // namespace
 
+int irs_launch_ffd(const float* in, float* out, bool adjoint, const float (*kernels)[32], const int* cps, float* work,
+                   int C, IrsDims g, IrsDims d, cudaStream_t st) {
+    IrsFfdAxis az, ay, ax;
+    IRS_TRY(make_axis(az, kernels[0], cps[0], cps[0]));
+    IRS_TRY(make_axis(ay, kernels[1], cps[1], cps[1]));
+    IRS_TRY(make_axis(ax, kernels[2], cps[2], cps[2]));
+    float* t1 = work;                                       // (C 3, D, gH, gW)
+    float* t2 = work + (size_t)C * 3 * d.D * g.H * g.W;     // (C 3, D, H, gW)
+    if (!adjoint) {
+        IRS_TRY(launch_axis(in, t1, false, (long long)C * 3, g.D, d.D, (long long)g.H * g.W, az, st));
+        IRS_TRY(launch_axis(t1, t2, false, (long long)C * 3 * d.D, g.H, d.H, g.W, ay, st));
+        return launch_axis(t2, out, false, (long long)C * 3 * d.D * d.H, g.W, d.W, 1, ax, st);
+    }
+    IRS_TRY(launch_axis(in, t2, true, (long long)C * 3 * d.D * d.H, g.W, d.W, 1, ax, st));
+    IRS_TRY(launch_axis(t2, t1, true, (long long)C * 3 * d.D, g.H, d.H, g.W, ay, st));
+    return launch_axis(t1, out, true, (long long)C * 3, g.D, d.D, (long long)g.H * g.W, az, st);
+}
+
 extern "C" size_t irs_ffd_work_floats(int C, int gD, int gH, int gW, int D, int H, int W) {
     if (C < 1 || gD < 1 || gH < 1 || gW < 1 || D < 1 || H < 1 || W < 1) return 0;
     return (size_t)C * 3 * ((size_t)D * gH * gW + (size_t)D * H * gW);
@@ -80,36 +98,31 @@ extern "C" int irs_bspline_axis(const float* in, float* out, int adjoint, long l
     return launch_axis(in, out, adjoint != 0, outer, g, n, inner, ax, (cudaStream_t)stream);
 }
 
+static int ffd_entry(const float* in, float* out, bool adjoint, const float* kd, const float* kh, const float* kw, int sD,
+                     int sH, int sW, float* work, int C, int gD, int gH, int gW, int D, int H, int W, void* stream) {
+    IRS_TRY(check_ffd(C, gD, gH, gW, D, H, W));
+    if (!in || !out || !work || !kd || !kh || !kw) return IRS_ERR_BAD_ARG;
+    const int cps[3] = {sD, sH, sW};
+    const float* src[3] = {kd, kh, kw};
+    float kernels[3][32];
+    for (int a = 0; a < 3; ++a) {
+        if (cps[a] < 1 || cps[a] > IRS_FFD_MAX_STRIDE) return IRS_ERR_BAD_ARG;
+        for (int j = 0; j < 32; ++j) kernels[a][j] = j < 4 * cps[a] - 1 ? src[a][j] : 0.f;
+    }
+    return irs_launch_ffd(in, out, adjoint, kernels, cps, work, C, IrsDims{gD, gH, gW}, IrsDims{D, H, W},
+                          (cudaStream_t)stream);
+}
+
 extern "C" int irs_ffd_fwd(const float* cp, const float* kernel_d_host, const float* kernel_h_host,
                            const float* kernel_w_host, int sD, int sH, int sW, float* work, float* dense, int C, int gD,
                            int gH, int gW, int D, int H, int W, void* stream) {
-    IRS_TRY(check_ffd(C, gD, gH, gW, D, H, W));
-    if (!cp || !work || !dense) return IRS_ERR_BAD_ARG;
-    IrsFfdAxis az, ay, ax;
-    IRS_TRY(make_axis(az, kernel_d_host, sD, sD));
-    IRS_TRY(make_axis(ay, kernel_h_host, sH, sH));
-    IRS_TRY(make_axis(ax, kernel_w_host, sW, sW));
-    cudaStream_t st = (cudaStream_t)stream;
-    float* t1 = work;                                    // (C 3, D, gH, gW)
-    float* t2 = work + (size_t)C * 3 * D * gH * gW;      // (C 3, D, H, gW)
-    IRS_TRY(launch_axis(cp, t1, false, (long long)C * 3, gD, D, (long long)gH * gW, az, st));
-    IRS_TRY(launch_axis(t1, t2, false, (long long)C * 3 * D, gH, H, gW, ay, st));
-    return launch_axis(t2, dense, false, (long long)C * 3 * D * H, gW, W, 1, ax, st);
+    return ffd_entry(cp, dense, false, kernel_d_host, kernel_h_host, kernel_w_host, sD, sH, sW, work, C, gD, gH, gW, D, H,
+                     W, stream);
 }
 
 extern "C" int irs_ffd_bwd(const float* g_dense, const float* kernel_d_host, const float* kernel_h_host,
                            const float* kernel_w_host, int sD, int sH, int sW, float* work, float* g_cp, int C, int gD,
                            int gH, int gW, int D, int H, int W, void* stream) {
-    IRS_TRY(check_ffd(C, gD, gH, gW, D, H, W));
-    if (!g_dense || !work || !g_cp) return IRS_ERR_BAD_ARG;
-    IrsFfdAxis az, ay, ax;
-    IRS_TRY(make_axis(az, kernel_d_host, sD, sD));
-    IRS_TRY(make_axis(ay, kernel_h_host, sH, sH));
-    IRS_TRY(make_axis(ax, kernel_w_host, sW, sW));
-    cudaStream_t st = (cudaStream_t)stream;
-    float* t1 = work;
-    float* t2 = work + (size_t)C * 3 * D * gH * gW;
-    IRS_TRY(launch_axis(g_dense, t2, true, (long long)C * 3 * D * H, gW, W, 1, ax, st));
-    IRS_TRY(launch_axis(t2, t1, true, (long long)C * 3 * D, gH, H, gW, ay, st));
-    return launch_axis(t1, g_cp, true, (long long)C * 3, gD, D, (long long)gH * gW, az, st);
+    return ffd_entry(g_dense, g_cp, true, kernel_d_host, kernel_h_host, kernel_w_host, sD, sH, sW, work, C, gD, gH, gW, D,
+                     H, W, stream);
 }

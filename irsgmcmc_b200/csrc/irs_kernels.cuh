@@ -97,6 +97,11 @@ int irs_launch_sgd_update(float* v, const float* sigma, long long sigma_cs, cons
                           const double* coef, long long coef_stride, float tau, float* grad_v, int C, IrsDims d,
                           cudaStream_t st);
 
+// --- irs_ffd.cu -------------------------------------------------------------------------------------------------------
+// kernels: cfg-style tables, 4 s - 1 taps per axis (D, H, W order); work: irs_ffd_work_floats() floats
+int irs_launch_ffd(const float* in, float* out, bool adjoint, const float (*kernels)[32], const int* cps, float* work,
+                   int C, IrsDims grid, IrsDims d, cudaStream_t st);
+
 // --- irs_data.cu ------------------------------------------------------------------------------------------------------
 int irs_launch_lcc_fwd(const float* im, const float* zF, int s, float* a, float* rs, float* z, int C, IrsDims d,
                        cudaStream_t st);

@@ -86,7 +86,22 @@ int check_config(const irs_sgld_config* c) {
     if (c->n_taps < 0 || c->n_taps > IRS_MAX_TAPS || (c->n_taps > 0 && c->n_taps % 2 == 0)) return IRS_ERR_BAD_ARG;
     if (c->svf_steps < 1 || c->svf_steps > IRS_MAX_SVF_STEPS) return IRS_ERR_BAD_ARG;
     if (!(c->n_mask >= 2.0) || !(c->tau >= 0.0) || c->gather_radius_max < 0) return IRS_ERR_BAD_ARG;
+    if (c->ffd_cps[0] != 0 || c->ffd_cps[1] != 0 || c->ffd_cps[2] != 0) {
+        const int n[3] = {c->D, c->H, c->W};
+        for (int a = 0; a < 3; ++a) {
+            if (c->ffd_cps[a] < 1 || c->ffd_cps[a] > 8 || c->ffd_grid[a] < 2) return IRS_ERR_BAD_ARG;
+            // the crop [cps, cps + n) must lie inside the (g - 1) cps + 1 elements of the transposed convolution
+            if ((long long)c->ffd_cps[a] + n[a] > (long long)(c->ffd_grid[a] - 1) * c->ffd_cps[a] + 1) return IRS_ERR_BAD_ARG;
+        }
+        IRS_CHECK_DIMS(c->C, c->ffd_grid[0], c->ffd_grid[1], c->ffd_grid[2]);
+    }
     return IRS_OK;
+}
+
+inline bool has_ffd(const irs_sgld_config* c) { return c->ffd_cps[0] > 0; }
+// the grid the chain state lives on: the control grid with the FFD, the image grid otherwise
+inline IrsDims state_dims(const irs_sgld_config* c) {
+    return has_ffd(c) ? IrsDims{c->ffd_grid[0], c->ffd_grid[1], c->ffd_grid[2]} : IrsDims{c->D, c->H, c->W};
 }
 
 }  // namespace
@@ -97,6 +112,8 @@ extern "C" size_t irs_sgld_partials_doubles(const irs_sgld_config* cfg) {
     size_t per_chain = (size_t)irs_data_blocks(d) * IRS_SUM_COUNT;
     const size_t fwd = irs_svf_fwd_max_blocks(d);   // the first squaring step reduces the regulariser energy
     if (fwd > per_chain) per_chain = fwd;
+    const size_t energy = (size_t)irs_reg_energy_blocks(state_dims(cfg));   // stand-alone energy kernel
+    if (energy > per_chain) per_chain = energy;
     return (size_t)cfg->C * per_chain;
 }
 
@@ -104,7 +121,8 @@ extern "C" int irs_sgld_launches_per_step(const irs_sgld_config* c) {
     if (check_config(c) != IRS_OK) return -1;
     int n = 1;                                   // langevin
     n += c->n_taps > 0 ? 3 : 0;                  // Sobolev z, y, x
-    n += (c->W % 4 == 0) ? 0 : 1;                // regulariser energy (an epilogue of the first squaring step otherwise)
+    n += (c->W % 4 == 0 && !has_ffd(c)) ? 0 : 1; // regulariser energy (an epilogue of the first squaring step otherwise)
+    n += has_ffd(c) ? 6 : 0;                     // B-spline FFD: three axis passes forward, three for the adjoint
     n += c->svf_steps;                           // scaling and squaring
     n += c->svf_steps > 4 ? 4 : c->svf_steps - 1; // cell maps behind the last four steps (exit at once below one voxel)
     n += 1;                                      // warp
@@ -138,10 +156,15 @@ static int sgld_step_impl(const irs_sgld_config* cfg, const irs_sgld_buffers* b,
         return IRS_ERR_BAD_ARG;
     if (cfg->data_term == IRS_DATA_LCC && (!b->lcc_a || !b->lcc_rs)) return IRS_ERR_BAD_ARG;
     if (!b->scratch2) return IRS_ERR_BAD_ARG;
+    const bool ffd = has_ffd(cfg);
+    if (ffd && (!b->ffd_dense || !b->ffd_grad || !b->ffd_scratch || !b->ffd_work)) return IRS_ERR_BAD_ARG;
 
     cudaStream_t st = (cudaStream_t)stream;
     const int C = cfg->C;
     const IrsDims d{cfg->D, cfg->H, cfg->W};
+    const IrsDims ds = state_dims(cfg);          // v, sigma, eps, css, grad_v live on this grid
+    float* smooth_work = ffd ? b->ffd_scratch : b->field_a;
+    const float* velocity = ffd ? b->ffd_dense : b->css;   // what scaling and squaring integrates
     const long long V = d.V();
     const size_t F = (size_t)C * 3 * V;
     const IrsHyperCfg hc = hyper_cfg(cfg);
@@ -155,23 +178,27 @@ static int sgld_step_impl(const irs_sgld_config* cfg, const irs_sgld_buffers* b,
         IrsTaps taps;
         taps.n = cfg->n_taps;
         for (int t = 0; t < cfg->n_taps; ++t) taps.w[t] = cfg->taps[t];
-        IRS_TRY(irs_launch_langevin(b->v, b->sigma, b->sigma_chain_stride, coef, rng_l, b->field_a, C, d, st));
-        IRS_TRY(irs_launch_smooth3(b->field_a, b->field_a, b->css, taps, C, d, st));
+        IRS_TRY(irs_launch_langevin(b->v, b->sigma, b->sigma_chain_stride, coef, rng_l, smooth_work, C, ds, st));
+        IRS_TRY(irs_launch_smooth3(smooth_work, smooth_work, b->css, taps, C, ds, st));
     } else {
-        IRS_TRY(irs_launch_langevin(b->v, b->sigma, b->sigma_chain_stride, coef, rng_l, b->css, C, d, st));
+        IRS_TRY(irs_launch_langevin(b->v, b->sigma, b->sigma_chain_stride, coef, rng_l, b->css, C, ds, st));
     }
+    // (1b) control points -> dense velocity field                                  utils/transformation.py:155-164
+    if (ffd) IRS_TRY(irs_launch_ffd(b->css, b->ffd_dense, false, cfg->ffd_kernel, cfg->ffd_cps, b->ffd_work, C, ds, d, st));
 
     mark(tm, st);
     // (2) + (3) scaling and squaring; its first step also reduces the regulariser energy y_c of css from the planes it
     // holds in shared memory (trainer.py:294, 311).  When that kernel cannot run (row pitch not addressable by the TMA
     // unit) the stand-alone energy kernel follows.
     int energy_done = 0;
-    IRS_TRY(irs_launch_svf_fwd(b->css, b->hist, b->maxabs, cfg->svf_steps, C, d, st, b->stats + IRS_STAT_ENERGY, IRS_STAT_SIZE,
-                               b->partials, b->counters, &energy_done));
+    // With the FFD the regulariser acts on the control-point field css, not on the field being integrated.
+    IRS_TRY(irs_launch_svf_fwd(velocity, b->hist, b->maxabs, cfg->svf_steps, C, d, st,
+                               ffd ? nullptr : b->stats + IRS_STAT_ENERGY, IRS_STAT_SIZE, b->partials, b->counters,
+                               &energy_done));
     const float* disp = b->hist + (size_t)(cfg->svf_steps - 1) * F;
     mark(tm, st);
     if (!energy_done)
-        IRS_TRY(irs_launch_reg_energy(b->css, b->stats + IRS_STAT_ENERGY, IRS_STAT_SIZE, b->partials, b->counters, C, d, st));
+        IRS_TRY(irs_launch_reg_energy(b->css, b->stats + IRS_STAT_ENERGY, IRS_STAT_SIZE, b->partials, b->counters, C, ds, st));
 
     mark(tm, st);
     // (4) warp the moving image at T (+ jitter)                                   trainer.py:296-300
@@ -222,13 +249,15 @@ static int sgld_step_impl(const irs_sgld_config* cfg, const irs_sgld_buffers* b,
 
     mark(tm, st);
     // (10) SVF adjoint -> dL/dcss (data part)                                      trainer.py:349
-    IRS_TRY(irs_launch_svf_bwd(b->css, b->hist, b->maxabs, b->field_a, b->field_b, b->grad_v, cfg->svf_steps,
-                               cfg->gather_radius_max, C, d, st));
+    IRS_TRY(irs_launch_svf_bwd(velocity, b->hist, b->maxabs, b->field_a, b->field_b, ffd ? b->ffd_grad : b->grad_v,
+                               cfg->svf_steps, cfg->gather_radius_max, C, d, st));
+    // (10b) dense gradient -> control points (gathers over each control point's support)
+    if (ffd) IRS_TRY(irs_launch_ffd(b->ffd_grad, b->grad_v, true, cfg->ffd_kernel, cfg->ffd_cps, b->ffd_work, C, ds, d, st));
 
     mark(tm, st);
     // (11) + regulariser gradient, sigma^2 preconditioning, SGD step               utils/functions.py:82-84, trainer.py:351
     IRS_TRY(irs_launch_sgd_update(b->v, b->sigma, b->sigma_chain_stride, b->css, b->grad_v, b->stats + IRS_STAT_REG_COEF,
-                                  IRS_STAT_SIZE, (float)cfg->tau, b->grad_v, C, d, st));
+                                  IRS_STAT_SIZE, (float)cfg->tau, b->grad_v, C, ds, st));
     mark(tm, st);
     return IRS_OK;
 }
@@ -274,17 +303,23 @@ extern "C" int irs_sgld_gmm_init(const irs_sgld_config* cfg, const irs_sgld_buff
     const long long V = d.V();
     const IrsHyperCfg hc = hyper_cfg(cfg);
     IrsRng none{nullptr, 0ull, nullptr, 0ull, 0};
+    const bool ffd = has_ffd(cfg);
+    if (ffd && (!b->ffd_dense || !b->ffd_scratch || !b->ffd_work)) return IRS_ERR_BAD_ARG;
+    const IrsDims ds = state_dims(cfg);   // v_sample is (1,3,gD,gH,gW) with the FFD
+    float* smooth_work = ffd ? b->ffd_scratch : b->field_a;
     if (cfg->n_taps > 0) {
         IrsTaps taps;
         taps.n = cfg->n_taps;
         for (int t = 0; t < cfg->n_taps; ++t) taps.w[t] = cfg->taps[t];
-        IRS_TRY(irs_launch_langevin(v_sample, nullptr, 0, 0.f, none, b->field_a, 1, d, st));
-        IRS_TRY(irs_launch_smooth3(b->field_a, b->field_a, b->css, taps, 1, d, st));
+        IRS_TRY(irs_launch_langevin(v_sample, nullptr, 0, 0.f, none, smooth_work, 1, ds, st));
+        IRS_TRY(irs_launch_smooth3(smooth_work, smooth_work, b->css, taps, 1, ds, st));
     } else {
-        IRS_TRY(irs_launch_langevin(v_sample, nullptr, 0, 0.f, none, b->css, 1, d, st));
+        IRS_TRY(irs_launch_langevin(v_sample, nullptr, 0, 0.f, none, b->css, 1, ds, st));
     }
+    if (ffd) IRS_TRY(irs_launch_ffd(b->css, b->ffd_dense, false, cfg->ffd_kernel, cfg->ffd_cps, b->ffd_work, 1, ds, d, st));
     // hist of a single chain is laid out with stride 3V per step when C = 1
-    IRS_TRY(irs_launch_svf_fwd(b->css, b->hist, b->maxabs, cfg->svf_steps, 1, d, st, nullptr, 0, nullptr, nullptr, nullptr));
+    IRS_TRY(irs_launch_svf_fwd(ffd ? b->ffd_dense : b->css, b->hist, b->maxabs, cfg->svf_steps, 1, d, st, nullptr, 0, nullptr,
+                               nullptr, nullptr));
     const float* disp = b->hist + (size_t)(cfg->svf_steps - 1) * 3 * V;
     IRS_TRY(irs_launch_warp_vox_fwd(b->moving, disp, none, 0.f, 0, b->im_warped, 1, d, st));
     if (cfg->data_term == IRS_DATA_LCC) {

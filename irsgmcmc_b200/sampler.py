@@ -28,9 +28,15 @@ class SGLDConfig:
                  uniform_noise=True, uniform_noise_magnitude=0.1, virtual_decimation=True, lr_log_std=0.2,
                  lr_logits=0.2, lr_reg=0.01, lr_decay=1e-3, betas=(0.9, 0.999), adam_eps=1e-8,
                  gmm_scale_prior=(0.0, 2.3), dirichlet_alpha=0.5, reg_scale_prior=(2.8, 5.0), gather_radius_max=2,
-                 seed=123):
+                 seed=123, transformation='SVF_3D', cps=None):
         if data_loss not in ('lcc', 'ssd'):
             raise ValueError(f'unknown data loss: {data_loss}')
+        if transformation not in ('SVF_3D', 'SVFFD_3D'):
+            raise ValueError(f'unknown transformation module: {transformation}')
+        if transformation == 'SVFFD_3D':   # configs/experiment5/config_SVFFD_*.json: "cps": [s, s, s]
+            if cps is None or len(cps) != 3 or not all(1 <= int(c) <= 8 for c in cps):
+                raise ValueError('SVFFD_3D needs cps = three control point spacings between 1 and 8')
+            cps = tuple(int(c) for c in cps)
         if reg_loss not in ('RegLoss_LogNormal', 'RegLoss_L2'):
             raise ValueError(f'unknown regularisation loss: {reg_loss}')
         self.__dict__.update(locals())
@@ -86,10 +92,22 @@ class SGLDSampler:
         else:
             self.fixed_term = im_f
 
+        # with SVFFD_3D the chain state lives on the control grid (data_loader/datasets.py:23-27), everything behind the
+        # B-spline FFD on the image grid
+        self.ffd = cfg.transformation == 'SVFFD_3D'
+        if self.ffd:
+            from .utils.transformation import B_spline_1D_kernel
+            from .utils.util import get_control_grid_size
+            self.state_dims = get_control_grid_size(self.dims, cfg.cps)
+            self._ffd_taps = [[float(k) for k in B_spline_1D_kernel(c)] for c in cfg.cps]
+        else:
+            self.state_dims = self.dims
+        gD, gH, gW = self.state_dims
+
         # state + workspace, allocated once (180 GB HBM: the SVF history is kept rather than recomputed)
-        self.v = torch.zeros(C, 3, D, H, W, **f32)
+        self.v = torch.zeros(C, 3, gD, gH, gW, **f32)
         self.sigma = None
-        self.css = torch.empty(C, 3, D, H, W, **f32)
+        self.css = torch.empty(C, 3, gD, gH, gW, **f32)
         self.hist = torch.empty(cfg.svf_steps, C, 3, D, H, W, **f32)
         self.im_warped = torch.empty(C, 1, D, H, W, **f32)
         self.z = torch.empty(C, 1, D, H, W, **f32)
@@ -99,7 +117,12 @@ class SGLDSampler:
         self._scratch2 = torch.empty(C, 1, D, H, W, **f32)
         self._field_a = torch.empty(C, 3, D, H, W, **f32)
         self._field_b = torch.empty(C, 3, D, H, W, **f32)
-        self.grad_v = torch.zeros(C, 3, D, H, W, **f32)
+        self.grad_v = torch.zeros(C, 3, gD, gH, gW, **f32)
+        if self.ffd:
+            self._ffd_dense = torch.empty(C, 3, D, H, W, **f32)
+            self._ffd_grad = torch.empty(C, 3, D, H, W, **f32)
+            self._ffd_scratch = torch.empty(C, 3, gD, gH, gW, **f32)
+            self._ffd_work = torch.empty(int(self.lib.irs_ffd_work_floats(C, gD, gH, gW, D, H, W)), **f32)
         self._maxabs = torch.zeros(int(self.lib.irs_svf_maxabs_floats(C, D, H, W, cfg.svf_steps)), **f32)
         self.hyper = torch.zeros(_lib.HYPER_SIZE, device=dev, dtype=torch.float64)
         self.stats = torch.zeros(C, _lib.STAT_SIZE, device=dev, dtype=torch.float64)
@@ -164,13 +187,19 @@ class SGLDSampler:
         c.w_reg_prior_shape, c.w_reg_prior_rate = shape, 1.0 / shape
         c.n_mask = self.n_mask
         c.seed = cfg.seed
+        if self.ffd:
+            for a in range(3):
+                c.ffd_cps[a], c.ffd_grid[a] = cfg.cps[a], self.state_dims[a]
+                for j, k in enumerate(self._ffd_taps[a]):
+                    c.ffd_kernel[a][j] = k
         return c
 
     def _buffers(self):
         b = _lib.SgldBuffers()
         p = lambda t: None if t is None else t.data_ptr()
         b.v, b.sigma = p(self.v), p(self.sigma)
-        b.sigma_chain_stride = 0 if self.sigma is None or self.sigma.shape[0] == 1 else 3 * self.V
+        gD, gH, gW = self.state_dims
+        b.sigma_chain_stride = 0 if self.sigma is None or self.sigma.shape[0] == 1 else 3 * gD * gH * gW
         b.fixed, b.moving, b.mask = p(self.fixed_term), p(self.moving_im), p(self.mask)
         b.eps, b.jitter_unit = p(self.eps_inject), p(self.jitter_inject)
         b.css, b.hist, b.im_warped, b.z = p(self.css), p(self.hist), p(self.im_warped), p(self.z)
@@ -178,6 +207,9 @@ class SGLDSampler:
         b.field_a, b.field_b, b.grad_v = p(self._field_a), p(self._field_b), p(self.grad_v)
         b.maxabs, b.hyper, b.stats = p(self._maxabs), p(self.hyper), p(self.stats)
         b.gmm_table, b.partials, b.counters = p(self._gmm_table), p(self._partials), p(self._counters)
+        if self.ffd:
+            b.ffd_dense, b.ffd_grad = p(self._ffd_dense), p(self._ffd_grad)
+            b.ffd_scratch, b.ffd_work = p(self._ffd_scratch), p(self._ffd_work)
         return b
 
     def _invalidate(self):
@@ -348,7 +380,7 @@ class SGLDSampler:
         return self.hist[-1]
 
     def transformation(self):
-        T = torch.empty_like(self.css)
+        T = torch.empty_like(self.displacement)
         D, H, W = self.dims
         _lib.check(self.lib.irs_svf_outputs(_lib.ptr(self.displacement), _lib.ptr(self._lin[0]), _lib.ptr(self._lin[1]),
                                             _lib.ptr(self._lin[2]), _lib.ptr(T), None, self.C, D, H, W, _lib.stream()))

@@ -49,6 +49,13 @@ def sampler_config_from_json(config):
         kw['reg_scale_prior'] = (a['loc'], a['scale'])
     if reg['type'] not in ('RegLoss_LogNormal', 'RegLoss_L2'):
         raise NotImplementedError(reg['type'])
+    # "transformation_module": {"type": "SVF_3D" | "SVFFD_3D", "args": {"cps": [..]}} (configs/experiment5, parse_config.py:100-108)
+    tm = config.get('transformation_module', {'type': 'SVF_3D', 'args': {}})
+    if tm['type'] not in ('SVF_3D', 'SVFFD_3D'):
+        raise NotImplementedError(tm['type'])
+    kw['transformation'] = tm['type']
+    if tm['type'] == 'SVFFD_3D':
+        kw['cps'] = tm.get('args', {}).get('cps')
     return SGLDConfig(**kw)
 
 
@@ -136,7 +143,7 @@ class Trainer:
         """the objects the reference's ConfigParser would create for VI from the JSON (parse_config.py:110-148,215-249)"""
         from .. import model as M
         from ..optimizers import Adam
-        from ..utils import RegistrationModule, SVF_3D, Sobolev_kernel_1D
+        from ..utils import RegistrationModule, SVF_3D, SVFFD_3D, Sobolev_kernel_1D
         cfg, sc, dev = self.config, self.sampler.cfg, self.device
         n = self.dims
         dof = 3.0 * float(np.prod(n))
@@ -146,7 +153,9 @@ class Trainer:
         mods = {'data_loss': data_loss, 'reg_loss': reg_loss, 'entropy_loss': M.EntropyMultivariateNormal(),
                 'scale_prior': M.LogScaleNormalPrior(*sc.gmm_scale_prior).to(dev),
                 'proportion_prior': M.DirichletPrior(sc.no_components, sc.dirichlet_alpha).to(dev),
-                'transformation_module': SVF_3D(n, sc.svf_steps).to(dev), 'registration_module': RegistrationModule()}
+                'transformation_module': (SVFFD_3D(n, sc.cps) if sc.transformation == 'SVFFD_3D'
+                                          else SVF_3D(n, sc.svf_steps)).to(dev),
+                'registration_module': RegistrationModule()}
         if sc.reg_learnable:
             if sc.reg_loss == 'RegLoss_LogNormal':
                 mods['loc_prior'] = M.LogEnergyExpGammaPrior(sc.w_reg, dof).to(dev)

@@ -84,7 +84,7 @@ def load():
 
 def make_trainer(ref, dims, no_chains, reg_type='RegLoss_LogNormal', w_reg=1.6, learnable=True, K=4, s=2,
                  sobolev_s=3, sobolev_lambda=0.5, tau=0.4, uniform_noise=None, virtual_decimation=True,
-                 lr_gmm=0.2, lr_reg=0.01, lr_decay=1e-3, dtype=None):
+                 lr_gmm=0.2, lr_reg=0.01, lr_decay=1e-3, dtype=None, cps=None):
     """
     builds the reference Trainer without running __init__ (hard-coded cuda:0, TensorBoard, pandas MetricTracker:
     base/base_trainer.py:16,52-54) and wires it like parse_config.py:110-148,215-249 + trainer/trainer.py:21-42,568-583
@@ -119,7 +119,8 @@ def make_trainer(ref, dims, no_chains, reg_type='RegLoss_LogNormal', w_reg=1.6, 
     losses['reg']['loss'] = reg
     t.losses = losses
     t.diff_op = reg.diff_op
-    t.transformation_module = ref.transformation.SVF_3D(dims)
+    # parse_config.py:100-108: the transformation module by name; SVFFD_3D with "cps" in configs/experiment5
+    t.transformation_module = ref.transformation.SVF_3D(dims) if cps is None else ref.transformation.SVFFD_3D(dims, cps)
     t.registration_module = ref.registration.RegistrationModule()
 
     Adam = ref.optim.Adam

@@ -447,7 +447,8 @@ class Config:
 
     def __init__(self, data='lcc', K=4, s=2, reg='lognormal', w_reg=1.6, reg_learnable=True, sobolev_s=3,
                  sobolev_lambda=0.5, svf_steps=12, tau=0.4, jitter_alpha=0.1, virtual_decimation=True, lr_gmm=0.2,
-                 lr_reg=0.01, lr_decay=1e-3, exact_grid=False):
+                 lr_reg=0.01, lr_decay=1e-3, exact_grid=False, cps=None):
+        # cps: control point spacing of SVFFD_3D as the transformation module (configs/experiment5); None = SVF_3D
         self.__dict__.update(locals())
         del self.__dict__['self']
 
@@ -456,7 +457,8 @@ class State:
     """everything a chain group carries between iterations (SURVEY §5 'checkpoint/resume' row)"""
 
     def __init__(self, cfg, v, sigma, dims, dtype=torch.float32):
-        self.cfg, self.v, self.sigma = cfg, v.clone(), sigma
+        # dims: the IMAGE size (dof of the regulariser, model/loss.py:134); with cfg.cps the state v lives on the control grid
+        self.cfg, self.v, self.sigma, self.dims = cfg, v.clone(), sigma, tuple(dims)
         K = cfg.K if cfg.data == 'lcc' else 1
         self.log_std, self.logits = torch.zeros(K, dtype=dtype), torch.zeros(K, dtype=dtype)
         self.adam_gmm = AdamState([self.log_std, self.logits], [cfg.lr_gmm, cfg.lr_gmm], cfg.lr_decay)
@@ -525,14 +527,15 @@ def sgld_transition(st, fixed, moving, eps=None, jitter_unit=None):
     if eps is None:
         eps = torch.randn_like(st.v)
     if cfg.jitter_alpha is not None and jitter_unit is None:
-        jitter_unit = torch.rand_like(st.v)
+        jitter_unit = torch.rand(C, 3, *st.dims, dtype=dtype)
 
     # trainer.py:292-293.  SGLD.backward = sigma^2 * g and SobolevGrad.backward = identity (utils/functions.py:82-84,
     # 107-109), i.e. dL/dv := sigma^2 * dL/d(css): differentiate w.r.t. css and scale afterwards.
     tau_noise = math.sqrt(2.0 * cfg.tau) * st.sigma * eps if cfg.tau > 0 else 0.0
     css = sobolev_smooth(st.v + tau_noise, st.taps).detach().requires_grad_(True)
 
-    T, disp = svf_exp_aten(css, cfg.svf_steps, cfg.exact_grid)                      # trainer.py:294
+    velocity = css if cfg.cps is None else ffd_dense(css, st.dims, cfg.cps)         # utils/transformation.py:163-164
+    T, disp = svf_exp_aten(velocity, cfg.svf_steps, cfg.exact_grid)                 # trainer.py:294
     T_s = T + uniform_jitter_normalised(jitter_unit, cfg.jitter_alpha, T.shape) if cfg.jitter_alpha is not None else T
     im_w = warp_aten(moving['im'].expand(C, -1, -1, -1, -1).to(dtype), T_s)          # trainer.py:296-300
 
@@ -575,7 +578,7 @@ def gmm_init(st, fixed, moving, v_sample, warm_up=25):
     """reference trainer/trainer.py:529-547"""
     cfg = st.cfg
     css = sobolev_smooth(v_sample, st.taps)
-    T, _ = svf_exp_aten(css, cfg.svf_steps, cfg.exact_grid)
+    T, _ = svf_exp_aten(css if cfg.cps is None else ffd_dense(css, st.dims, cfg.cps), cfg.svf_steps, cfg.exact_grid)
     im_w = warp_aten(moving['im'].to(css.dtype), T)
     z = lcc_map(fixed['im'].to(css.dtype), im_w, cfg.s) if cfg.data == 'lcc' else ssd_map(fixed['im'], im_w)
     mask = fixed['mask']

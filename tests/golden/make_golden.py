@@ -31,14 +31,25 @@ def np32(t):
     return t.detach().cpu().numpy().copy()   # copy: parameters are updated in place by the optimisers later on
 
 
-def transition_vectors(ref, n, C, reg_type, learnable, w_reg, tag, iters=2):
+def transition_vectors(ref, n, C, reg_type, learnable, w_reg, tag, iters=2, cps=None):
+    """cps: SVFFD_3D as the transformation module (configs/experiment5): state, sigma and eps on the control grid"""
     torch.manual_seed(123)
     fixed, moving, vp = make_pair(n)
     out = {'n': n, 'C': C}
+    sdims = (n, n, n) if cps is None else ref.util.get_control_grid_size((n, n, n), cps)
+    if cps is not None:
+        out['cps'], out['grid'] = np.array(cps), np.array(sdims)
     for dtype, sfx in ((torch.float32, ''), (torch.float64, '_f64')):
         torch.manual_seed(7)
         t = ref_import.make_trainer(ref, (n, n, n), C, reg_type=reg_type, w_reg=w_reg, learnable=learnable,
-                                    uniform_noise=0.1, dtype=dtype if dtype == torch.float64 else None)
+                                    uniform_noise=0.1, dtype=dtype if dtype == torch.float64 else None, cps=cps)
+        dense = []
+        if cps is not None:   # keep the gradient w.r.t. the dense velocity field (see ffd_vectors)
+            def keep(mod, inp, res):
+                res.retain_grad()
+                dense.append(res)
+
+            t.transformation_module.cubic_B_spline_FFD.register_forward_hook(keep)
         if dtype == torch.float64:  # RegistrationModule rejects fp64 (utils/registration.py:13-15,32)
             t.registration_module = lambda im, T: F.grid_sample(im, T.permute(0, 2, 3, 4, 1), mode='bilinear',
                                                                 padding_mode='border', align_corners=True)
@@ -46,14 +57,18 @@ def transition_vectors(ref, n, C, reg_type, learnable, w_reg, tag, iters=2):
         gmm.init_parameters(torch.tensor(0.7))
         cast = lambda d: {k: (v.to(dtype) if v.dtype == torch.float32 else v).expand(C, *v.shape[1:]) for k, v in d.items()}
         fx, mv = cast(fixed), cast(moving)
-        v0 = (0.8 * torch.randn(C, 3, n, n, n)).to(dtype)
-        sigma = torch.exp(0.5 * vp['log_var']).to(dtype).expand(C, -1, -1, -1, -1)
+        v0 = ((0.8 if cps is None else 1.5) * torch.randn(C, 3, *sdims)).to(dtype)
+        sigma = torch.exp(0.5 * vp['log_var']).to(dtype)
+        if cps is not None:
+            sigma = (0.5 + torch.rand(1, 3, *sdims)).to(dtype)
+        sigma = sigma.expand(C, -1, -1, -1, -1)
         ref_import.attach_state(t, v0, sigma, 0.4)
         if sfx == '':
             out['v0'], out['sigma'] = np32(v0), np32(sigma[:1])
         for it in range(iters):
-            eps = torch.randn(C, 3, n, n, n)
+            eps = torch.randn(C, 3, *sdims)
             ju = torch.rand(C, 3, n, n, n)
+            dense.clear()
             ref.util.get_noise_Langevin = lambda s, tau, e=eps.to(dtype): math.sqrt(2.0 * tau) * s * e
             ref.util.get_noise_uniform = lambda shape, device, alpha, j=ju.to(dtype): -2.0 * alpha * j + alpha
             v_before = t.v_curr_state.detach().clone()
@@ -74,6 +89,8 @@ def transition_vectors(ref, n, C, reg_type, learnable, w_reg, tag, iters=2):
             out[p + 'reg_energy'] = np.array([float(x) for x in aux['reg_energy']])
             out[p + 'grad_v'] = np32((v_before - t.v_curr_state.detach()) / 0.4)
             out[p + 'v_after'] = np32(t.v_curr_state)
+            if cps is not None:
+                out[p + 'velocity'], out[p + 'grad_dense'] = np32(dense[0]), np32(dense[0].grad)
             out[p + 'log_std'], out[p + 'logits'] = np32(gmm.log_std), np32(gmm.logits)
             out[p + 'reg_params'] = np.array([float(reg.loc), float(reg.log_scale)] if reg_type == 'RegLoss_LogNormal'
                                              else [float(reg.log_w_reg)])
@@ -229,3 +246,4 @@ if __name__ == '__main__':
         transition_vectors(ref, 12, 2, 'RegLoss_L2', True, 1.4, 'lcc_l2')
     if 'ffd' in which:
         ffd_vectors(ref)
+        transition_vectors(ref, 16, 2, 'RegLoss_LogNormal', True, 1.6, 'svffd_lognormal', cps=(4, 4, 4))

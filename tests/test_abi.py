@@ -57,14 +57,19 @@ def test_config_struct_layout_matches_c(built):
     """sizeof(irs_sgld_config / irs_sgld_buffers) as the C compiler sees them"""
     import subprocess
     import tempfile
-    src = '#include <stdio.h>\n#include "irsgmcmc.h"\nint main(){printf("%zu %zu", sizeof(irs_sgld_config), sizeof(irs_sgld_buffers));return 0;}'
+    src = ('#include <stdio.h>\n#include <stddef.h>\n#include "irsgmcmc.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu", '
+           'sizeof(irs_sgld_config), sizeof(irs_sgld_buffers), offsetof(irs_sgld_config, seed), '
+           'offsetof(irs_sgld_config, ffd_cps), offsetof(irs_sgld_config, ffd_grid), offsetof(irs_sgld_config, ffd_kernel), '
+           'offsetof(irs_sgld_buffers, ffd_dense));return 0;}')
     with tempfile.TemporaryDirectory() as d:
         with open(os.path.join(d, 't.c'), 'w') as f:
             f.write(src)
         subprocess.check_call(['gcc', '-I', os.path.join(ROOT, 'include'), os.path.join(d, 't.c'), '-o', os.path.join(d, 't')])
-        a, b = subprocess.check_output([os.path.join(d, 't')]).decode().split()
+        a, b, *offs = [int(x) for x in subprocess.check_output([os.path.join(d, 't')]).decode().split()]
     from irsgmcmc_b200 import _lib
-    assert int(a) == ctypes.sizeof(_lib.SgldConfig) and int(b) == ctypes.sizeof(_lib.SgldBuffers)
+    assert a == ctypes.sizeof(_lib.SgldConfig) and b == ctypes.sizeof(_lib.SgldBuffers)
+    C, B = _lib.SgldConfig, _lib.SgldBuffers
+    assert offs == [C.seed.offset, C.ffd_cps.offset, C.ffd_grid.offset, C.ffd_kernel.offset, B.ffd_dense.offset]
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason='checks the behaviour without a GPU')
@@ -125,6 +130,17 @@ def test_config_from_reference_json():
                        'uniform_noise': {'enabled': True, 'magnitude': 0.1}}}
     c = sampler_config_from_json(cfg)
     assert (c.data_loss, c.no_components, c.s, c.reg_loss, c.w_reg, c.tau) == ('lcc', 4, 2, 'RegLoss_LogNormal', 1.6, 0.4)
+    assert c.transformation == 'SVF_3D' and c.cps is None
+    cfg['transformation_module'] = {'type': 'SVFFD_3D', 'args': {'cps': [4, 4, 4]}}   # configs/experiment5/config_SVFFD_4.json
+    c = sampler_config_from_json(cfg)
+    assert c.transformation == 'SVFFD_3D' and c.cps == (4, 4, 4)
+    cfg['transformation_module'] = {'type': 'SVFFD_3D', 'args': {}}
+    with pytest.raises(ValueError):
+        sampler_config_from_json(cfg)
+    cfg['transformation_module'] = {'type': 'SVF_2D', 'args': {}}
+    with pytest.raises(NotImplementedError):
+        sampler_config_from_json(cfg)
+    del cfg['transformation_module']
     cfg['reg_loss']['type'] = 'RegLoss_Student'
     with pytest.raises(NotImplementedError):
         sampler_config_from_json(cfg)

@@ -167,6 +167,34 @@ def test_oracle_transition_vs_reference_golden(tag, reg, w_reg):
         assert rel(regp, g[p + 'reg_params']) < 1e-7
 
 
+def test_oracle_svffd_transition_vs_reference_golden():
+    """SVFFD_3D as the transformation module (configs/experiment5): chain state on the control grid"""
+    from irsgmcmc_b200.data_loader.synthetic import make_pair
+    g = load('transition_svffd_lognormal.npz')
+    n, C, cps = int(g['n']), int(g['C']), tuple(int(x) for x in g['cps'])
+    assert O.control_grid_size((n,) * 3, cps) == tuple(int(x) for x in g['grid'])
+    torch.manual_seed(123)
+    fixed, moving, _ = make_pair(n)
+    for dtype, sfx, tol_f, tol_g in ((torch.float32, '', 1e-5, 2e-3), (torch.float64, '_f64', 1e-6, 1e-5)):
+        cfg = O.Config(reg='lognormal', w_reg=1.6, cps=cps)
+        st = O.State(cfg, g[f'it0{sfx}_v_before'].to(dtype), g['sigma'].to(dtype).expand(C, -1, -1, -1, -1), (n, n, n), dtype)
+        st.init_gmm(0.7)
+        cast = lambda d: {k: (v.to(dtype) if v.dtype == torch.float32 else v) for k, v in d.items()}
+        lt, out, aux, grad_v = O.sgld_transition(st, cast(fixed), cast(moving), g['it0_eps'].to(dtype),
+                                                 g['it0_jitter'].to(dtype))
+        p = f'it0{sfx}_'
+        assert out['curr_state'].shape == g[p + 'curr_state'].shape == (C, 3, *g['grid'].tolist())
+        for key in ('curr_state', 'transformation', 'displacement', 'im_moving_warped'):
+            assert rel(out[key], g[p + key]) < tol_f, (key, dtype)
+        assert rel(O.ffd_dense(out['curr_state'], (n,) * 3, cps), g[p + 'velocity']) < tol_f
+        assert rel(torch.stack(aux['alpha']), g[p + 'alpha']) < 1e-4
+        assert rel(torch.stack(lt['data']), g[p + 'data']) < 1e-4
+        assert rel(torch.stack(lt['reg']), g[p + 'reg']) < 1e-6
+        assert rel(torch.stack(aux['reg_energy']), g[p + 'reg_energy']) < 1e-6
+        assert rel(grad_v, g[p + 'grad_v']) < tol_g, dtype
+        assert rel(torch.stack((st.loc, st.log_scale)), g[p + 'reg_params']) < 1e-7
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # CUDA path vs reference golden vectors (GPU)
 # ---------------------------------------------------------------------------------------------------------------------
@@ -230,3 +258,59 @@ def test_cuda_transition_vs_reference_golden(tag, reg, w_reg, built):
         if it == 0:
             assert grad_ok(s.grad_v, g[p + 'grad_v'], g[p64 + 'grad_v'], 'golden grad_v')
             assert rel(s.gmm_parameters()[0], g[p + 'log_std']) < 1e-5
+
+
+@pytest.mark.gpu
+def test_cuda_svffd_transition_vs_reference_golden(built):
+    """the fused CUDA step with SVFFD_3D as the transformation model on the reference's inputs and injected noise"""
+    from irsgmcmc_b200.sampler import SGLDSampler, SGLDConfig
+    from irsgmcmc_b200.data_loader.synthetic import make_pair
+    g = load('transition_svffd_lognormal.npz')
+    n, C, cps = int(g['n']), int(g['C']), tuple(int(x) for x in g['cps'])
+    torch.manual_seed(123)
+    fixed, moving, _ = make_pair(n)
+    s = SGLDSampler(fixed, moving, C, SGLDConfig(transformation='SVFFD_3D', cps=cps), device='cuda:0')
+    assert s.v.shape == (C, 3, *g['grid'].tolist())
+    assert s.launches_per_step() == SGLDSampler(fixed, moving, C, SGLDConfig(), device='cuda:0').launches_per_step() + 7
+    s.set_state(g['v0'], g['sigma'])
+    s.init_gmm(sigma_hat=0.7)
+    for it in range(2):
+        s.set_noise(g[f'it{it}_eps'], g[f'it{it}_jitter'])
+        s.step(1, use_graph=False)
+        torch.cuda.synchronize()
+        tol = 1e-5 if it == 0 else 2e-3    # iteration 1 starts from a state that already differs by the kink noise
+        p, p64 = f'it{it}_', f'it{it}_f64_'
+        out = s.output()
+        for key in ('curr_state', 'transformation', 'displacement', 'im_moving_warped'):
+            assert out[key].shape == g[p + key].shape and rel(out[key], g[p + key]) < tol, (it, key)
+        assert rel(s._ffd_dense, g[p + 'velocity']) < tol
+        terms = s.loss_terms()
+        assert rel(terms['reg_energy'], g[p + 'reg_energy']) < tol and rel(terms['reg'], g[p + 'reg']) < tol
+        assert rel(terms['alpha'], g[p + 'alpha']) < max(tol, 1e-4) and rel(terms['data'], g[p + 'data']) < max(tol, 1e-4)
+        if it == 0:
+            # kink flips (SURVEY surprise 9) are isolated voxels of the DENSE gradient: the acceptance rule applies there;
+            # a control point sums 15^3 of them, so its gradient is compared in the L2 norm
+            assert grad_ok(s._ffd_grad, g[p + 'grad_dense'], g[p64 + 'grad_dense'], 'golden SVFFD dense gradient')
+            assert rel(s.grad_v, g[p64 + 'grad_v']) < 2e-3 and s.grad_v.shape == g[p + 'grad_v'].shape
+            assert rel(s.gmm_parameters()[0], g[p + 'log_std']) < 1e-5
+        assert rel(s.v, g[p + 'v_after']) < 2e-3
+    # graph replay == eager, Philox noise on the control grid (the FFD launches are captured like the others)
+    outs = []
+    for use_graph in (False, True):
+        r = SGLDSampler(fixed, moving, C, SGLDConfig(transformation='SVFFD_3D', cps=cps), device='cuda:0')
+        r.set_state(g['v0'], g['sigma'])
+        r.init_gmm(sigma_hat=0.7)
+        r.step(4, use_graph=use_graph)
+        torch.cuda.synchronize()
+        outs.append((r.v.clone(), r.hyper.clone()))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    assert bool(torch.isfinite(outs[0][0]).all()) and not torch.equal(outs[0][0].cpu(), g['v0'])
+    # Trainer.__GMM_init through the FFD (irs_sgld_gmm_init) against the oracle
+    torch.manual_seed(1)
+    v_sample = 1.5 * torch.randn(1, 3, *g['grid'].tolist())
+    r = SGLDSampler(fixed, moving, 1, SGLDConfig(transformation='SVFFD_3D', cps=cps), device='cuda:0')
+    r.init_gmm(v_sample)
+    st = O.State(O.Config(cps=cps), v_sample, torch.ones_like(v_sample), (n, n, n))
+    O.gmm_init(st, fixed, moving, v_sample)
+    ls, lg = r.gmm_parameters()
+    assert rel(ls, st.log_std) < 1e-4 and rel(lg, st.logits) < 1e-3

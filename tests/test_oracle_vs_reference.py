@@ -74,6 +74,54 @@ def test_transition_matches_reference(ref, dtype, reg_name, reg_type):
             assert abs(float(st.log_w_reg) - float(reg.log_w_reg)) < 1e-6
 
 
+@pytest.mark.parametrize('dtype', [torch.float32, torch.float64])
+def test_svffd_transition_matches_reference(ref, dtype):
+    """the same with SVFFD_3D as the transformation module (configs/experiment5): the chain state on the control grid"""
+    from irsgmcmc_b200.data_loader.synthetic import make_pair
+    n, C, cps = 16, 2, (4, 4, 4)
+    grid = O.control_grid_size((n,) * 3, cps)
+    torch.manual_seed(321)
+    fixed, moving, _ = make_pair(n)
+    t = ref_import.make_trainer(ref, (n, n, n), C, reg_type='RegLoss_LogNormal', w_reg=1.6, uniform_noise=0.1,
+                                dtype=dtype if dtype == torch.float64 else None, cps=cps)
+    if dtype == torch.float64:
+        t.registration_module = lambda im, T: F.grid_sample(im, T.permute(0, 2, 3, 4, 1), mode='bilinear',
+                                                            padding_mode='border', align_corners=True)
+    gmm, reg = t.losses['data']['loss'], t.losses['reg']['loss']
+    gmm.init_parameters(torch.tensor(1.0))
+    cast = lambda d: {k: (v.to(dtype) if v.dtype == torch.float32 else v).expand(C, *v.shape[1:]) for k, v in d.items()}
+    fx, mv = cast(fixed), cast(moving)
+    v0 = (1.5 * torch.randn(C, 3, *grid)).to(dtype)
+    sigma = (0.5 + torch.rand(1, 3, *grid)).to(dtype).expand(C, -1, -1, -1, -1)
+    ref_import.attach_state(t, v0, sigma, 0.4)
+    st = O.State(O.Config(reg='lognormal', w_reg=1.6, cps=cps), v0, sigma, (n, n, n), dtype)
+    st.init_gmm(1.0)
+    f_tol, g_tol = (1e-5, 5e-4) if dtype == torch.float32 else (1e-12, 1e-6)
+    for it in range(2):
+        eps, ju = torch.randn(C, 3, *grid).to(dtype), torch.rand(C, 3, n, n, n).to(dtype)
+        ref.util.get_noise_Langevin = lambda s, tau, e=eps: math.sqrt(2.0 * tau) * s * e
+        ref.util.get_noise_uniform = lambda shape, device, alpha, j=ju: -2.0 * alpha * j + alpha
+        st.v = t.v_curr_state.detach().clone()
+        v_before = st.v.clone()
+        lt, out, aux = t._SGLD_transition(fx, mv, gmm, reg)
+        lt2, out2, aux2, grad_v = O.sgld_transition(st, {k: v[:1] for k, v in fx.items()}, {k: v[:1] for k, v in mv.items()},
+                                                    eps, ju)
+        assert out['curr_state'].shape == (C, 3, *grid) and out['displacement'].shape == (C, 3, n, n, n)
+        for key in ('curr_state', 'transformation', 'displacement', 'im_moving_warped'):
+            assert rel(out2[key], out[key]) < f_tol, (it, key)
+        assert rel(torch.stack(lt2['data']), torch.stack([a.detach() for a in lt['data']])) < 1e-4
+        assert rel(torch.stack(lt2['reg']), torch.stack([a.detach() for a in lt['reg']])) < 1e-6
+        assert rel(torch.stack(aux2['reg_energy']), torch.stack([a.detach() for a in aux['reg_energy']])) < 1e-6
+        assert rel(grad_v, (v_before - t.v_curr_state.detach()) / 0.4) < g_tol
+        assert rel(st.log_std, gmm.log_std.detach()) < 1e-4 and rel(st.logits, gmm.logits.detach()) < 1e-3
+        st.log_std.copy_(gmm.log_std.detach())
+        st.logits.copy_(gmm.logits.detach())
+        for dst, p in zip(st.adam_gmm.m + st.adam_gmm.v, [t.optimizer_GMM.state[q][k] for k in ('exp_avg', 'exp_avg_sq')
+                                                            for q in (gmm.log_std, gmm.logits)]):
+            dst.copy_(p)
+        assert abs(float(st.loc) - float(reg.loc)) < 1e-6 and abs(float(st.log_scale) - float(reg.log_scale)) < 1e-6
+
+
 def test_reference_adam_matches_oracle_adam(ref):
     torch.manual_seed(0)
     p_ref = [torch.nn.Parameter(torch.randn(4)), torch.nn.Parameter(torch.randn(4))]

@@ -28,10 +28,22 @@ def main():
     ap.add_argument('--size', type=int, default=128)
     ap.add_argument('--chains', type=int, default=1)
     ap.add_argument('--amp', type=float, default=1.5, help='max |v| in voxels')
+    ap.add_argument('--ffd', type=int, default=0, help='control point spacing: time only the B-spline FFD ops')
     args = ap.parse_args()
     n, C = args.size, args.chains
     dev = 'cuda:0'
     torch.manual_seed(0)
+    if args.ffd:
+        from irsgmcmc_b200.utils import B_spline_1D_kernel, get_control_grid_size
+        cps, dims = (args.ffd,) * 3, (n,) * 3
+        grid = get_control_grid_size(dims, cps)
+        ks = [tuple(float(x) for x in B_spline_1D_kernel(args.ffd))] * 3
+        cp, G = torch.randn(C, 3, *grid, device=dev), torch.randn(C, 3, *dims, device=dev)
+        for name, fn in ((f'ffd_fwd cps={args.ffd}', lambda: ops.ffd_fwd(cp, ks, cps, dims)),
+                         (f'ffd_bwd cps={args.ffd}', lambda: ops.ffd_bwd(G, ks, cps, grid))):
+            us = timeit(fn)
+            print(f'{name:55s} {us:10.1f} us   {us * 1e3 / (C * n ** 3):8.3f} ns/voxel')
+        return
     taps = list(Sobolev_kernel_1D(3, 0.5)[0].astype('float32'))
     v = langevin_sobolev(torch.randn(C, 3, n, n, n, device=dev), None, 0.0, taps)
     v = v / v.abs().max() * args.amp
