@@ -14,15 +14,12 @@ namespace {
 
 template <int VEC, bool ADJOINT>
 __global__ void __launch_bounds__(256)
-ffd_axis_kernel(const float* __restrict__ in, float* __restrict__ out, long long total, int g, int n, long long inner,
+ffd_axis_kernel(const float* __restrict__ in, float* __restrict__ out, unsigned groups, int g, int n, unsigned inner,
                 const __grid_constant__ IrsFfdAxis ax) {
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total / VEC; i += stride) {
+    const unsigned stride = gridDim.x * blockDim.x;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < groups; i += stride) {
         float r[VEC];
-#pragma unroll
-        for (int k = 0; k < VEC; ++k)
-            r[k] = ADJOINT ? irs_body_ffd_axis_bwd(in, i * VEC + k, g, n, inner, ax)
-                           : irs_body_ffd_axis_fwd(in, i * VEC + k, g, n, inner, ax);
+        irs_body_ffd_axis_group<VEC, ADJOINT>(in, i, g, n, inner, ax, r);
         if constexpr (VEC == 4) reinterpret_cast<float4*>(out)[i] = make_float4(r[0], r[1], r[2], r[3]);
         else out[i] = r[0];
     }
@@ -42,20 +39,28 @@ int launch_axis(const float* in, float* out, bool adjoint, long long outer, int 
     // every dense element must exist in the un-cropped result of the transposed convolution: (g - 1) s + 1 elements
     if (g < 1 || n < 1 || outer < 1 || inner < 1 || (long long)ax.off + n > (long long)(g - 1) * ax.s + 1)
         return IRS_ERR_BAD_ARG;
-    const long long total = outer * (adjoint ? g : n) * inner;
-    const bool vec = total % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
-    const long long work = vec ? total / 4 : total;
-    long long blocks = (work + 255) / 256;
-    if (blocks > 148 * 8) blocks = 148 * 8;
-    if (blocks < 1) blocks = 1;
-    if (vec) {
-        if (adjoint) ffd_axis_kernel<4, true><<<(unsigned)blocks, 256, 0, st>>>(in, out, total, g, n, inner, ax);
-        else ffd_axis_kernel<4, false><<<(unsigned)blocks, 256, 0, st>>>(in, out, total, g, n, inner, ax);
-    } else {
-        if (adjoint) ffd_axis_kernel<1, true><<<(unsigned)blocks, 256, 0, st>>>(in, out, total, g, n, inner, ax);
-        else ffd_axis_kernel<1, false><<<(unsigned)blocks, 256, 0, st>>>(in, out, total, g, n, inner, ax);
+    // 32-bit flat indices inside a launch: larger arrays go in slices of whole `outer` rows (rows are independent)
+    const long long row_in = (long long)(adjoint ? n : g) * inner, row_out = (long long)(adjoint ? g : n) * inner;
+    if (row_in >= (1ll << 31) || row_out >= (1ll << 31)) return IRS_ERR_UNSUPPORTED;
+    const long long rows_per_launch = (1ll << 31) / (row_in > row_out ? row_in : row_out);
+    for (long long o0 = 0; o0 < outer; o0 += rows_per_launch) {
+        const long long rows = outer - o0 < rows_per_launch ? outer - o0 : rows_per_launch;
+        const float* src = in + o0 * row_in;
+        float* dst = out + o0 * row_out;
+        const long long total = rows * row_out;
+        const bool vec = total % 4 == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0;
+        const unsigned groups = (unsigned)(vec ? total / 4 : total);
+        unsigned blocks = (groups + 255) / 256;
+        if (blocks > 148 * 8) blocks = 148 * 8;
+        if (vec) {
+            if (adjoint) ffd_axis_kernel<4, true><<<blocks, 256, 0, st>>>(src, dst, groups, g, n, (unsigned)inner, ax);
+            else ffd_axis_kernel<4, false><<<blocks, 256, 0, st>>>(src, dst, groups, g, n, (unsigned)inner, ax);
+        } else {
+            if (adjoint) ffd_axis_kernel<1, true><<<blocks, 256, 0, st>>>(src, dst, groups, g, n, (unsigned)inner, ax);
+            else ffd_axis_kernel<1, false><<<blocks, 256, 0, st>>>(src, dst, groups, g, n, (unsigned)inner, ax);
+        }
+        IRS_LAUNCH_CHECK();
     }
-    IRS_LAUNCH_CHECK();
     return IRS_OK;
 }
 

@@ -20,41 +20,81 @@ struct IrsFfdAxis {
     float k[IRS_FFD_MAX_KERNEL + 1];   // the reference's B_spline_1D_kernel(s): 4 s - 1 taps
 };
 
-// arrays are (outer, len, inner) row-major; idx enumerates the OUTPUT (outer, n, inner)
-IRS_HD float irs_body_ffd_axis_fwd(const float* __restrict__ cp, long long idx, int g, int n, long long inner,
+// position inside an (outer, len, inner) row-major array; flat indices stay below 2^32 elements per launch (checked by the
+// launcher), so the two divisions are 32-bit -- the 64-bit ones cost more than the interpolation itself
+struct IrsFfdPos {
+    unsigned o, x, in_i;
+};
+
+IRS_HD IrsFfdPos irs_ffd_decompose(unsigned idx, unsigned len, unsigned inner) {
+    IrsFfdPos p;
+    const unsigned rest = idx / inner;
+    p.in_i = idx - rest * inner;
+    p.o = rest / len;
+    p.x = rest - p.o * len;
+    return p;
+}
+
+// the next flat index
+IRS_HD void irs_ffd_advance(IrsFfdPos& p, unsigned len, unsigned inner) {
+    if (++p.in_i == inner) {
+        p.in_i = 0;
+        if (++p.x == len) { p.x = 0; ++p.o; }
+    }
+}
+
+// dense element p.x of row (p.o, p.in_i) from the g control points of that row; p.x + off + 2 s - 1 = q s + r
+IRS_HD float irs_body_ffd_axis_fwd(const float* __restrict__ cp, IrsFfdPos p, int q, int r, int g, unsigned inner,
                                    const IrsFfdAxis& ax) {
-    const long long in_i = idx % inner;
-    const long long rest = idx / inner;
-    const int x = (int)(rest % n);
-    const long long o = rest / n;
-    const int t = x + ax.off + 2 * ax.s - 1;
-    const int q = t / ax.s, r = t - q * ax.s;
-    const float* base = cp + (o * g) * inner + in_i;
+    const float* base = cp + ((size_t)p.o * g) * inner + p.in_i;
     float acc = 0.f;
 #pragma unroll
     for (int m = 3; m >= 0; --m) {   // ascending control point index, the order conv_transpose1d accumulates in
         const int i = q - m, j = r + m * ax.s;
-        if (i >= 0 && i < g && j <= 4 * ax.s - 2) acc = fmaf(ax.k[j], base[(long long)i * inner], acc);
+        if (i >= 0 && i < g && j <= 4 * ax.s - 2) acc = fmaf(ax.k[j], base[(size_t)i * inner], acc);
     }
     return acc;
 }
 
-// adjoint: idx enumerates the control-point side (outer, g, inner); sums over the dense elements in the support
-IRS_HD float irs_body_ffd_axis_bwd(const float* __restrict__ gd, long long idx, int g, int n, long long inner,
-                                   const IrsFfdAxis& ax) {
-    const long long in_i = idx % inner;
-    const long long rest = idx / inner;
-    const int i = (int)(rest % g);
-    const long long o = rest / g;
+// adjoint: control point p.x of row (p.o, p.in_i) sums over the dense elements (n of them) in its support
+IRS_HD float irs_body_ffd_axis_bwd(const float* __restrict__ gd, IrsFfdPos p, int n, unsigned inner, const IrsFfdAxis& ax) {
+    const int i = (int)p.x;
     // 0 <= t - i s <= 4 s - 2 with t = x + off + 2 s - 1
     int lo = i * ax.s - ax.off - 2 * ax.s + 1, hi = lo + 4 * ax.s - 2;
     lo = lo < 0 ? 0 : lo;
     hi = hi > n - 1 ? n - 1 : hi;
-    const float* base = gd + (o * n) * inner + in_i;
+    const float* base = gd + ((size_t)p.o * n) * inner + p.in_i;
     float acc = 0.f;
     for (int x = lo; x <= hi; ++x) {
         const int j = x + ax.off + 2 * ax.s - 1 - i * ax.s;
-        acc = fmaf(ax.k[j], base[(long long)x * inner], acc);
+        acc = fmaf(ax.k[j], base[(size_t)x * inner], acc);
     }
     return acc;
+}
+
+// VEC consecutive flat output elements starting at first * VEC (what one CUDA thread computes)
+template <int VEC, bool ADJOINT>
+IRS_HD void irs_body_ffd_axis_group(const float* __restrict__ in, unsigned first, int g, int n, unsigned inner,
+                                    const IrsFfdAxis& ax, float* r) {
+    const unsigned len = ADJOINT ? (unsigned)g : (unsigned)n;
+    IrsFfdPos p = irs_ffd_decompose(first * VEC, len, inner);
+    // (q, rem) of the current dense element follow p.x without further divisions
+    const int t = (int)p.x + ax.off + 2 * ax.s - 1;
+    int q = t / ax.s, rem = t - q * ax.s;
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+        r[k] = ADJOINT ? irs_body_ffd_axis_bwd(in, p, n, inner, ax) : irs_body_ffd_axis_fwd(in, p, q, rem, g, inner, ax);
+        const unsigned x_before = p.x;
+        irs_ffd_advance(p, len, inner);
+        if (!ADJOINT && p.x != x_before) {
+            if (p.x == 0) {   // next row
+                const int t0 = ax.off + 2 * ax.s - 1;
+                q = t0 / ax.s;
+                rem = t0 - q * ax.s;
+            } else if (++rem == ax.s) {
+                rem = 0;
+                ++q;
+            }
+        }
+    }
 }

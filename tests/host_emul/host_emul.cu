@@ -195,8 +195,18 @@ extern "C" void emul_bspline_axis(const float* in, float* out, int adjoint, long
                                   long long inner, const float* kernel, int s, int off) {
     const IrsFfdAxis ax = emul_axis(kernel, s, off);
     const long long total = outer * (adjoint ? g : n) * inner;
-    for (long long i = 0; i < total; ++i)
-        out[i] = adjoint ? irs_body_ffd_axis_bwd(in, i, g, n, inner, ax) : irs_body_ffd_axis_fwd(in, i, g, n, inner, ax);
+    // like the launcher: groups of four consecutive elements when the total allows it, single elements otherwise
+    if (total % 4 == 0) {
+        for (unsigned i = 0; i < (unsigned)(total / 4); ++i) {
+            if (adjoint) irs_body_ffd_axis_group<4, true>(in, i, g, n, (unsigned)inner, ax, out + 4 * (size_t)i);
+            else irs_body_ffd_axis_group<4, false>(in, i, g, n, (unsigned)inner, ax, out + 4 * (size_t)i);
+        }
+    } else {
+        for (unsigned i = 0; i < (unsigned)total; ++i) {
+            if (adjoint) irs_body_ffd_axis_group<1, true>(in, i, g, n, (unsigned)inner, ax, out + i);
+            else irs_body_ffd_axis_group<1, false>(in, i, g, n, (unsigned)inner, ax, out + i);
+        }
+    }
 }
 
 extern "C" void emul_ffd(const float* in, float* out, int adjoint, const float* kd, const float* kh, const float* kw,

@@ -94,6 +94,27 @@ def test_device_arithmetic_on_host(built, gold, tag):
     assert rel(out, full) < 1e-6
 
 
+@pytest.mark.parametrize('n,cps,C', [(10, (3, 2, 4), 2), (6, (1, 1, 1), 2), (18, (8, 5, 7), 4)])
+def test_device_arithmetic_groups_crossing_rows(built, n, cps, C):
+    """sizes where a thread's four consecutive outputs straddle row and plane boundaries (rows not a multiple of four
+    while the total is), against the oracle"""
+    emul = ctypes.CDLL(built['emul'])
+    dims = (n,) * 3
+    grid = O.control_grid_size(dims, cps)
+    assert (C * 3 * n ** 3) % 4 == 0 and n % 4 != 0
+    ks = [np.ascontiguousarray(O.bspline_taps(s).numpy()) for s in cps]
+    gen = torch.Generator().manual_seed(5)
+    cp = torch.randn(C, 3, *grid, generator=gen)
+    G = torch.randn(C, 3, *dims, generator=gen)
+    cp64 = cp.double().requires_grad_(True)
+    ref = O.ffd_dense(cp64, dims, cps)
+    g64, = torch.autograd.grad((ref * G.double()).sum(), cp64)
+    dense, g_cp = np.zeros((C, 3, *dims), np.float32), np.zeros((C, 3, *grid), np.float32)
+    emul.emul_ffd(P(cp.numpy()), P(dense), 0, P(ks[0]), P(ks[1]), P(ks[2]), *cps, C, *grid, *dims)
+    emul.emul_ffd(P(G.numpy()), P(g_cp), 1, P(ks[0]), P(ks[1]), P(ks[2]), *cps, C, *grid, *dims)
+    assert rel(dense, ref) < 1e-6 and rel(g_cp, g64) < 1e-6
+
+
 def test_oracle_conv1d_axis(gold):
     for tag in 'ab':
         _, cps, _ = case(gold, tag)
