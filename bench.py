@@ -13,6 +13,7 @@ with NCCL once after the timed region (reported, not part of the metric).
 """
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -122,7 +123,9 @@ def workload_config(args, chains, n):
     return {'workload': f'{n}^3 synthetic brain-MRI-shaped pair, {"LCC+GMM(K=4,s=2)" if args.data == "lcc" else "SSD(K=1)"} '
                         f'data term, virtual decimation, uniform jitter 0.1, Sobolev s=3, '
                         f'{"RegLoss_LogNormal w=1.6 learnable" if args.data == "lcc" else "RegLoss_L2 w=1.4"}, SVF 12 steps, '
-                        f'tau 0.4, VI-shaped init; {chains} SGLD chain(s) per GPU (BASELINE.json configs[1])',
+                        f'tau 0.4, VI-shaped init; {chains} SGLD chain(s) per GPU (BASELINE.json configs[1])'
+                        + (f'; SECONDARY configuration: SVFFD_3D transformation, control point spacing {args.cps}'
+                           if getattr(args, 'cps', 0) else ''),
             'volume': [n, n, n], 'chains_per_gpu': chains, 'parallelism': 'independent chains sharded by rank',
             'l2_policy': 'working set per transition (SVF history 288 MiB/chain at 128^3 + 20 field-sized buffers) '
                          'exceeds the 126 MB L2; no explicit flush'}
@@ -140,6 +143,8 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-graph', action='store_true')
     ap.add_argument('--e2e-steps', type=int, default=0, help='default: min(steps, 50)')
+    ap.add_argument('--cps', type=int, default=0, help='secondary configuration: SVFFD_3D with this control point '
+                    'spacing as the transformation model (reference configs/experiment5); 0 = SVF_3D, the headline')
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)
@@ -167,8 +172,13 @@ def main():
     V = n ** 3
     fixed, moving, vp = make_pair(n)
     reg = 'RegLoss_LogNormal' if args.data == 'lcc' else 'RegLoss_L2'
+    ffd = dict(transformation='SVFFD_3D', cps=(args.cps,) * 3) if args.cps else {}
     cfg = SGLDConfig(data_loss=args.data, reg_loss=reg, w_reg=1.6 if args.data == 'lcc' else 1.4,
-                     reg_learnable=args.data == 'lcc')
+                     reg_learnable=args.data == 'lcc', **ffd)
+    if args.cps:   # the variational parameters live on the control grid (reference data_loader/datasets.py:23-27,57-68)
+        from irsgmcmc_b200.utils import get_control_grid_size
+        gdims = (1, 3, *get_control_grid_size((n, n, n), cfg.cps))
+        vp = {'mu': torch.zeros(gdims), 'log_var': torch.full(gdims, math.log(0.5 ** 2)), 'u': torch.full(gdims, 0.1)}
     sampler = SGLDSampler(fixed, moving, C, cfg, device=dev, chain_offset=rank * C)
     gen = torch.Generator(device=dev).manual_seed(123 + rank)
     sampler.init_chains('VI', vp, generator=gen)
@@ -270,6 +280,8 @@ def main():
     kernel_ms = stage_ms['svf_adjoint'] / svf_steps
     achieved = SVF_BWD_BYTES_PER_VOXEL * C * V / (kernel_ms * 1e-3) / 1e9
     bytes_step = BYTES_PER_VOXEL_STEP_LCC if args.data == 'lcc' else BYTES_PER_VOXEL_STEP_SSD
+    if args.cps:   # proposal (36 B) and update (60 B) act on the control grid; the FFD writes / its adjoint reads 12 B per voxel
+        bytes_step = bytes_step - 96 + 24 + 96.0 * sampler.v[0, 0].numel() / V
     step_gbs = bytes_step * (value / world) / 1e9
 
     # ---- posterior moments: Welford update + NCCL merge (once per run; outside the metric) ----
