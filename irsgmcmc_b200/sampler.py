@@ -265,6 +265,32 @@ class SGLDSampler:
         _lib.check(self.lib.irs_sgld_gmm_init(ctypes.byref(self._cconf), ctypes.byref(b), _lib.ptr(v_sample), warm_up,
                                               _lib.stream()))
 
+    # ------------------------------------------------------------------------------------------------------------------
+    # checkpoint / resume (the reference has none -- a run that dies starts over)
+    # ------------------------------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def state_dict(self):
+        """everything the chains carry between transitions, as host tensors: states, preconditioner, the shared mixture /
+        regulariser parameters with their Adam moments and the Philox offset (`hyper`), the running posterior moments.
+        A sampler restored from it continues bit-identically (the noise is a function of seed, chain, iteration)."""
+        return {'dims': tuple(self.dims), 'state_dims': tuple(self.state_dims), 'no_chains': self.C,
+                'chain_offset': self.chain_offset, 'seed': self.cfg.seed, 'iteration': self.iteration,
+                'v': self.v.cpu(), 'sigma': None if self.sigma is None else self.sigma.cpu(), 'hyper': self.hyper.cpu(),
+                'n_kept': self.n_kept, 'disp_mean': self.disp_mean.cpu(), 'disp_m2': self.disp_m2.cpu(),
+                'im_mean': self.im_mean.cpu(), 'im_m2': self.im_m2.cpu()}
+
+    @torch.no_grad()
+    def load_state_dict(self, sd):
+        for key, mine in (('dims', tuple(self.dims)), ('state_dims', tuple(self.state_dims)), ('no_chains', self.C),
+                          ('chain_offset', self.chain_offset), ('seed', self.cfg.seed)):
+            if tuple(sd[key]) != mine if isinstance(mine, tuple) else sd[key] != mine:
+                raise ValueError(f'checkpoint does not match this sampler: {key} = {sd[key]} (here {mine})')
+        self.set_state(sd['v'], sd['sigma'])
+        self.hyper.copy_(sd['hyper'])
+        self.iteration, self.n_kept = int(sd['iteration']), int(sd['n_kept'])
+        for name in ('disp_mean', 'disp_m2', 'im_mean', 'im_m2'):
+            getattr(self, name).copy_(sd[name])
+
     def set_noise(self, eps=None, jitter_unit=None):
         """explicit N(0,1) / U[0,1) numbers (C,3,D,H,W) instead of Philox: exact noise-on parity tests"""
         self.eps_inject = None if eps is None else eps.to(self.device, torch.float32).contiguous()

@@ -357,3 +357,31 @@ def test_run_VI_then_MCMC(pkg):
     t._SGLD_init(vp)
     res = t._run_MCMC(m['data_loss'], m['reg_loss'], speed_test_iters=0)
     assert res['n'] == 3 * C and torch.isfinite(res['mean']).all()
+
+
+def test_run_VI_then_MCMC_svffd(pkg):
+    """the same with SVFFD_3D as the transformation model (reference configs/experiment5/config_SVFFD_4.json): variational
+    parameters, chain state and preconditioner on the control grid; VI in drop-in mode, sampling with the fused step"""
+    from irsgmcmc_b200.trainer import Trainer
+    from irsgmcmc_b200.data_loader.synthetic import make_pair
+    U = pkg[0]
+    n, C, cps = 16, 2, [4, 4, 4]
+    torch.manual_seed(4)
+    fixed, moving, _ = make_pair(n)
+    gdims = (1, 3, *U.get_control_grid_size((n,) * 3, cps))
+    vp0 = {'mu': torch.zeros(gdims), 'log_var': torch.full(gdims, math.log(0.5 ** 2)), 'u': torch.full(gdims, 0.1)}
+    cfg = _reference_style_config(C, burn_in=2, samples=6, period=2)
+    cfg['transformation_module'] = {'type': 'SVFFD_3D', 'args': {'cps': cps}}
+    cfg['trainer']['no_iters_VI'] = 3
+    t = Trainer(cfg, fixed, moving, vp0, device=torch.device(DEV))
+    assert t.sampler.v.shape == (C, *gdims[1:]) and t.sampler.displacement.shape == (C, 3, n, n, n)
+    vp, m, hist = t._run_VI()
+    assert isinstance(m['transformation_module'], U.SVFFD_3D)
+    assert len(hist) == 3 and all(torch.isfinite(h['loss']) for h in hist)
+    assert vp['mu'].shape == gdims and not torch.equal(vp['mu'].cpu(), vp0['mu'])
+    t._SGLD_init(vp)
+    lt, out, aux = t._SGLD_transition(None, None, m['data_loss'], m['reg_loss'])
+    assert out['curr_state'].shape == (C, *gdims[1:]) and out['transformation'].shape == (C, 3, n, n, n)
+    assert all(torch.isfinite(x) for x in lt['data'] + lt['reg'])
+    res = t._run_MCMC(m['data_loss'], m['reg_loss'], speed_test_iters=0)
+    assert res['n'] == 3 * C and torch.isfinite(res['mean']).all() and res['mean'].shape == (3, n, n, n)
