@@ -48,7 +48,9 @@ int launch_axis(const float* in, float* out, bool adjoint, long long outer, int 
         const float* src = in + o0 * row_in;
         float* dst = out + o0 * row_out;
         const long long total = rows * row_out;
-        const bool vec = total % 4 == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0;
+        // Along the contiguous axis the adjoint's lanes read windows s elements apart: one control point per lane keeps a
+        // warp's loads within 32 s floats (4 cache lines at s = 4), four per lane would spread them over 16.
+        const bool vec = total % 4 == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0 && !(adjoint && inner == 1);
         const unsigned groups = (unsigned)(vec ? total / 4 : total);
         unsigned blocks = (groups + 255) / 256;
         if (blocks > 148 * 8) blocks = 148 * 8;
