@@ -98,3 +98,63 @@ IRS_HD void irs_body_ffd_axis_group(const float* __restrict__ in, unsigned first
         }
     }
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Table forms used by the fast kernels.  Everything that depends only on the coordinate along the axis is computed once
+// per block: per dense element the four control-point indices (ascending, clamped into the grid) and their weights
+// (zero where the generic body skips a term), so an output costs two table reads, four loads and four FMAs.
+// ---------------------------------------------------------------------------------------------------------------------
+struct IrsFfdEntry {
+    int i[4];     // q - 3 .. q, clamped to [0, g - 1]
+    float w[4];   // taps[r + 3 s], taps[r + 2 s], taps[r + s], taps[r]; 0 for a term outside the grid / the kernel
+};
+
+IRS_HD IrsFfdEntry irs_ffd_entry(int x, int g, const IrsFfdAxis& ax) {
+    const int t = x + ax.off + 2 * ax.s - 1;
+    const int q = t / ax.s, r = t - q * ax.s;
+    IrsFfdEntry e;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        const int m = 3 - a, i = q - m, j = r + m * ax.s;
+        const bool ok = i >= 0 && i < g && j <= 4 * ax.s - 2;
+        e.i[a] = i < 0 ? 0 : (i > g - 1 ? g - 1 : i);
+        e.w[a] = ok ? ax.k[j] : 0.f;
+    }
+    return e;
+}
+
+// same accumulation order as irs_body_ffd_axis_fwd (ascending control point index)
+IRS_HD float irs_body_ffd_axis_fwd_tab(const float* __restrict__ row, unsigned inner, const IrsFfdEntry& e) {
+    float acc = 0.f;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) acc = fmaf(e.w[a], row[(size_t)e.i[a] * inner], acc);
+    return acc;
+}
+
+// Adjoint along the contiguous axis from a staged copy of the dense row: element x of the row sits at irs_ffd_skew(x).
+// With an even spacing the lanes of a warp (consecutive control points) would read shared-memory words s apart; the skew
+// x + (x >> tz), tz = trailing zero bits of s, turns that into s + s / 2^tz, which is odd: no bank conflicts.
+struct IrsFfdSkew {
+    int tz, mask;   // mask = 0 switches the skew off (odd spacing)
+};
+
+IRS_HD IrsFfdSkew irs_ffd_make_skew(int s) {
+    IrsFfdSkew k;
+    k.tz = 0;
+    k.mask = (s & 1) ? 0 : -1;
+    if (k.mask) while (!((s >> k.tz) & 1)) ++k.tz;
+    return k;
+}
+IRS_HD int irs_ffd_skew(int x, IrsFfdSkew k) { return x + ((x >> k.tz) & k.mask); }
+IRS_HD int irs_ffd_row_pitch(int n, IrsFfdSkew k) { return irs_ffd_skew(n - 1, k) + 1; }
+
+// same accumulation order as irs_body_ffd_axis_bwd (ascending dense element)
+IRS_HD float irs_body_ffd_axis_bwd_row(const float* __restrict__ srow, IrsFfdSkew k, int i, int n, const IrsFfdAxis& ax) {
+    int lo = i * ax.s - ax.off - 2 * ax.s + 1, hi = lo + 4 * ax.s - 2;
+    int j = lo < 0 ? -lo : 0;   // first tap that falls on the row
+    lo = lo < 0 ? 0 : lo;
+    hi = hi > n - 1 ? n - 1 : hi;
+    float acc = 0.f;
+    for (int x = lo; x <= hi; ++x, ++j) acc = fmaf(ax.k[j], srow[irs_ffd_skew(x, k)], acc);
+    return acc;
+}

@@ -3,6 +3,7 @@
 // Runs the library's __host__ __device__ per-voxel arithmetic (csrc/irs_common.cuh, irs_bodies.cuh, irs_hyper.cuh) in
 // plain loops on the CPU so that the `-m "not gpu"` tests can check it against the oracle without a GPU.  The CUDA
 // kernels call exactly these functions once per thread.
+#include <algorithm>
 #include <cstring>
 #include <vector>
 
@@ -195,6 +196,30 @@ extern "C" void emul_bspline_axis(const float* in, float* out, int adjoint, long
                                   long long inner, const float* kernel, int s, int off) {
     const IrsFfdAxis ax = emul_axis(kernel, s, off);
     const long long total = outer * (adjoint ? g : n) * inner;
+    if (inner == 1 && !adjoint) {   // ffd_fwd_rows_kernel: one table entry per x, rows marched
+        for (int x = 0; x < n; ++x) {
+            const IrsFfdEntry e = irs_ffd_entry(x, g, ax);
+            for (long long row = 0; row < outer; ++row)
+                out[row * n + x] = irs_body_ffd_axis_fwd_tab(in + row * g, 1u, e);
+        }
+        return;
+    }
+    if (inner == 1 && adjoint) {    // ffd_bwd_rows_kernel: rb rows staged with the bank-conflict skew, then gathered
+        const IrsFfdSkew sk = irs_ffd_make_skew(ax.s);
+        const int pitch = irs_ffd_row_pitch(n, sk);
+        long long rb = 2048 / n;
+        rb = rb < 1 ? 1 : (rb > 16 ? 16 : rb);
+        std::vector<float> s_rows((size_t)rb * pitch);
+        for (long long r0 = 0; r0 < outer; r0 += rb) {
+            const long long here = outer - r0 < rb ? outer - r0 : rb;
+            std::fill(s_rows.begin(), s_rows.end(), -1.0e30f);   // a read of an unstaged word would show
+            for (long long r = 0; r < here; ++r)
+                for (int x = 0; x < n; ++x) s_rows[r * pitch + irs_ffd_skew(x, sk)] = in[(r0 + r) * n + x];
+            for (long long e = 0; e < here * g; ++e)
+                out[r0 * g + e] = irs_body_ffd_axis_bwd_row(s_rows.data() + (e / g) * pitch, sk, (int)(e % g), n, ax);
+        }
+        return;
+    }
     // like the launcher: groups of four consecutive elements when the total allows it, single elements otherwise
     if (total % 4 == 0) {
         for (unsigned i = 0; i < (unsigned)(total / 4); ++i) {

@@ -250,3 +250,23 @@ def test_gpu_ffd_fullsize_adjoint_identity(built, n, cps):
     # a 16^3 corner of the volume against the oracle (the support of a voxel is local)
     sub = O.ffd_dense(x.cpu(), dims, cps)[..., :16, :16, :16]
     assert rel(Ax[..., :16, :16, :16], sub) < 1e-6
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('n,cps,C', [(128, (4, 4, 4), 1), (40, (2, 6, 2), 3), (33, (3, 1, 6), 2), (20, (8, 8, 8), 1)])
+def test_gpu_ffd_fast_kernels_match_generic(built, n, cps, C, monkeypatch):
+    """the kernels of the contiguous axis (rows marched with the table entry in registers; rows staged in shared memory
+    with the bank-conflict skew) against the generic axis kernel: same terms in the same order"""
+    from irsgmcmc_b200 import ops
+    dims = (n,) * 3
+    grid = O.control_grid_size(dims, cps)
+    ks = [tuple(float(x) for x in O.bspline_taps(s)) for s in cps]
+    g = torch.Generator(device=DEV).manual_seed(11)
+    x = torch.randn(C, 3, *grid, device=DEV, generator=g)
+    y = torch.randn(C, 3, *dims, device=DEV, generator=g)
+    fast = ops.ffd_fwd(x, ks, cps, dims), ops.ffd_bwd(y, ks, cps, grid)
+    monkeypatch.setenv('IRS_FFD_GENERIC', '1')
+    slow = ops.ffd_fwd(x, ks, cps, dims), ops.ffd_bwd(y, ks, cps, grid)
+    torch.cuda.synchronize()
+    for a, b in zip(fast, slow):
+        assert bool(torch.isfinite(a).all()) and float((a - b).abs().max()) <= 1e-6 * float(b.abs().max())
