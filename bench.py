@@ -74,8 +74,9 @@ class ClockSampler:
                 'samples': len(sm)}
 
 
-def oracle_transition_rate(n, steps, warmup, chains=1, data='lcc'):
-    """times the oracle port of Trainer._SGLD_transition on the host cores; returns (voxel-steps/s, ms/step, threads)"""
+def oracle_transition_rate(n, steps, warmup, chains=1, data='lcc', cps=0):
+    """times the oracle port of Trainer._SGLD_transition on the host cores; returns (voxel-steps/s, ms/step, threads)
+    cps > 0: SVFFD_3D with that control point spacing (the secondary configuration of --cps)"""
     import torch
     from oracle import sgld_oracle as O
     from irsgmcmc_b200.data_loader.synthetic import make_pair
@@ -83,9 +84,10 @@ def oracle_transition_rate(n, steps, warmup, chains=1, data='lcc'):
     torch.manual_seed(123)
     fixed, moving, vp = make_pair(n)
     cfg = O.Config(data=data, K=4 if data == 'lcc' else 1, reg='lognormal' if data == 'lcc' else 'l2',
-                   w_reg=1.6 if data == 'lcc' else 1.4)
-    sigma = torch.exp(0.5 * vp['log_var']).expand(chains, -1, -1, -1, -1)
-    v0 = vp['mu'] + sigma * torch.randn(chains, 3, n, n, n) + 0.1 * torch.randn(1)
+                   w_reg=1.6 if data == 'lcc' else 1.4, cps=(cps,) * 3 if cps else None)
+    sdims = O.control_grid_size((n, n, n), cfg.cps) if cps else (n, n, n)
+    sigma = torch.full((chains, 3, *sdims), 0.5)       # exp(log_var / 2) of make_pair's variational parameters
+    v0 = sigma * torch.randn(chains, 3, *sdims) + 0.1 * torch.randn(1)
     st = O.State(cfg, v0, sigma, (n, n, n))
     O.gmm_init(st, fixed, moving, v0[:1], warm_up=5)
     for _ in range(warmup):
@@ -104,11 +106,11 @@ def run_reference(args):
         return
     n = args.size
     # bounded sample: keep (steps + warmup) transitions within a few minutes; voxel-steps/s is volume-normalised
-    rate64, ms64, threads = oracle_transition_rate(64, 1, 1, 1, args.data)
+    rate64, ms64, threads = oracle_transition_rate(64, 1, 1, 1, args.data, args.cps)
     budget_s = 150.0
     est = (ms64 / 1e3) * (n / 64.0) ** 3 * (args.steps + args.warmup)
     n_run = n if est <= budget_s else 64
-    value, ms, threads = oracle_transition_rate(n_run, args.steps, args.warmup, 1, args.data)
+    value, ms, threads = oracle_transition_rate(n_run, args.steps, args.warmup, 1, args.data, args.cps)
     sample = f'{args.steps} timed + {args.warmup} warm-up oracle transitions at {n_run}^3, 1 chain, fp32, {threads} threads'
     line = {'impl': 'reference', 'metric': 'SGLD voxel-steps/s', 'value': value, 'unit': 'voxel-steps/s',
             'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms,
@@ -296,7 +298,7 @@ def main():
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
         n_cpu = n if n <= 128 else 128
-        v_cpu, ms_cpu, threads = oracle_transition_rate(n_cpu, 2, 0, 1, args.data)
+        v_cpu, ms_cpu, threads = oracle_transition_rate(n_cpu, 2, 0, 1, args.data, args.cps)
         cpu = {'value': v_cpu, 'unit': 'voxel-steps/s', 'cores': threads, 'kind': 'port',
                'sample': f'2 oracle transitions (oracle/sgld_oracle.py, torch CPU fp32, {threads} threads) at {n_cpu}^3, '
                          f'1 chain, {ms_cpu:.0f} ms each'}
