@@ -3,3 +3,5 @@ irsgmcmc_b200 -- B200-native SGLD registration step of dgrzech/ir-sgmcmc (hand-w
 PyTorch for device memory / streams / torch.distributed).  See DESIGN.md.
 """
 __version__ = '0.1.0'
+
+from . import torch_ops  # noqa: E402,F401  registers torch.ops.irsgmcmc.* (CUDA kernels only)
