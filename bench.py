@@ -99,6 +99,43 @@ def oracle_transition_rate(n, steps, warmup, chains=1, data='lcc', cps=0):
     return chains * n ** 3 * steps / dt, 1e3 * dt / max(steps, 1), torch.get_num_threads()
 
 
+def aten_gpu_transition_rate(n, steps, warmup, data='lcc', cps=0, device='cuda'):
+    """
+    SURVEY section 8(d), "the reference running its own PyTorch path on the B200": the oracle port of Trainer._SGLD_transition
+    (the reference's operators: F.grid_sample with its scatter-atomics backward, dense 125-tap convolutions, autograd) with
+    every tensor on the GPU.  A reported baseline like cpu_baseline, never part of `value`.  The oracle creates its helper
+    tensors with plain factory calls, so the default device is switched for the duration of the measurement.
+    """
+    import torch
+    from oracle import sgld_oracle as O
+    from irsgmcmc_b200.data_loader.synthetic import make_pair
+    torch.manual_seed(123)
+    fixed, moving, _ = make_pair(n)                       # host generators inside: before the default device changes
+    fixed = {k: v.to(device) for k, v in fixed.items()}
+    moving = {k: v.to(device) for k, v in moving.items()}
+    torch.set_default_device(device)
+    try:
+        cfg = O.Config(data=data, K=4 if data == 'lcc' else 1, reg='lognormal' if data == 'lcc' else 'l2',
+                       w_reg=1.6 if data == 'lcc' else 1.4, cps=(cps,) * 3 if cps else None)
+        sdims = O.control_grid_size((n, n, n), cfg.cps) if cps else (n, n, n)
+        sigma = torch.full((1, 3, *sdims), 0.5)
+        v0 = sigma * torch.randn(1, 3, *sdims) + 0.1 * torch.randn(1)
+        st = O.State(cfg, v0, sigma, (n, n, n))
+        O.gmm_init(st, fixed, moving, v0[:1], warm_up=5)
+        sync = torch.cuda.synchronize if str(device).startswith('cuda') else (lambda: None)
+        for _ in range(warmup):
+            O.sgld_transition(st, fixed, moving)
+        sync()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            O.sgld_transition(st, fixed, moving)
+        sync()
+        dt = time.perf_counter() - t0
+    finally:
+        torch.set_default_device('cpu')
+    return n ** 3 * steps / dt, 1e3 * dt / max(steps, 1)
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU implementation of the path = the oracle port (the reference is Python on
     PyTorch; /root/reference does not travel to the GPU box), all host threads, rank 0 only."""
@@ -145,6 +182,8 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-graph', action='store_true')
     ap.add_argument('--e2e-steps', type=int, default=0, help='default: min(steps, 50)')
+    ap.add_argument('--aten-gpu-baseline', action='store_true', help='also time the oracle port of the reference with all '
+                    'tensors on the GPU (ATen kernels): the GPU-vs-GPU comparison of SURVEY section 8(d); opt-in')
     ap.add_argument('--cps', type=int, default=0, help='secondary configuration: SVFFD_3D with this control point '
                     'spacing as the transformation model (reference configs/experiment5); 0 = SVF_3D, the headline')
     args = ap.parse_args()
@@ -303,6 +342,15 @@ def main():
                'sample': f'2 oracle transitions (oracle/sgld_oracle.py, torch CPU fp32, {threads} threads) at {n_cpu}^3, '
                          f'1 chain, {ms_cpu:.0f} ms each'}
 
+    aten_gpu = None
+    if rank == 0 and args.aten_gpu_baseline:
+        try:
+            v_gpu, ms_gpu = aten_gpu_transition_rate(n if n <= 128 else 128, 3, 1, args.data, args.cps, device=str(dev))
+            aten_gpu = {'value': v_gpu, 'unit': 'voxel-steps/s', 'ms_per_step': ms_gpu, 'kind': 'port on the GPU (ATen)',
+                        'sample': '3 timed + 1 warm-up oracle transitions, 1 chain, fp32, wall clock around synchronize'}
+        except Exception as exc:   # a baseline must not cost the bench line
+            aten_gpu = {'unavailable': f'{type(exc).__name__}: {exc}'[:300]}
+
     if rank == 0:
         line = {'metric': 'SGLD voxel-steps/s', 'value': value, 'unit': 'voxel-steps/s', 'n_gpus': world,
                 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_max / args.steps,
@@ -320,6 +368,8 @@ def main():
                                   'frac': step_gbs / peak},
                 'stage_ms': {k: round(v, 4) for k, v in stage_ms.items()},
                 'moments_merge_ms': merge_ms, 'graph': use_graph, 'clocks': clock_info, 'cpu_baseline': cpu}
+        if aten_gpu is not None:
+            line['aten_gpu_baseline'] = aten_gpu
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
