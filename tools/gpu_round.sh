@@ -19,3 +19,9 @@ ncu --set full --clock-control none --import-source on -k "regex:langevin|smooth
 fi
 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke exit $?" >> gpurun_out/smoke.log; tail -2 gpurun_out/smoke.log
 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.log 2>&1; tail -1 gpurun_out/bench_ref.log | cut -c1-300
+# secondary configuration (SVFFD_3D, spacing 4), the GPU-vs-GPU baseline, and the FFD kernels' metrics
+python bench.py --cps 4 --steps 100 --warmup 5 --e2e-steps 20 --no-cpu-baseline > gpurun_out/bench_svffd4.log 2>&1; tail -1 gpurun_out/bench_svffd4.log | cut -c1-300
+python bench.py --steps 50 --warmup 5 --no-cpu-baseline --aten-gpu-baseline > gpurun_out/bench_aten_gpu.log 2>&1; tail -1 gpurun_out/bench_aten_gpu.log | grep -o '"aten_gpu_baseline".*' | cut -c1-400
+if [ "$1" != "noprof" ]; then
+bash tools/gpu_ffd_ncu.sh
+fi
