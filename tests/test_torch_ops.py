@@ -135,7 +135,7 @@ def test_gpu_svf_and_smoothing_ops_match_the_modules(pkg):
     x = torch.randn(C, 3, n, n, n, device=DEV, requires_grad=True)
     y = torch.ops.irsgmcmc.sobolev_smooth(x, taps)
     (y * G).sum().backward()
-    assert rel(y, O.sobolev_smooth(x.detach().cpu(), O.sobolev_taps(3, 0.5).astype('float32'))) < 1e-6
+    assert rel(y, O.sobolev_smooth(x.detach().cpu(), O.sobolev_taps(3, 0.5).astype("float32"))) < 1e-5
     assert torch.equal(x.grad, G)     # SobolevGrad.backward is the identity (reference utils/functions.py:107-109)
 
 
@@ -151,7 +151,7 @@ def test_gpu_lcc_energy_and_ffd_ops_match_the_launchers(pkg):
     (zn * G).sum().backward()
     zn_r, a_r, rs_r = ops.lcc_normalise(im, 2)
     assert torch.equal(zn, zn_r) and torch.equal(x.grad, ops.lcc_normalise_bwd(G, a_r, rs_r, 2))
-    assert rel(zn, O.lcc_normalise(im.cpu(), 2)) < 1e-5
+    assert rel(zn, O.lcc_normalise(im.cpu(), 2)) < 1e-4   # wiring check; parity proper is tests/test_gpu_ops.py
     v = torch.randn(C, 3, n, n, n, device=DEV, generator=gen).requires_grad_(True)
     e = torch.ops.irsgmcmc.reg_energy(v)
     w = torch.tensor([0.5, -2.0], device=DEV, dtype=torch.float64)
