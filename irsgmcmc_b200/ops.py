@@ -149,6 +149,8 @@ def bspline_axis(x, kernel, dim, stride, adjoint=False, crop_start=0, out_len=No
     for n in x.shape[dim + 1:]:
         inner *= int(n)
     if adjoint:
+        if out_len is None:
+            raise ValueError('bspline_axis(adjoint=True) needs out_len = the number of control points along the axis')
         n, g = int(x.shape[dim]), int(out_len)
     else:
         g = int(x.shape[dim])

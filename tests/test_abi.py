@@ -51,6 +51,24 @@ def test_argument_validation_without_gpu(built):
     # 12 global maxima + 12 cell maps of 2 chains x (1 x 1 x 1) cells of 32 x 8 x 8 voxels
     assert lib.irs_svf_maxabs_floats(2, 4, 5, 6, 12) == 12 * (1 + 2 * 1)
     assert lib.irs_svf_maxabs_floats(1, 128, 128, 128, 12) == 12 * (1 + 4 * 16 * 16)
+    # cubic B-spline FFD: workspace = the two intermediates of the axis passes; null pointers / spacings out of range
+    assert lib.irs_ffd_work_floats(2, 35, 35, 35, 128, 128, 128) == 2 * 3 * (128 * 35 * 35 + 128 * 128 * 35)
+    assert lib.irs_ffd_work_floats(0, 35, 35, 35, 128, 128, 128) == 0
+    k = _lib.host_floats([0.0] * 35)
+    assert lib.irs_ffd_fwd(None, k, k, k, 4, 4, 4, None, None, 1, 7, 7, 7, 16, 16, 16, None) == -1
+    assert lib.irs_ffd_bwd(None, k, k, k, 4, 4, 4, None, None, 1, 7, 7, 7, 16, 16, 16, None) == -1
+    assert lib.irs_bspline_axis(None, None, 0, 6, 7, 16, 49, k, 4, 4, None) == -1
+    cfg = _lib.SgldConfig()
+    cfg.C, cfg.D, cfg.H, cfg.W, cfg.K, cfg.lcc_s, cfg.svf_steps, cfg.n_mask = 1, 16, 16, 16, 4, 2, 12, 100.0
+    assert lib.irs_sgld_launches_per_step(ctypes.byref(cfg)) > 0
+    plain = lib.irs_sgld_launches_per_step(ctypes.byref(cfg))
+    for a in range(3):
+        cfg.ffd_cps[a], cfg.ffd_grid[a] = 4, 7
+    assert lib.irs_sgld_launches_per_step(ctypes.byref(cfg)) == plain + 7   # 6 FFD passes + the stand-alone energy kernel
+    cfg.ffd_grid[1] = 5   # (5 - 1) * 4 + 1 = 17 elements cannot hold the crop [4, 20)
+    assert lib.irs_sgld_launches_per_step(ctypes.byref(cfg)) == -1
+    cfg.ffd_grid[1], cfg.ffd_cps[2] = 7, 9
+    assert lib.irs_sgld_launches_per_step(ctypes.byref(cfg)) == -1
 
 
 def test_config_struct_layout_matches_c(built):
