@@ -115,6 +115,28 @@ def test_device_arithmetic_groups_crossing_rows(built, n, cps, C):
     assert rel(dense, ref) < 1e-6 and rel(g_cp, g64) < 1e-6
 
 
+def test_device_arithmetic_random_shapes(built):
+    """seeded sweep over volume sizes, spacings 1..8 per axis and chain counts: forward against the oracle, and the
+    adjoint identity <A x, y> = <x, A^T y> between the two directions of the device arithmetic"""
+    emul = ctypes.CDLL(built['emul'])
+    rng = np.random.default_rng(2024)
+    for _ in range(16):
+        n = int(rng.integers(4, 23))
+        cps = tuple(int(c) for c in rng.integers(1, 9, size=3))
+        C = int(rng.integers(1, 4))
+        dims = (n,) * 3
+        grid = O.control_grid_size(dims, cps)
+        ks = [np.ascontiguousarray(O.bspline_taps(s).numpy()) for s in cps]
+        x = rng.standard_normal((C, 3, *grid)).astype(np.float32)
+        y = rng.standard_normal((C, 3, *dims)).astype(np.float32)
+        Ax, Aty = np.zeros_like(y), np.zeros_like(x)
+        emul.emul_ffd(P(x), P(Ax), 0, P(ks[0]), P(ks[1]), P(ks[2]), *cps, C, *grid, *dims)
+        emul.emul_ffd(P(y), P(Aty), 1, P(ks[0]), P(ks[1]), P(ks[2]), *cps, C, *grid, *dims)
+        assert rel(Ax, O.ffd_dense(torch.from_numpy(x).double(), dims, cps)) < 1e-6, (n, cps, C)
+        lhs, rhs = float((Ax.astype(np.float64) * y).sum()), float((x.astype(np.float64) * Aty).sum())
+        assert abs(lhs - rhs) <= 1e-5 * float(np.linalg.norm(Ax.astype(np.float64))) + 1e-9, (n, cps, C)
+
+
 def test_oracle_conv1d_axis(gold):
     for tag in 'ab':
         _, cps, _ = case(gold, tag)
