@@ -147,6 +147,8 @@ def run_reference(args):
     budget_s = 150.0
     est = (ms64 / 1e3) * (n / 64.0) ** 3 * (args.steps + args.warmup)
     n_run = n if est <= budget_s else 64
+    if n_run == 64 and n > 32 and (ms64 / 1e3) * (args.steps + args.warmup) > budget_s:
+        n_run = 32   # many steps on few cores: a still smaller sample of the same workload
     value, ms, threads = oracle_transition_rate(n_run, args.steps, args.warmup, 1, args.data, args.cps)
     sample = f'{args.steps} timed + {args.warmup} warm-up oracle transitions at {n_run}^3, 1 chain, fp32, {threads} threads'
     line = {'impl': 'reference', 'metric': 'SGLD voxel-steps/s', 'value': value, 'unit': 'voxel-steps/s',
