@@ -142,17 +142,21 @@ def run_reference(args):
     if int(os.environ.get('RANK', '0')) != 0:
         return
     n = args.size
-    # bounded sample: keep (steps + warmup) transitions within a few minutes; voxel-steps/s is volume-normalised
-    rate64, ms64, threads = oracle_transition_rate(64, 1, 1, 1, args.data, args.cps)
-    budget_s = 150.0
-    est = (ms64 / 1e3) * (n / 64.0) ** 3 * (args.steps + args.warmup)
-    n_run = n if est <= budget_s else 64
-    if n_run == 64 and n > 32 and (ms64 / 1e3) * (args.steps + args.warmup) > budget_s:
-        n_run = 32   # many steps on few cores: a still smaller sample of the same workload
-    value, ms, threads = oracle_transition_rate(n_run, args.steps, args.warmup, 1, args.data, args.cps)
-    sample = f'{args.steps} timed + {args.warmup} warm-up oracle transitions at {n_run}^3, 1 chain, fp32, {threads} threads'
+    # Bounded sample WITHOUT changing the workload: the volume stays the requested one (a smaller volume is another
+    # workload: the driver's ratio must be like for like).  When K + W transitions of the CPU port would not finish within the
+    # budget, fewer are timed -- each transition is the same deterministic amount of work, so voxel-steps/s does not depend on
+    # the count -- and the line says so (`steps_timed`, `sample`).
+    budget_s = float(os.environ.get('IRS_REF_BUDGET_S', '150'))
+    probe_value, probe_ms, threads = oracle_transition_rate(n, 1, 0, 1, args.data, args.cps)   # one untimed-region warm-up
+    steps_run = int(max(1, min(args.steps, (budget_s - probe_ms / 1e3) // (probe_ms / 1e3) - min(args.warmup, 1))))
+    warm_run = min(args.warmup, 1) if steps_run < args.steps else args.warmup
+    n_run = n
+    value, ms, threads = oracle_transition_rate(n_run, steps_run, warm_run, 1, args.data, args.cps)
+    sample = (f'{steps_run} timed + {warm_run} warm-up oracle transitions at {n_run}^3, 1 chain, fp32, {threads} threads'
+              + ('' if steps_run == args.steps else f' (of the {args.steps} + {args.warmup} asked: time bound {budget_s:.0f} s; '
+                                                    f'same volume, fewer repetitions)'))
     line = {'impl': 'reference', 'metric': 'SGLD voxel-steps/s', 'value': value, 'unit': 'voxel-steps/s',
-            'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms,
+            'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'steps_timed': steps_run, 'ms_per_step': ms,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
             'config': workload_config(args, 1, n_run),
             'cpu_baseline': {'value': value, 'unit': 'voxel-steps/s', 'cores': threads, 'kind': 'port', 'sample': sample},

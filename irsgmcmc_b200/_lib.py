@@ -21,6 +21,7 @@ MAX_K = 8
 HYPER_GMM_STEP, HYPER_LOG_STD, HYPER_LOGITS = 0, 1, 9
 HYPER_M_LOG_STD, HYPER_V_LOG_STD, HYPER_M_LOGITS, HYPER_V_LOGITS = 17, 25, 33, 41
 HYPER_REG_STEP, HYPER_REG_P, HYPER_REG_M, HYPER_REG_V, HYPER_ITER = 49, 50, 52, 54, 56
+HYPER_GMM_BETA_POW, HYPER_REG_BETA_POW = 57, 59
 STAT_ALPHA, STAT_DATA, STAT_REG, STAT_ENERGY, STAT_NLL_PRE, STAT_REG_COEF = 0, 1, 2, 3, 4, 5
 
 DATA_LCC, DATA_SSD = 0, 1

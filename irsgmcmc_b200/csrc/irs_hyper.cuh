@@ -52,13 +52,16 @@ IRS_HD void irs_gmm_table(const double* log_std, const double* logits, int K, Ir
     }
 }
 
-// reference utils/util.py:446-485.  NaN when a lag-1 correlation is <= 0, like the reference.
+// reference utils/util.py:446-485.  NaN when a lag-1 correlation is negative, like the reference: torch.clamp(max=1)
+// propagates NaN, whereas fminf(1, NaN) returns 1 (IEEE minNum) -- hence the explicit select.  A correlation of exactly 0
+// gives -log(0) = +inf -> clamped to 1, in both.
 IRS_HD double irs_vd_alpha(const double* sums, double n_mask) {
     const double var = sums[IRS_SUM_RR] / n_mask;
     float prod = 1.f;
     for (int a = 0; a < 3; ++a) {
         const float corr = (float)((sums[IRS_SUM_RD + a] / n_mask) / var);
-        prod *= fminf(1.f, -0.63661977236758134f * logf(corr));
+        const float t = -0.63661977236758134f * logf(corr);
+        prod *= (t != t) ? t : fminf(1.f, t);
     }
     return (double)sqrtf(prod);
 }

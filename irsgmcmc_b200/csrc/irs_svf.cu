@@ -20,6 +20,7 @@
 //                              unit cannot address (W % 4 != 0), and steps with 1 <= max|u| < 2 inside the TMA kernels
 //   irs_body_svf_fwd / irs_body_svf_bwd, svf_step_bwd_scatter_kernel   global gathers / atomic scatter for larger radii
 #include <cstdlib>
+#include <mutex>
 #include <type_traits>
 
 #include "irs_kernels.cuh"
@@ -1295,6 +1296,24 @@ svf_outputs_kernel(const float* __restrict__ u_all, const float* __restrict__ li
     }
 }
 
+// Launch configuration that depends on the device: the opt-in shared-memory size is a per-device function attribute and
+// the resident-CTA counts come from that device's occupancy calculator.  A process that drives several GPUs (one sampler per
+// device) must not reuse the first device's state, so everything is cached PER DEVICE behind a mutex.
+struct SvfDeviceState {
+    bool fwd_tma_ready = false, bwd_tile_ready = false, bwd_tma_ready = false, bwd_tma2_ready = false;
+    int fwd_ctas = 0;
+    int slots_fwd_tma = 0, slots_fwd_tile = 0, slots_bwd_tile = 0, slots_bwd_tma = 0;
+    int two = -1;
+};
+constexpr int kMaxDevices = 64;
+SvfDeviceState g_svf_dev[kMaxDevices];
+std::mutex g_svf_mu;
+inline SvfDeviceState& svf_device_state() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return g_svf_dev[(dev % kMaxDevices + kMaxDevices) % kMaxDevices];
+}
+
 template <typename K>
 static int resident_ctas(K kernel, size_t smem) {
     int per_sm = 0, sms = 148, dev = 0;
@@ -1336,20 +1355,29 @@ int irs_launch_svf_fwd(const float* v, float* hist, float* maxabs, int n_steps, 
     if (tma) {
         const size_t smem = zmax(svf_fwd_tma_smem(), svf_fwd_tile_smem_compact(RF));
         using Kern = void (*)(CUtensorMap, const float*, float, float*, const float*, float*, int, IrsDims, IrsEnergyOut);
-        static Kern kern = nullptr, kern_e = nullptr;
-        static int slots = 0;
-        if (kern == nullptr) {
-            int ctas = 5;   // measured at 128^3: 4 -> 0.212 ms, 5 -> 0.200 ms, 6 -> 0.208 ms for the 12 forward steps
-            if (const char* ev = getenv("IRS_FWD_CTAS")) ctas = atoi(ev);   // development override
+        Kern kern = nullptr, kern_e = nullptr;
+        int slots = 0;
+        {
+            std::lock_guard<std::mutex> lock(g_svf_mu);
+            SvfDeviceState& ds = svf_device_state();
+            if (ds.fwd_ctas == 0) {
+                ds.fwd_ctas = 5;   // measured at 128^3: 4 -> 0.212 ms, 5 -> 0.200 ms, 6 -> 0.208 ms for the 12 forward steps
+                if (const char* ev = getenv("IRS_FWD_CTAS")) ds.fwd_ctas = atoi(ev);   // development override
+            }
+            const int ctas = ds.fwd_ctas;
             kern = ctas <= 4 ? (Kern)svf_step_fwd_tma_kernel<4, false>
                              : (ctas == 5 ? (Kern)svf_step_fwd_tma_kernel<5, false> : (Kern)svf_step_fwd_tma_kernel<6, false>);
             kern_e = ctas <= 4 ? (Kern)svf_step_fwd_tma_kernel<4, true>
                                : (ctas == 5 ? (Kern)svf_step_fwd_tma_kernel<5, true> : (Kern)svf_step_fwd_tma_kernel<6, true>);
-            e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) return (int)e;
-            e = cudaFuncSetAttribute(kern_e, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) return (int)e;
-            slots = resident_ctas(kern, smem);
+            if (!ds.fwd_tma_ready) {
+                e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                if (e != cudaSuccess) return (int)e;
+                e = cudaFuncSetAttribute(kern_e, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                if (e != cudaSuccess) return (int)e;
+                ds.slots_fwd_tma = resident_ctas(kern, smem);
+                ds.fwd_tma_ready = true;
+            }
+            slots = ds.slots_fwd_tma;
         }
         const int seg_len = svf_seg_len(d, C, slots, 3, "IRS_SVF_SEG_FWD", true);
         dim3 tgrid(tiles * ((d.D + seg_len - 1) / seg_len), C);
@@ -1371,8 +1399,18 @@ int irs_launch_svf_fwd(const float* v, float* hist, float* maxabs, int n_steps, 
         if (with_energy && energy_done) *energy_done = 1;
         return (int)cudaGetLastError();
     }
-    static int slots = 0;
-    if (slots == 0) slots = resident_ctas(svf_step_fwd_tile_kernel<RF>, svf_fwd_tile_smem(RF));
+    int slots = 0;
+    {
+        std::lock_guard<std::mutex> lock(g_svf_mu);
+        SvfDeviceState& ds = svf_device_state();
+        if (ds.slots_fwd_tile == 0) {
+            e = cudaFuncSetAttribute(svf_step_fwd_tile_kernel<RF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)svf_fwd_tile_smem(RF));
+            if (e != cudaSuccess) return (int)e;
+            ds.slots_fwd_tile = resident_ctas(svf_step_fwd_tile_kernel<RF>, svf_fwd_tile_smem(RF));
+        }
+        slots = ds.slots_fwd_tile;
+    }
     const int seg_len = svf_seg_len(d, C, slots, 2 * RF + 2);
     dim3 tgrid(tiles * ((d.D + seg_len - 1) / seg_len), C);
     for (int k = 0; k < n_steps; ++k) {
@@ -1390,38 +1428,43 @@ int irs_launch_svf_bwd(const float* v, const float* hist, const float* maxabs, f
                        int n_steps, int gather_radius_max, int C, IrsDims d, cudaStream_t st) {
     const size_t F = (size_t)C * 3 * d.V();
     const float scale0 = 1.0f / (float)(1 << n_steps);
-    static bool configured = false;
     const size_t smem = svf_bwd_tile_smem(2);
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(svf_step_bwd_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-        configured = true;
-    }
     const int tiles = ((d.W + TILE_X - 1) / TILE_X) * ((d.H + TILE_Y - 1) / TILE_Y);
     const long long vblocks = (d.V() + 255) / 256;
     dim3 vgrid((unsigned)(vblocks < 1184 ? vblocks : 1184), 1);   // persistent: see svf_step_bwd_scatter_kernel
     const bool tma = irs_tma_field_ok(v, d.W) && irs_tma_field_ok(hist, d.W) && irs_tma_field_ok(g_u, d.W) &&
                      irs_tma_field_ok(g_work, d.W) && (F % 4) == 0;
     const size_t smem_tma = zmax(svf_bwd_tma_smem(), smem);
-    static bool configured_tma = false;
-    if (tma && !configured_tma) {
-        cudaError_t e = cudaFuncSetAttribute(svf_step_bwd_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tma);
-        if (e != cudaSuccess) return (int)e;
-        configured_tma = true;
-    }
-    static int slots = 0, slots_tma = 0, two = -1;
-    if (slots == 0) slots = resident_ctas(svf_step_bwd_tile_kernel, smem);
     const size_t smem_tma2 = zmax(svf_bwd_tma2_smem(), smem);
-    if (two < 0) {   // two targets per thread (32 x 16 tiles) unless IRS_BWD_NT=1 (development switch)
-        two = (getenv("IRS_BWD_NT") && atoi(getenv("IRS_BWD_NT")) == 1) ? 0 : 1;
-        if (two) {
+    int slots = 0, slots_tma = 0, two = 1;
+    {
+        std::lock_guard<std::mutex> lock(g_svf_mu);
+        SvfDeviceState& ds = svf_device_state();
+        if (!ds.bwd_tile_ready) {
+            cudaError_t e = cudaFuncSetAttribute(svf_step_bwd_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return (int)e;
+            ds.slots_bwd_tile = resident_ctas(svf_step_bwd_tile_kernel, smem);
+            ds.bwd_tile_ready = true;
+        }
+        if (ds.two < 0)   // two targets per thread (32 x 16 tiles) unless IRS_BWD_NT=1 (development switch)
+            ds.two = (getenv("IRS_BWD_NT") && atoi(getenv("IRS_BWD_NT")) == 1) ? 0 : 1;
+        two = ds.two;
+        if (tma && two == 1 && !ds.bwd_tma2_ready) {
             cudaError_t e = cudaFuncSetAttribute(svf_step_bwd_tma2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tma2);
             if (e != cudaSuccess) return (int)e;
+            ds.slots_bwd_tma = resident_ctas(svf_step_bwd_tma2_kernel, smem_tma2);
+            ds.bwd_tma2_ready = true;
         }
+        if (tma && two == 0 && !ds.bwd_tma_ready) {
+            cudaError_t e = cudaFuncSetAttribute(svf_step_bwd_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tma);
+            if (e != cudaSuccess) return (int)e;
+            ds.slots_bwd_tma = resident_ctas(svf_step_bwd_tma_kernel, smem_tma);
+            ds.bwd_tma_ready = true;
+        }
+        slots = ds.slots_bwd_tile;
+        slots_tma = ds.slots_bwd_tma;
     }
     const bool tma2 = tma && two == 1;
-    if (tma && slots_tma == 0)
-        slots_tma = tma2 ? resident_ctas(svf_step_bwd_tma2_kernel, smem_tma2) : resident_ctas(svf_step_bwd_tma_kernel, smem_tma);
     const int seg_len = tma ? svf_seg_len(d, C, slots_tma, 4, "IRS_SVF_SEG_BWD", true, tma2 ? B2_TY : TILE_Y) : svf_seg_len(d, C, slots, 6);
     const int nseg = (d.D + seg_len - 1) / seg_len;
     const int tiles2 = ((d.W + TILE_X - 1) / TILE_X) * ((d.H + B2_TY - 1) / B2_TY);

@@ -219,26 +219,19 @@ class SGLDSampler:
     # initialisation (reference trainer/trainer.py:529-547, 585-611)
     # ------------------------------------------------------------------------------------------------------------------
     @torch.no_grad()
-    def init_chains(self, MCMC_init='VI', var_params_q_v=None, generator=None):
-        """Trainer.__SGLD_init: 'VI' draws v_c = mu + eps_c sigma + x_c u and uses sigma = exp(log_var / 2) as the
-        preconditioner; 'identity' / 'noise' start from 0 / N(0,1) with sigma = 1"""
-        dev = self.device
-        if MCMC_init == 'VI':
-            mu, log_var, u = (var_params_q_v[k].to(dev, torch.float32) for k in ('mu', 'log_var', 'u'))
-            sigma = torch.exp(0.5 * log_var)
-            for c in range(self.C):  # utils/sampler.py:4-21, one draw per chain
-                eps = torch.randn(sigma.shape, device=dev, generator=generator)
-                x = torch.randn(1, device=dev, generator=generator)
-                self.v[c] = (mu + eps * sigma + x * u)[0]
-            self.sigma = sigma.contiguous()
-        elif MCMC_init == 'identity':
-            self.v.zero_()
-            self.sigma = None
-        elif MCMC_init == 'noise':
-            self.v.copy_(torch.randn(self.v.shape, device=dev, generator=generator))
-            self.sigma = None
-        else:
-            raise ValueError(f'unknown MCMC_init: {MCMC_init}')
+    def init_chains(self, MCMC_init='VI', var_params_q_v=None, generator=None, no_chains_total=None):
+        """Trainer.__SGLD_init (reference trainer/trainer.py:585-611): 'VI' draws v_c = mu + eps_c sigma + x_c u (one
+        sample_q_v call per chain, utils/sampler.py:4-21) and uses sigma = exp(log_var / 2) as the preconditioner;
+        'identity' / 'noise' start from 0 / N(0,1) with sigma = 1.
+
+        The draws follow the reference's order over GLOBAL chain ids: this shard (chains chain_offset .. chain_offset + C of
+        no_chains_total) skips the numbers of the chains before it, so identically seeded ranks start every chain exactly
+        where a single-GPU run with all chains would -- and no two shards start from the same states."""
+        from .utils.sampler import draw_chain_states
+        v, sigma = draw_chain_states(MCMC_init, var_params_q_v, self.C, self.chain_offset, no_chains_total, generator,
+                                     state_shape=tuple(self.v.shape[1:]), device=self.device)
+        self.v.copy_(v)
+        self.sigma = sigma
         self._invalidate()
 
     @torch.no_grad()

@@ -80,6 +80,10 @@ class Trainer:
         self.structures_dict = structures_dict or {}
         self.logger = logger
 
+        world = torch.distributed.get_world_size() if torch.distributed.is_available() and torch.distributed.is_initialized() else 1
+        if self.no_chains_total < world:   # every rank sees the same numbers: all of them raise, nobody hangs in a collective
+            raise ValueError(f'no_chains = {self.no_chains_total} is smaller than the number of ranks ({world}): '
+                             f'every rank needs at least one chain')
         offset, count = parallel.chain_shard(self.no_chains_total)
         if chain_offset is not None:
             offset = chain_offset
@@ -108,35 +112,94 @@ class Trainer:
 
     def _SGLD_init(self, var_params_q_v=None, generator=None):
         var_params_q_v = var_params_q_v or self.var_params_q_v
-        self.sampler.init_chains(self.MCMC_init, var_params_q_v, generator=generator)
+        self.sampler.init_chains(self.MCMC_init, var_params_q_v, generator=generator, no_chains_total=self.no_chains_total)
         self.SGLD_params = {'sigma': self.sampler.sigma, 'tau': self.sampler.cfg.tau}
         self.v_curr_state = self.sampler.v
 
     # -- parameter mirroring between the drop-in modules and the device-side hyper state -----------------------------
-    def _push_hyper(self, data_loss, reg_loss):
+    # The reference creates optimizer_GMM / optimizer_reg ONCE (trainer.py:62-66) and they persist through __GMM_init
+    # (25 steps), VI (two mixture steps per iteration) and MCMC: MCMC starts with the decayed rate lr / (1 + step lr_decay),
+    # warm moments and bias corrections counted from step 0.  The device keeps the same state in `hyper`
+    # (csrc/irs_hyper.cuh), so parameters AND optimiser state travel in both directions.
+    def _reg_params(self, reg_loss):
+        if hasattr(reg_loss, 'loc'):
+            return [reg_loss.loc, reg_loss.log_scale]
+        return [reg_loss.log_w_reg]
+
+    def _push_adam(self, optimizer, params, step_slot, m_slots, v_slots, beta_slot):
+        h = self.sampler.hyper
+        betas = optimizer.param_groups[0]['betas']
+        step = t = 0
+        for p, ms, vs in zip(params, m_slots, v_slots):
+            st = optimizer.state.get(p, {})
+            k = p.numel()
+            if len(st) == 0:
+                h[ms:ms + k] = 0.0
+                h[vs:vs + k] = 0.0
+                continue
+            step, t = int(st['step']), int(st['step']) - int(st.get('reinit', 0))
+            h[ms:ms + k] = st['exp_avg'].detach().double().reshape(-1).to(h.device)
+            h[vs:vs + k] = st['exp_avg_sq'].detach().double().reshape(-1).to(h.device)
+        h[step_slot] = float(step)
+        h[beta_slot] = betas[0] ** t       # the device multiplies these running products by beta once per step
+        h[beta_slot + 1] = betas[1] ** t
+
+    def _pull_adam(self, optimizer, params, step_slot, m_slots, v_slots):
+        h = self.sampler.hyper.cpu()
+        step = int(round(float(h[step_slot])))
+        for p, ms, vs in zip(params, m_slots, v_slots):
+            k = p.numel()
+            st = optimizer.state[p]
+            st['step'] = step
+            st.setdefault('reinit', 0)
+            st['exp_avg'] = h[ms:ms + k].to(p.dtype).view_as(p).to(p.device)
+            st['exp_avg_sq'] = h[vs:vs + k].to(p.dtype).view_as(p).to(p.device)
+
+    def _push_hyper(self, data_loss, reg_loss, optimizer_GMM=None, optimizer_reg=None):
+        from .. import _lib as L
         s, K = self.sampler, self.sampler.cfg.no_components
+        optimizer_GMM = optimizer_GMM if optimizer_GMM is not None else getattr(self, 'optimizer_GMM', None)
+        optimizer_reg = optimizer_reg if optimizer_reg is not None else getattr(self, 'optimizer_reg', None)
         if data_loss is not None:
-            s.hyper[1:1 + K] = data_loss.log_std.detach().double().to(s.device)
-            s.hyper[9:9 + K] = data_loss.logits.detach().double().to(s.device)
+            s.hyper[L.HYPER_LOG_STD:L.HYPER_LOG_STD + K] = data_loss.log_std.detach().double().to(s.device)
+            s.hyper[L.HYPER_LOGITS:L.HYPER_LOGITS + K] = data_loss.logits.detach().double().to(s.device)
+            if optimizer_GMM is not None:
+                self._push_adam(optimizer_GMM, [data_loss.log_std, data_loss.logits], L.HYPER_GMM_STEP,
+                                [L.HYPER_M_LOG_STD, L.HYPER_M_LOGITS], [L.HYPER_V_LOG_STD, L.HYPER_V_LOGITS],
+                                L.HYPER_GMM_BETA_POW)
         if reg_loss is not None:
-            if hasattr(reg_loss, 'loc'):
-                s.hyper[50] = reg_loss.loc.detach().double()
-                s.hyper[51] = reg_loss.log_scale.detach().double()
-            else:
-                s.hyper[50] = reg_loss.log_w_reg.detach().double()
+            params = self._reg_params(reg_loss)
+            for i, p in enumerate(params):
+                s.hyper[L.HYPER_REG_P + i] = p.detach().double()
+            if optimizer_reg is not None and getattr(reg_loss, 'learnable', False):
+                self._push_adam(optimizer_reg, params, L.HYPER_REG_STEP, [L.HYPER_REG_M + i for i in range(len(params))],
+                                [L.HYPER_REG_V + i for i in range(len(params))], L.HYPER_REG_BETA_POW)
 
     @torch.no_grad()
-    def _pull_hyper(self, data_loss, reg_loss):
+    def _pull_hyper(self, data_loss, reg_loss, optimizer_GMM=None, optimizer_reg=None, with_optimizers=True):
+        """device state -> modules.  with_optimizers=False copies the parameters only (device-to-device, no host
+        synchronisation: what _SGLD_transition does after every step); the optimiser state needs the step counters on the
+        host and is mirrored at the end of _run_MCMC / on request"""
+        from .. import _lib as L
         s, K = self.sampler, self.sampler.cfg.no_components
+        if with_optimizers:
+            optimizer_GMM = optimizer_GMM if optimizer_GMM is not None else getattr(self, 'optimizer_GMM', None)
+            optimizer_reg = optimizer_reg if optimizer_reg is not None else getattr(self, 'optimizer_reg', None)
+        else:
+            optimizer_GMM = optimizer_reg = None
         if data_loss is not None:
-            data_loss.log_std.copy_(s.hyper[1:1 + K].to(data_loss.log_std.dtype))
-            data_loss.logits.copy_(s.hyper[9:9 + K].to(data_loss.logits.dtype))
+            data_loss.log_std.copy_(s.hyper[L.HYPER_LOG_STD:L.HYPER_LOG_STD + K].to(data_loss.log_std.dtype))
+            data_loss.logits.copy_(s.hyper[L.HYPER_LOGITS:L.HYPER_LOGITS + K].to(data_loss.logits.dtype))
+            if optimizer_GMM is not None:
+                self._pull_adam(optimizer_GMM, [data_loss.log_std, data_loss.logits], L.HYPER_GMM_STEP,
+                                [L.HYPER_M_LOG_STD, L.HYPER_M_LOGITS], [L.HYPER_V_LOG_STD, L.HYPER_V_LOGITS])
         if reg_loss is not None:
-            if hasattr(reg_loss, 'loc'):
-                reg_loss.loc.copy_(s.hyper[50].to(reg_loss.loc.dtype))
-                reg_loss.log_scale.copy_(s.hyper[51].to(reg_loss.log_scale.dtype))
-            else:
-                reg_loss.log_w_reg.copy_(s.hyper[50].to(reg_loss.log_w_reg.dtype))
+            params = self._reg_params(reg_loss)
+            for i, p in enumerate(params):
+                p.copy_(s.hyper[L.HYPER_REG_P + i].to(p.dtype))
+            if optimizer_reg is not None and getattr(reg_loss, 'learnable', False):
+                self._pull_adam(optimizer_reg, params, L.HYPER_REG_STEP, [L.HYPER_REG_M + i for i in range(len(params))],
+                                [L.HYPER_REG_V + i for i in range(len(params))])
 
     # -- VI warm start (reference trainer.py:79-223), on the drop-in modules through autograd ------------------------
     def _build_VI_modules(self):
@@ -277,7 +340,29 @@ class Trainer:
                             'loss': loss.detach(), 'alpha': aux['alpha']})
         self.var_params_q_v = {k: v.detach() for k, v in vp.items()}
         self._vi_modules = m
+        # one optimiser per hyper-parameter group for the whole run (reference trainer.py:62-66): MCMC continues with them
+        self.optimizer_GMM, self.optimizer_reg = m['optimizer_GMM'], m.get('optimizer_reg')
+        self._gmm_pushed = False   # the next transition pushes the parameters AND the optimiser state VI left behind
         return self.var_params_q_v, m, history
+
+    def _run_model(self, VI=None, MCMC=None, speed_test_iters=0):
+        """the reference's Trainer._run_model (trainer.py:478-504): mixture initialisation (25 Adam steps), VI warm start,
+        then SGLD -- with the mixture / regulariser parameters and their Adam state handed from stage to stage"""
+        tr = self.config['trainer']
+        VI = bool(tr.get('VI', False)) if VI is None else VI
+        MCMC = bool(tr.get('MCMC', True)) if MCMC is None else MCMC
+        self._GMM_init()
+        m = self._build_VI_modules()
+        self._pull_hyper(m['data_loss'], m['reg_loss'], m['optimizer_GMM'], m.get('optimizer_reg'))
+        self.optimizer_GMM, self.optimizer_reg = m['optimizer_GMM'], m.get('optimizer_reg')
+        result = {'modules': m}
+        if VI:
+            result['var_params_q_v'], _, result['VI_history'] = self._run_VI(modules=m)
+        if MCMC:
+            self._SGLD_init()
+            self._gmm_pushed = False
+            result.update(self._run_MCMC(m['data_loss'], m['reg_loss'], speed_test_iters=speed_test_iters))
+        return result
 
     # -- the hot path -------------------------------------------------------------------------------------------------
     def _SGLD_transition(self, fixed=None, moving=None, data_loss=None, reg_loss=None):
@@ -296,7 +381,7 @@ class Trainer:
             self._gmm_pushed = True
         s.step(1)
         if data_loss is not None or reg_loss is not None:
-            self._pull_hyper(data_loss, reg_loss)
+            self._pull_hyper(data_loss, reg_loss, with_optimizers=False)
         st = s.stats
         C = self.no_chains
         loss_terms = {'data': [st[c, 1].float() for c in range(C)], 'reg': [st[c, 2].float() for c in range(C)]}
@@ -345,9 +430,12 @@ class Trainer:
                     dsc.append(calc_DSC_GPU(self.no_chains, seg_f, seg_w, self.structures_dict))
                 n_folded, _ = calc_no_non_diffeomorphic_voxels(T, diff_op)
                 folded.append(n_folded)
-                if (n_folded > 0.001 * self.no_voxels).any():  # reference trainer.py:441-445 (exits the process there)
+                bad = bool((n_folded > 0.001 * self.no_voxels).any())
+                if parallel.any_rank(bad, s.device):   # reference trainer.py:441-445 (exits the process there)
+                    # the flag is all-reduced first: every rank leaves together instead of one raising while the others
+                    # wait for it in the moments merge
                     raise RuntimeError(f'sample {it}: {n_folded} voxels where the sampled transformation is not '
-                                       f'diffeomorphic')
+                                       f'diffeomorphic' + ('' if bad else ' (on another rank)'))
         if data_loss is not None or reg_loss is not None:
             self._pull_hyper(data_loss, reg_loss)
         mom = s.posterior_moments()

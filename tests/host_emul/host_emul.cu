@@ -155,6 +155,9 @@ double emul_gmm_stats_step(const float* z, const unsigned char* mask, double* hy
     return alpha;
 }
 
+// virtual decimation factor from the five lag sums (RR, RD, RH, RW at IRS_SUM_RR..): what the device evaluates
+double emul_vd_alpha(const double* sums, double n_mask) { return irs_vd_alpha(sums, n_mask); }
+
 // cfg_d: reg_type, learnable, lr0, lr1, lr_decay, beta1, beta2, eps, prior_loc, prior_scale, w_reg, dof, shape, rate
 void emul_reg_hyper_step(double* hyper, const double* cfg_d, int C, double* stats) {
     IrsHyperCfg cfg = {};

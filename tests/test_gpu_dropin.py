@@ -385,3 +385,72 @@ def test_run_VI_then_MCMC_svffd(pkg):
     assert all(torch.isfinite(x) for x in lt['data'] + lt['reg'])
     res = t._run_MCMC(m['data_loss'], m['reg_loss'], speed_test_iters=0)
     assert res['n'] == 3 * C and torch.isfinite(res['mean']).all() and res['mean'].shape == (3, n, n, n)
+
+
+def test_adam_state_travels_from_VI_to_MCMC(pkg):
+    """the reference creates optimizer_GMM / optimizer_reg once and they persist through __GMM_init, VI and
+    MCMC (trainer/trainer.py:62-66).  After two VI iterations the first SGLD transition must step the mixture and the
+    regulariser hyper-parameters with the step counters, decayed rates and moments VI left behind -- compared with the
+    oracle carrying ONE AdamState through the same sequence (a restart from step 0 moves log_std ~3x further)."""
+    from irsgmcmc_b200.trainer import Trainer
+    from irsgmcmc_b200.data_loader.synthetic import make_pair
+    n, C, n_vi = 16, 2, 2
+    torch.manual_seed(21)
+    fixed, moving, vp0 = make_pair(n)
+    cfg = _reference_style_config(C)
+    cfg['optimizer_reg'] = {'type': 'Adam', 'args': {'lr_loc': 0.01, 'lr_log_scale': 0.01, 'lr_decay': 0.001}}
+    cfg['optimizer_q_v'] = {'type': 'Adam', 'args': {'lr_mu': 0.0, 'lr_log_var': 0.0, 'lr_u': 0.0, 'lr_decay': 0.0}}
+    t = Trainer(cfg, fixed, moving, vp0, device=torch.device(DEV))
+    m = t._build_VI_modules()
+    m['data_loss'].init_parameters(0.7)
+    noise = [(torch.randn(1, 3, n, n, n), torch.randn(1), torch.rand(1, 3, n, n, n), torch.rand(1, 3, n, n, n))
+             for _ in range(n_vi)]
+    t._run_VI(vp0, no_iters=n_vi, modules=m, noise=iter([tuple(x.to(DEV) for x in nz) for nz in noise]))
+    step_after_vi = m['optimizer_GMM'].state[m['data_loss'].log_std]['step']
+    assert step_after_vi == 2 * n_vi
+
+    st = O.State(O.Config(reg='lognormal', w_reg=1.6), torch.zeros(C, 3, n, n, n), torch.ones(1), (n, n, n))
+    st.init_gmm(0.7)
+    for eps, x, j1, j2 in noise:   # q(v) is frozen (lr 0): both sides see the same samples
+        O.vi_iteration(st, fixed, moving, vp0, eps, x, j1, j2)
+    assert rel(m['data_loss'].log_std, st.log_std) < 1e-4 and st.adam_gmm.step_no == step_after_vi
+
+    v0 = 0.5 * torch.randn(C, 3, n, n, n)
+    sigma = torch.exp(0.5 * vp0['log_var'])
+    eps, ju = torch.randn(C, 3, n, n, n), torch.rand(C, 3, n, n, n)
+    t.sampler.set_state(v0, sigma)
+    t.sampler.set_noise(eps, ju)
+    t.SGLD_params = {'sigma': t.sampler.sigma, 'tau': 0.4}
+    ls_before = m['data_loss'].log_std.detach().clone()
+    t._SGLD_transition(None, None, m['data_loss'], m['reg_loss'])     # pushes parameters + optimiser state, steps, pulls
+    st.v, st.sigma = v0.clone(), sigma.expand(C, -1, -1, -1, -1)
+    O.sgld_transition(st, fixed, moving, eps, ju)
+    moved = float((m['data_loss'].log_std.detach().cpu() - ls_before.cpu()).norm())
+    err = float((m['data_loss'].log_std.detach().cpu() - st.log_std).norm())
+    print('log_std moved by', moved, 'distance from the oracle', err)
+    assert err < 2e-3 * moved + 1e-6
+    assert rel(m['data_loss'].logits, st.logits) < 1e-3
+    assert rel(torch.stack((m['reg_loss'].loc.detach().cpu(), m['reg_loss'].log_scale.detach().cpu())).double(),
+               torch.stack((st.loc, st.log_scale))) < 1e-7
+    t._pull_hyper(m['data_loss'], m['reg_loss'])                      # optimiser state mirrored back on request
+    assert m['optimizer_GMM'].state[m['data_loss'].log_std]['step'] == step_after_vi + C
+    assert rel(m['optimizer_GMM'].state[m['data_loss'].log_std]['exp_avg'], st.adam_gmm.m[0]) < 1e-3
+    assert m['optimizer_reg'].state[m['reg_loss'].loc]['step'] == n_vi + 1
+
+
+def test_run_model_GMM_init_then_VI_then_MCMC(pkg):
+    """Trainer._run_model = the reference's orchestration (trainer/trainer.py:478-504): __GMM_init, _run_VI, _run_MCMC with
+    the optimiser state handed over between the stages"""
+    from irsgmcmc_b200.trainer import Trainer
+    from irsgmcmc_b200.data_loader.synthetic import make_pair
+    n, C = 16, 2
+    torch.manual_seed(3)
+    fixed, moving, vp0 = make_pair(n)
+    cfg = _reference_style_config(C, burn_in=2, samples=6, period=2)
+    cfg['trainer'].update({'no_iters_VI': 3, 'VI': True, 'MCMC': True})
+    t = Trainer(cfg, fixed, moving, vp0, device=torch.device(DEV))
+    res = t._run_model()
+    m = res['modules']
+    assert len(res['VI_history']) == 3 and res['n'] == 3 * C and torch.isfinite(res['mean']).all()
+    # 25 warm-up steps + 2 per VI iteration + C per transition (8 transitions)
+    assert m['optimizer_GMM'].state[m['data_loss'].log_std]['step'] == 25 + 2 * 3 + C * 8

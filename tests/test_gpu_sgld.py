@@ -257,3 +257,62 @@ def test_checkpoint_resume_is_bit_identical(built, ffd, tmp_path):
     assert torch.equal(a.disp_mean, b.disp_mean) and torch.equal(a.disp_m2, b.disp_m2) and a.n_kept == b.n_kept == 2 * C
     with pytest.raises(ValueError):
         SGLDSampler(fixed, moving, C, SGLDConfig(**kw), device=DEV, chain_offset=0).load_state_dict(a.state_dict())
+
+
+@pytest.mark.parametrize('init', ['VI', 'identity', 'noise'])
+def test_init_chains_pinned_to_reference_draws(built, init):
+    """A16: SGLDSampler.init_chains on the device == draw_chain_states (pinned bit-exactly to the reference's
+    Trainer.__SGLD_init in tests/test_oracle_vs_reference.py) for the same seeded CUDA generator; a shard with a chain
+    offset starts its chains where the single-GPU run starts the same global chain ids"""
+    from irsgmcmc_b200.sampler import SGLDSampler, SGLDConfig
+    from irsgmcmc_b200.utils.sampler import draw_chain_states, sample_q_v
+    from irsgmcmc_b200.data_loader.synthetic import make_pair
+    n, C = 16, 4
+    fixed, moving, vp = make_pair(n)
+    g = torch.Generator().manual_seed(3)
+    vp = {'mu': torch.randn(1, 3, n, n, n, generator=g), 'log_var': torch.randn(1, 3, n, n, n, generator=g) - 1.0,
+          'u': 0.1 * torch.randn(1, 3, n, n, n, generator=g)}
+    vp_dev = {k: v.to(DEV) for k, v in vp.items()}
+    s = SGLDSampler(fixed, moving, C, SGLDConfig(), device=DEV)
+    torch.manual_seed(11)
+    s.init_chains(init, vp)
+    torch.manual_seed(11)
+    if init == 'VI':   # the reference's loop, with this package's mirror of utils/sampler.py on the device
+        want = torch.stack([sample_q_v(vp_dev)[0] for _ in range(C)])
+        assert torch.equal(s.sigma, torch.exp(0.5 * vp_dev['log_var']))
+    elif init == 'identity':
+        want = torch.zeros(C, 3, n, n, n, device=DEV)
+    else:
+        want = torch.randn([C, 3, n, n, n], device=DEV)
+    assert torch.equal(s.v, want)
+    if init != 'VI':
+        assert s.sigma is None   # sigma = 1 (trainer.py:602)
+    shard = SGLDSampler(fixed, moving, 2, SGLDConfig(), device=DEV, chain_offset=2)
+    torch.manual_seed(11)
+    shard.init_chains(init, vp, no_chains_total=C)
+    assert torch.equal(shard.v, s.v[2:])
+    gen = torch.Generator(device=DEV).manual_seed(11)
+    s.init_chains(init, vp, generator=gen)
+    assert torch.equal(s.v, want)
+
+
+def test_second_device_or_fresh_context_launch_configuration(built):
+    """the opt-in shared-memory attribute and occupancy-derived grid sizes are cached per DEVICE; with two GPUs a
+    sampler on cuda:1 after one on cuda:0 must run the TMA kernels and give the same result"""
+    from irsgmcmc_b200.sampler import SGLDSampler, SGLDConfig
+    from irsgmcmc_b200.data_loader.synthetic import make_pair
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs two GPUs')
+    n, C = 32, 1
+    fixed, moving, vp = make_pair(n)
+    outs = []
+    for dev in ('cuda:0', 'cuda:1'):
+        torch.manual_seed(0)
+        s = SGLDSampler(fixed, moving, C, SGLDConfig(), device=dev)
+        s.set_state(0.5 * torch.randn(C, 3, n, n, n), torch.exp(0.5 * vp['log_var']))
+        s.init_gmm(sigma_hat=0.7)
+        s.step(3, use_graph=False)
+        torch.cuda.synchronize(dev)
+        outs.append(s.v.cpu())
+    torch.cuda.set_device(0)
+    assert torch.equal(outs[0], outs[1])

@@ -137,6 +137,21 @@ def test_mixture_step(emul, K):
         assert rel(dz, zz.grad.flatten()) < 1e-4
 
 
+def test_vd_factor_non_positive_correlations(emul):
+    """reference utils/util.py:481-485: alpha = sqrt(prod_a clamp(-(2/pi) log(corr_a), max=1)); torch.clamp propagates the
+    NaN of a NEGATIVE lag-1 correlation, a correlation of exactly zero gives +inf -> 1 (fminf would hide the NaN)"""
+    emul.emul_vd_alpha.restype = ctypes.c_double
+    n_mask = 1000.0
+    for corr in ([0.5, 0.4, 0.3], [0.5, -0.1, 0.3], [0.0, 0.4, 0.3], [0.9, 0.95, 0.99], [-0.2, -0.1, 0.0]):
+        sums = np.zeros(32, np.float64)
+        sums[1] = 2.0 * n_mask                      # sum r^2 -> var = 2
+        sums[2:5] = np.array(corr) * 2.0 * n_mask   # lag sums / n_mask / var = corr
+        got = emul.emul_vd_alpha(P(sums), ctypes.c_double(n_mask))
+        c = torch.tensor(corr, dtype=torch.float32)
+        want = float(torch.sqrt(torch.prod(torch.clamp(-2.0 / math.pi * torch.log(c), max=1.0))))
+        assert (math.isnan(got) and math.isnan(want)) or abs(got - want) <= 1e-6 * max(abs(want), 1e-30), (corr, got, want)
+
+
 @pytest.mark.parametrize('reg,learnable', [('lognormal', True), ('lognormal', False), ('l2', True), ('l2', False)])
 def test_regulariser_hyper_step(emul, reg, learnable):
     n, C, w_reg = 32, 3, 1.6

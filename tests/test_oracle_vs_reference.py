@@ -209,3 +209,38 @@ def test_vi_sample_loss_matches_reference(ref, reg_name, reg_type):
     for a, b in zip(g_or, g_ref):
         assert rel(a, b) < 5e-4
     assert rel(st.log_std, gmm.log_std.detach()) < 1e-4
+
+
+@pytest.mark.parametrize('init', ['VI', 'identity', 'noise'])
+def test_chain_initialisation_matches_reference(ref, init):
+    """A16: Trainer.__SGLD_init / sample_q_v of the unmodified reference (trainer/trainer.py:585-611, utils/sampler.py:4-21)
+    against draw_chain_states (what SGLDSampler.init_chains runs) for the same seeded default generator: bit-identical
+    states and preconditioner; a shard of the chains reproduces the same states for its global chain ids"""
+    from irsgmcmc_b200.utils.sampler import draw_chain_states, sample_q_v
+    n, C = 10, 5
+    g = torch.Generator().manual_seed(3)
+    vp = {'mu': torch.randn(1, 3, n, n, n, generator=g), 'log_var': torch.randn(1, 3, n, n, n, generator=g) - 1.0,
+          'u': 0.1 * torch.randn(1, 3, n, n, n, generator=g)}
+    t = ref.trainer.Trainer.__new__(ref.trainer.Trainer)
+    t.device, t.no_chains, t.MCMC_init = 'cpu', C, init
+    t.config = {'optimizer_SG_MCMC': {'args': {'lr': 0.4}}}
+    t._Trainer__init_optimizer_SG_MCMC = lambda: None
+    torch.manual_seed(77)
+    t._Trainer__SGLD_init({k: v.clone() for k, v in vp.items()})
+    torch.manual_seed(77)
+    v, sigma = draw_chain_states(init, vp, C)
+    assert torch.equal(v, t.v_curr_state.detach())
+    ref_sigma = t.SGLD_params['sigma']
+    assert torch.equal(ref_sigma, torch.ones_like(ref_sigma) if sigma is None else sigma.expand_as(ref_sigma))
+    assert t.SGLD_params['tau'] == 0.4
+    # sharded: chains 2..4 of 5 on "rank 1" draw what the single process gave those global ids
+    torch.manual_seed(77)
+    v_shard, _ = draw_chain_states(init, vp, 3, chain_offset=2, no_chains_total=C)
+    assert torch.equal(v_shard, v[2:])
+    # the mirror of utils/sampler.py itself, single draw and antithetic pair
+    for k in (1, 2):
+        torch.manual_seed(5)
+        a = ref.sampler.sample_q_v(vp, no_samples=k)
+        torch.manual_seed(5)
+        b = sample_q_v(vp, no_samples=k)
+        assert all(torch.equal(x, y) for x, y in zip(a if k == 2 else (a,), b if k == 2 else (b,)))
