@@ -98,7 +98,9 @@ def check(report):
     Gradient-like quantities (SURVEY surprise 9: the position-gradient of trilinear interpolation jumps at cell faces, so
     1-ulp differences flip a few voxels' slopes and *any* two fp32 implementations differ by 1e-5..4e-4): the yardstick is
     the fp32 oracle's own distance from the fp64 oracle.  The flips are rare random events, so the yardstick is taken
-    over all iterations of the run (a single iteration can have a lucky 4e-6) and capped at 1e-3.
+    over all iterations of the run (a single iteration can have a lucky 4e-6).  Above 1e-3 (64^3 SSD: a handful of flipped
+    voxels carry O(1) slopes, the fp32 oracle itself is 1.2e-3 from fp64) the CUDA path must additionally be no farther from
+    fp64 than 1.25 x the fp32 oracle in the SAME iteration.
     """
     for r in report:
         for k in FWD_KEYS:
@@ -106,7 +108,7 @@ def check(report):
     for k in ('z', 'alpha', 'data', 'grad_v', 'step', 'log_std', 'logits', 'reg_p'):
         yard = max(r[k][1] for r in report)
         for r in report:
-            ok = r[k][0] <= max(1e-5, 2 * yard) and r[k][0] < 1e-3
+            ok = r[k][0] <= max(1e-5, 2 * yard) and (r[k][0] < 1e-3 or r[k][0] <= 1.25 * r[k][1])
             if not ok and k in ('grad_v', 'step'):   # no flip in the fp32 oracle on this input: count ours instead
                 frac, inlier, overall = r['grad_v_kink']
                 ok = frac <= 2e-3 and inlier <= 1e-4 and overall <= 2e-3
