@@ -10,7 +10,8 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libirsgmcmc.so')
+# IRSGMCMC_LIB: development override (A/B builds of the same library; irsgmcmc_b200/build.py `out=`)
+LIB_PATH = os.environ.get('IRSGMCMC_LIB') or os.path.join(_HERE, 'libirsgmcmc.so')
 
 c_float_p = ctypes.c_void_p
 HYPER_SIZE = 96

@@ -30,18 +30,43 @@ def _stale(target, sources):
     return any(os.path.getmtime(s) > t for s in sources)
 
 
-def build_library(force=False, verbose=False):
+def _compile_object(src, obj, deps, defines, verbose, force):
+    if not force and not _stale(obj, [src] + deps):
+        return None
+    cmd = [_nvcc(), '-c'] + NVCC_FLAGS + [f'-D{d}' for d in defines] + (['-Xptxas', '-v'] if verbose else []) + [src, '-o', obj]
+    return subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+
+
+def build_library(force=False, verbose=False, defines=(), out=None):
+    """one object per translation unit (compiled in parallel, rebuilt only when stale), then one link.
+    `defines` / `out`: development variants (e.g. defines=['IRS_X1=1'], out='libirsgmcmc_x1.so'; picked up at run time
+    through the IRSGMCMC_LIB environment variable, see _lib.py)."""
     sources = sorted(glob.glob(os.path.join(CSRC, '*.cu')))
-    deps = sources + glob.glob(os.path.join(CSRC, '*.cuh')) + [os.path.join(ROOT, 'include', 'irsgmcmc.h')]
-    if not force and not _stale(LIB, deps):
-        return LIB
-    cmd = [_nvcc(), '-shared'] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + sources + ['-o', LIB]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        raise RuntimeError('nvcc failed:\n' + res.stdout + res.stderr)
+    headers = glob.glob(os.path.join(CSRC, '*.cuh')) + [os.path.join(ROOT, 'include', 'irsgmcmc.h')]
+    lib = LIB if out is None else os.path.join(HERE, out)
+    tag = '' if not defines else '_' + '_'.join(d.replace('=', '-') for d in defines)
+    objdir = os.path.join(HERE, 'build', 'obj' + tag)
+    os.makedirs(objdir, exist_ok=True)
+    objs, procs = [], []
+    for src in sources:
+        obj = os.path.join(objdir, os.path.basename(src)[:-3] + '.o')
+        objs.append(obj)
+        p = _compile_object(src, obj, headers, list(defines), verbose, force)
+        if p is not None:
+            procs.append((src, p))
+    log = ''
+    for src, p in procs:
+        text, _ = p.communicate()
+        if p.returncode != 0:
+            raise RuntimeError(f'nvcc failed on {src}:\n{text}')
+        log += text
     if verbose:
-        print(res.stderr)
-    return LIB
+        print(log)
+    if procs or not os.path.isfile(lib) or _stale(lib, objs):
+        res = subprocess.run([_nvcc(), '-shared', '-o', lib] + objs, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError('link failed:\n' + res.stdout + res.stderr)
+    return lib
 
 
 def build_host_emulation(force=False):

@@ -254,6 +254,19 @@ __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
     return *reinterpret_cast<float2*>(&rd);
 }
 
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+    unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a), rb = *reinterpret_cast<unsigned long long*>(&b), rd;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+    return *reinterpret_cast<float2*>(&rd);
+}
+// scalar x pair (+ pair): ptxas folds the duplicated scalar into the .F32 broadcast operand of FFMA2 / FMUL2
+__device__ __forceinline__ float2 ffma2s(float s, float2 b, float2 c) { return ffma2(make_float2(s, s), b, c); }
+__device__ __forceinline__ float2 fmul2s(float s, float2 b) { return fmul2(make_float2(s, s), b); }
+
+#ifndef IRS_BWD_V2
+#define IRS_BWD_V2 1   // adjoint consumer: straight-line path for gradient-carrying neighbourhoods, z components of the two
+#endif                 // targets packed (FFMA2), cheaper row flags (0 = the round-1 consumer, kept for A/B timing)
+
 // position term of the adjoint: sum_c g_c * grad trilinear[u_c](p).  Interpolation is linear in the corner values, so
 // the three components are combined at the eight corners first (w = g . u) and ONE gradient is interpolated.
 template <int RS>
@@ -1091,10 +1104,140 @@ __device__ __forceinline__ void svf_bwd_tma2_body(const BwdTmaCtx& c) {
             float4* r = rec + rec_e[k];
             r[0] = make_float4(cx, cy, g0, g1);
             r[B2_NR] = make_float4(g2, wm, w0, wp);
+#if IRS_BWD_V2
+            if (((__float_as_uint(g0) | __float_as_uint(g1) | __float_as_uint(g2)) << 1) != 0u)   // any non-zero (+-0 are zero)
+                c.row_nz[MP * B2_EY + rec_row[k]] = 1;
+#else
             if (g0 != 0.f || g1 != 0.f || g2 != 0.f) c.row_nz[MP * B2_EY + rec_row[k]] = 1;
+#endif
         }
     };
 
+#if IRS_BWD_V2
+    // Accumulators: XY[j][b] = components (x, y) of target j in bank b; ZZ[b] = component z of targets (0, 1) in bank b.
+    // A record of the two source rows that both targets see costs 3 FMUL2 + 9 FFMA2 for its 18 products (the z components of
+    // the two targets share one packed FMA); bank 0 = target plane s-1, 1 = s, 2 = s+1, rotated by register moves per plane.
+    float2 XY[2][3], ZZ[3];
+#pragma unroll
+    for (int b = 0; b < 3; ++b) { XY[0][b] = XY[1][b] = ZZ[b] = make_float2(0.f, 0.f); }
+    int gi = ((s_first - 1) * d.H + y0) * d.W + x;   // index of target 0 in plane s-1 (target 1: + W)
+    irs_mbar_wait(&c.bar_u[0], 0);
+    irs_mbar_wait(&c.bar_u[1], 0);
+    irs_mbar_wait(&c.bar_g[0], 0);
+    produce(0);
+    __syncthreads();
+    if (tid == 0 && BWD_NG < n_g) {
+        irs_mbar_expect_tx(&c.bar_g[0], B2_BYTES);
+        irs_tma_load_plane(c.G, c.tmap_g, &c.bar_g[0], c.x0t - TMA_XO, c.y0t - 1, zs - 1 + BWD_NG, 3 * c.chain);
+    }
+
+    for (int it = 0; it < n_it; ++it) {
+        const int M = it % 3, BP = (it + 1) % 3, BMf = (it + 2) % 3;   // ring slots (gradient planes, row flags)
+        const int s = s_first + it;
+        irs_mbar_wait(&c.bar_u[(it + 2) & 3], ((it + 2) >> 2) & 1);
+        if (tid < B2_EY) c.row_nz[BMf * B2_EY + tid] = 0;
+        if (it + 1 < n_it) {
+            irs_mbar_wait(&c.bar_g[BP], ((it + 1) / 3) & 1);
+            produce(it + 1);
+        }
+        const float* Us = c.U + ((it + 1) & 3) * SS;
+        const float4* rec = reinterpret_cast<const float4*>(c.REC) + (it & 1) * (2 * B2_NR);
+        if ((act[0] || act[1]) && s >= 0 && s < d.D) {
+            const int* nz = c.row_nz + M * B2_EY + ty0;   // flags of record rows ty0 .. ty0 + 3
+            const int nz1 = nz[1], nz2 = nz[2];
+            float gown[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
+            // A row without gradient adds exact zeros, so the four rows run as ONE straight-line block whenever any of them
+            // carries gradient (warp-uniform): the scheduler can overlap the record loads of a row with the previous row's FMAs.
+            if ((nz[0] | nz1 | nz2 | nz[3]) != 0) {
+#pragma unroll
+                for (int ox = -1; ox <= 1; ++ox) {   // row 0: target 0 only (oy = -1); row 3: target 1 only (oy = +1)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const float4* r = rec + (lr0 + (e == 0 ? -1 : 2) * TMA_EX + ox);
+                        const float4 r0 = r[0], r1 = r[B2_NR];
+                        const float w = hat_small_rt(r0.x, ox) * hat_small_rt(r0.y, e == 0 ? -1 : 1);
+                        const float2 g01 = make_float2(r0.z, r0.w);
+                        const float w0 = w * r1.y, w1 = w * r1.z, w2 = w * r1.w;
+                        XY[e][0] = ffma2s(w0, g01, XY[e][0]);
+                        XY[e][1] = ffma2s(w1, g01, XY[e][1]);
+                        XY[e][2] = ffma2s(w2, g01, XY[e][2]);
+                        if (e == 0) { ZZ[0].x = fmaf(w0, r1.x, ZZ[0].x); ZZ[1].x = fmaf(w1, r1.x, ZZ[1].x); ZZ[2].x = fmaf(w2, r1.x, ZZ[2].x); }
+                        else        { ZZ[0].y = fmaf(w0, r1.x, ZZ[0].y); ZZ[1].y = fmaf(w1, r1.x, ZZ[1].y); ZZ[2].y = fmaf(w2, r1.x, ZZ[2].y); }
+                    }
+                }
+#pragma unroll
+                for (int rr = 1; rr <= 2; ++rr) {    // rows seen by both targets: oy = rr - 1 (target 0), rr - 2 (target 1)
+#pragma unroll
+                    for (int ox = -1; ox <= 1; ++ox) {
+                        const float4* r = rec + (lr0 + (rr - 1) * TMA_EX + ox);
+                        const float4 r0 = r[0], r1 = r[B2_NR];
+                        const float wx = hat_small_rt(r0.x, ox);
+                        const float2 W = fmul2s(wx, make_float2(hat_small_rt(r0.y, rr - 1), hat_small_rt(r0.y, rr - 2)));
+                        const float2 g01 = make_float2(r0.z, r0.w);
+                        const float2 W0 = fmul2s(r1.y, W), W1 = fmul2s(r1.z, W), W2 = fmul2s(r1.w, W);
+                        XY[0][0] = ffma2s(W0.x, g01, XY[0][0]); XY[1][0] = ffma2s(W0.y, g01, XY[1][0]); ZZ[0] = ffma2s(r1.x, W0, ZZ[0]);
+                        XY[0][1] = ffma2s(W1.x, g01, XY[0][1]); XY[1][1] = ffma2s(W1.y, g01, XY[1][1]); ZZ[1] = ffma2s(r1.x, W1, ZZ[1]);
+                        XY[0][2] = ffma2s(W2.x, g01, XY[0][2]); XY[1][2] = ffma2s(W2.y, g01, XY[1][2]); ZZ[2] = ffma2s(r1.x, W2, ZZ[2]);
+                        if (ox == 0) { gown[rr - 1][0] = r0.z; gown[rr - 1][1] = r0.w; gown[rr - 1][2] = r1.x; }
+                    }
+                }
+            }
+            // ---- direct + position terms ----
+            if (s >= zs && s < ze) {
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    if (!act[j] || (j == 0 ? nz1 : nz2) == 0) continue;
+                    const int lc = lc0 + j * BW;
+                    const float g0 = gown[j][0], g1 = gown[j][1], g2 = gown[j][2];
+                    float px = xf + Us[lc] * c.in_scale, py = (float)(y0 + j) + Us[CS + lc] * c.in_scale,
+                          pz = (float)s + Us[2 * CS + lc] * c.in_scale;
+                    const float mx = irs_inside(px, d.W) * c.in_scale, my = irs_inside(py, d.H) * c.in_scale,
+                                mz = irs_inside(pz, d.D) * c.in_scale;
+                    px = irs_clampf(px, 0.f, xmax); py = irs_clampf(py, 0.f, ymax); pz = irs_clampf(pz, 0.f, zmax);
+                    const float fx0 = floorf(px), fy0 = floorf(py), fz0 = floorf(pz);
+                    const float fx = px - fx0, fy = py - fy0, fz = pz - fz0;
+                    const int ix = (int)fx0, iy = (int)fy0, iz = (int)fz0;
+                    const int s0 = (it + 1 + (iz - s)) & (TMA_NS - 1), s1 = (s0 + 1) & (TMA_NS - 1);
+                    const int i000 = s0 * SS + (iy - (c.y0t - 1)) * BW + (ix - (c.x0t - TMA_XO));
+                    float jx, jy, jz;
+                    ring_interp_grad_dot<BW>(c.U, CS, i000, (s1 - s0) * SS, g0, g1, g2, fx, fy, fz, jx, jy, jz);
+                    XY[j][1].x += g0 + mx * jx;
+                    XY[j][1].y += g1 + my * jy;
+                    if (j == 0) ZZ[1].x += g2 + mz * jz; else ZZ[1].y += g2 + mz * jz;
+                }
+            }
+        }
+        // ---- target plane s-1 is complete ----
+        if (s - 1 >= zs && s - 1 < ze) {
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                if (act[j]) {
+                    const int o = gi + j * d.W;
+                    c.g[o] = XY[j][0].x * c.out_scale;
+                    c.g[Vi + o] = XY[j][0].y * c.out_scale;
+                    c.g[2 * Vi + o] = (j == 0 ? ZZ[0].x : ZZ[0].y) * c.out_scale;
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j) { XY[j][0] = XY[j][1]; XY[j][1] = XY[j][2]; XY[j][2] = make_float2(0.f, 0.f); }
+        ZZ[0] = ZZ[1]; ZZ[1] = ZZ[2]; ZZ[2] = make_float2(0.f, 0.f);
+        gi += HW;
+        __syncthreads();
+        if (tid == 0) {
+            if (it + 4 < n_u) {
+                irs_mbar_expect_tx(&c.bar_u[it & 3], B2_BYTES);
+                irs_tma_load_plane(c.U + (it & 3) * SS, c.tmap_u, &c.bar_u[it & 3], c.x0t - TMA_XO, c.y0t - 1, zs + 2 + it,
+                                   3 * c.chain);
+            }
+            if (it + 1 + BWD_NG < n_g) {
+                irs_mbar_expect_tx(&c.bar_g[BP], B2_BYTES);
+                irs_tma_load_plane(c.G + BP * SS, c.tmap_g, &c.bar_g[BP], c.x0t - TMA_XO, c.y0t - 1, zs + 3 + it, 3 * c.chain);
+            }
+        }
+    }
+}
+#else
     BwdAcc acc[2];
     acc[0].clear(); acc[1].clear();
     int gi = ((s_first - 1) * d.H + y0) * d.W + x;   // index of target 0 in plane s-1 (target 1: + W)
@@ -1199,6 +1342,7 @@ __device__ __forceinline__ void svf_bwd_tma2_body(const BwdTmaCtx& c) {
         }
     }
 }
+#endif
 
 __global__ void __launch_bounds__(TILE_T, 2)
 svf_step_bwd_tma2_kernel(const __grid_constant__ CUtensorMap tmap_u, const __grid_constant__ CUtensorMap tmap_g,
