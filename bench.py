@@ -176,6 +176,131 @@ def workload_config(args, chains, n):
                          'exceeds the 126 MB L2; no explicit flush'}
 
 
+def pin_rank_to_cores(local_rank, local_world):
+    """one contiguous share of the host cores per rank: with 8 processes on one node an unpinned rank that loses its core for a
+    millisecond shows up as 5 % of a 20 ms timed region (max over ranks)"""
+    try:
+        cores = sorted(os.sched_getaffinity(0))
+        per = len(cores) // max(local_world, 1)
+        if local_world > 1 and per >= 1:
+            os.sched_setaffinity(0, cores[local_rank * per:(local_rank + 1) * per])
+            return per
+    except (AttributeError, OSError):
+        pass
+    return None
+
+
+def graph_length(steps):
+    """transitions per CUDA graph for a timed region of `steps`: the whole region in ONE replay up to 40 transitions,
+    otherwise the largest divisor of `steps` in [10, 40] (10 with an eager remainder when there is none)"""
+    if steps <= 40:
+        return max(steps, 1)
+    for g in range(40, 9, -1):
+        if steps % g == 0:
+            return g
+    return 10
+
+
+def run_config(tag, n, chains, data, world, rank, dev, peak, barrier, seg_dice=False, moments=False, flush_l2=False,
+               target_ms=1200.0):
+    """
+    One entry of the `configs` sub-record: a BASELINE.json configuration other than the headline, measured in the same run with
+    the same rules (CUDA events on the launching stream, barrier + synchronize on both sides, max over ranks, >= 3 warm-up
+    transitions).  `seg_dice`: every transition is followed by the nearest-neighbour warp of the int16 segmentation and the
+    Dice counts of the 15 structures (the reference's own speed loop includes the segmentation warp, trainer.py:467-476).
+    `moments`: also times the Welford update of all chains and the NCCL merge of the moments, warm.
+    `flush_l2`: the working set fits the 126 MB L2 (64^3, one chain): a 256 MB buffer is overwritten between transitions and
+    every transition is timed on its own.
+    """
+    import gc
+    import torch
+    import torch.distributed as dist
+    from irsgmcmc_b200 import ops
+    from irsgmcmc_b200.sampler import SGLDSampler, SGLDConfig
+    from irsgmcmc_b200.data_loader.synthetic import make_pair, STRUCTURE_LABELS
+    V = n ** 3
+    fixed, moving, vp = make_pair(n, device=dev)
+    lcc = data == 'lcc'
+    cfg = SGLDConfig(data_loss=data, reg_loss='RegLoss_LogNormal' if lcc else 'RegLoss_L2', w_reg=1.6 if lcc else 1.4,
+                     reg_learnable=lcc)
+    sampler = SGLDSampler(fixed, moving, chains, cfg, device=dev, chain_offset=rank * chains)
+    sampler.init_chains('VI', vp, generator=torch.Generator(device=dev).manual_seed(123 + rank))
+    sampler.init_gmm()
+    seg_f = fixed['seg'].to(dev) if seg_dice else None
+    counts = None
+
+    def one():
+        nonlocal counts
+        sampler.step(1)
+        if seg_dice:
+            counts = ops.dice_counts(seg_f, sampler.warp_segmentation(), STRUCTURE_LABELS)
+
+    def allmax(x):
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for _ in range(3):
+        one()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(); one(); one(); e1.record()
+    barrier()
+    est = allmax(e0.elapsed_time(e1)) / 2
+    K = int(min(50, max(3, target_ms / max(est, 1e-3))))
+    if flush_l2:
+        flush = torch.empty(256 << 20, device=dev, dtype=torch.uint8)
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+        barrier()
+        for a, b in evs:
+            flush.zero_()
+            a.record(); one(); b.record()
+        barrier()
+        ms = allmax(sum(a.elapsed_time(b) for a, b in evs))
+        del flush
+    else:
+        barrier()
+        e0.record()
+        for _ in range(K):
+            one()
+        e1.record()
+        barrier()
+        ms = allmax(e0.elapsed_time(e1))
+    value = world * chains * V * K / (ms * 1e-3)
+    bytes_step = BYTES_PER_VOXEL_STEP_LCC if lcc else BYTES_PER_VOXEL_STEP_SSD
+    out = {'config': tag, 'volume': [n, n, n], 'data_term': 'LCC+GMM(K=4)' if lcc else 'SSD(K=1)',
+           'chains_per_gpu': chains, 'chains_total': chains * world, 'steps': K, 'warmup': 5,
+           'ms_per_step': ms / K, 'voxel_steps_per_s': value, 'iterations_per_s': K / (ms * 1e-3),
+           'step_roofline_frac': bytes_step * (value / world) / 1e9 / peak, 'bytes_per_voxel_step': bytes_step,
+           'gpu_launches_per_step': sampler.launches_per_step() + (3 if seg_dice else 0),
+           'l2': 'flushed between transitions (256 MB overwrite), each transition timed on its own' if flush_l2
+                 else 'working set exceeds the 126 MB L2'}
+    if seg_dice:
+        c = counts[0].double().cpu()
+        dice = (2 * c[:, 2] / (c[:, 0] + c[:, 1]).clamp(min=1)).tolist()
+        out['per_step_extras'] = 'transformation + nearest-neighbour int16 segmentation warp + Dice counts (15 structures)'
+        out['dice_mean_last_sample'] = sum(dice) / len(dice)
+        out['asd'] = 'unavailable (SimpleITK contour distance, not on the GPU path)'
+    if moments:
+        sampler.accumulate()
+        sampler.posterior_moments()          # warm: buffers allocated, NCCL channels for this size set up
+        barrier()
+        e0.record(); sampler.accumulate(); e1.record()
+        barrier()
+        out['welford_update_ms'] = allmax(e0.elapsed_time(e1))
+        barrier()
+        e0.record(); mom = sampler.posterior_moments(); e1.record()
+        barrier()
+        out['moments_merge_ms'] = allmax(e0.elapsed_time(e1))
+        out['moments_payload_bytes'] = 2 * 4 * 4 * V
+        out['moments_n'] = int(mom['n'])
+    del sampler
+    gc.collect()
+    torch.cuda.empty_cache()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -188,8 +313,11 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-graph', action='store_true')
     ap.add_argument('--e2e-steps', type=int, default=0, help='default: min(steps, 50)')
-    ap.add_argument('--aten-gpu-baseline', action='store_true', help='also time the oracle port of the reference with all '
-                    'tensors on the GPU (ATen kernels): the GPU-vs-GPU comparison of SURVEY section 8(d); opt-in')
+    ap.add_argument('--aten-gpu-baseline', action='store_true', help='(default at N = 1) also time the oracle port of the '
+                    'reference with all tensors on the GPU (ATen kernels): the GPU-vs-GPU comparison of SURVEY section 8(d)')
+    ap.add_argument('--no-aten-gpu-baseline', action='store_true')
+    ap.add_argument('--no-configs', action='store_true', help='skip the `configs` sub-record (the other BASELINE.json '
+                    'configurations, measured after the headline in the same run)')
     ap.add_argument('--cps', type=int, default=0, help='secondary configuration: SVFFD_3D with this control point '
                     'spacing as the transformation model (reference configs/experiment5); 0 = SVF_3D, the headline')
     args = ap.parse_args()
@@ -211,6 +339,7 @@ def main():
         raise RuntimeError('bench.py needs a CUDA device: there is no CPU path (use --impl reference for the CPU baseline)')
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
+    cores_per_rank = pin_rank_to_cores(local_rank, int(os.environ.get('LOCAL_WORLD_SIZE', world)))
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         dist.init_process_group('nccl', device_id=dev)
@@ -238,9 +367,17 @@ def main():
         torch.cuda.synchronize()
 
     # ---- device-resident throughput ----
-    # W warm-up transitions as asked (the first one captures the graph), topped up to 20 so that the clocks have ramped and
-    # the graph is resident before the timed region; the timed region is exactly K transitions
-    sampler.step(max(args.warmup, 20), use_graph=use_graph)
+    # The timed region is exactly K transitions, replayed as CUDA graphs of `g` transitions each (one replay for K <= 40): all
+    # state lives on the device, so the host issues K / g launches and cannot perturb the region (at 8 ranks x 20 single-step
+    # replays a 1 ms host hiccup on any rank cost 5 %).  Warm-up: W transitions as asked, topped up to >= 20 and to whole
+    # replays of the same graph, so that clocks have ramped and the graph is resident.
+    g_len = graph_length(args.steps) if use_graph else 1
+    if use_graph:
+        sampler.capture(1)
+        sampler.capture(g_len)
+    n_warm = max(args.warmup, 20)
+    n_warm = -(-n_warm // g_len) * g_len
+    sampler.step(n_warm, use_graph=use_graph)
     barrier()
     clocks = ClockSampler(local_rank) if rank == 0 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -251,7 +388,11 @@ def main():
     ms = e0.elapsed_time(e1)
     clock_info = clocks.stop() if clocks else None
     t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    per_rank_ms = [ms]
     if world > 1:
+        gathered = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(gathered, t)
+        per_rank_ms = [float(x.item()) for x in gathered]
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t.item())
     value = world * C * V * args.steps / (ms_max * 1e-3)
@@ -331,14 +472,43 @@ def main():
         bytes_step = bytes_step - 96 + 24 + 96.0 * sampler.v[0, 0].numel() / V
     step_gbs = bytes_step * (value / world) / 1e9
 
-    # ---- posterior moments: Welford update + NCCL merge (once per run; outside the metric) ----
+    # ---- posterior moments: Welford update + NCCL merge (once per run / log period; outside the metric), timed WARM ----
     sampler.accumulate()
+    sampler.posterior_moments()
     barrier()
     e0.record()
     mom = sampler.posterior_moments()
     e1.record()
     barrier()
-    merge_ms = e0.elapsed_time(e1)
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    merge_ms = float(t.item())
+    merge_bytes = 2 * 4 * 4 * V      # two phases x (3 + 1) fp32 volumes
+    # ring-equivalent bus bandwidth of the two all-reduces (NCCL convention: 2 (N-1)/N x bytes / time)
+    merge_bus_gbs = (2.0 * (world - 1) / world) * merge_bytes / (merge_ms * 1e-3) / 1e9 if world > 1 else None
+
+    # ---- the other BASELINE.json configurations, same run, same rules (the headline above is not touched by them) ----
+    configs = None
+    default_headline = args.size == 128 and args.chains == 1 and args.data == 'lcc' and not args.cps and use_graph
+    if default_headline and not args.no_configs:
+        configs = []
+        todo = [dict(tag='configs[0]: 64^3 SSD + RegLoss_L2, 1 chain per GPU', n=64, chains=1, data='ssd', flush_l2=True, target_ms=300.0),
+                dict(tag=f'configs[2]: 128^3 LCC, 64 chains sharded over {world} GPU(s) (strong scaling), Welford + NCCL merge',
+                     n=128, chains=max(64 // world, 1), data='lcc', moments=True),
+                dict(tag='configs[3]: 256^3 LCC, 1 chain per GPU, segmentation warp + Dice per transition', n=256, chains=1,
+                     data='lcc', seg_dice=True, target_ms=600.0)]
+        if world == 1:
+            todo += [dict(tag='configs[4]a: 1024 chains at 64^3 SSD', n=64, chains=1024, data='ssd'),
+                     dict(tag='configs[4]b: 16 chains at 256^3 LCC', n=256, chains=16, data='lcc')]
+        for kw in todo:
+            tag = kw.pop('tag')
+            try:
+                configs.append(run_config(tag, kw.pop('n'), kw.pop('chains'), kw.pop('data'), world, rank, dev, peak, barrier, **kw))
+            except Exception as exc:   # a secondary configuration must not cost the headline line
+                configs.append({'config': tag, 'unavailable': f'{type(exc).__name__}: {exc}'[:300]})
+                if world > 1:
+                    raise
 
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
@@ -349,7 +519,7 @@ def main():
                          f'1 chain, {ms_cpu:.0f} ms each'}
 
     aten_gpu = None
-    if rank == 0 and args.aten_gpu_baseline:
+    if rank == 0 and (args.aten_gpu_baseline or (world == 1 and not args.no_aten_gpu_baseline)):
         try:
             v_gpu, ms_gpu = aten_gpu_transition_rate(n if n <= 128 else 128, 3, 1, args.data, args.cps, device=str(dev))
             aten_gpu = {'value': v_gpu, 'unit': 'voxel-steps/s', 'ms_per_step': ms_gpu, 'kind': 'port on the GPU (ATen)',
@@ -373,7 +543,11 @@ def main():
                 'step_roofline': {'bytes_per_voxel_step': bytes_step, 'achieved_gbs_per_gpu': step_gbs,
                                   'frac': step_gbs / peak},
                 'stage_ms': {k: round(v, 4) for k, v in stage_ms.items()},
-                'moments_merge_ms': merge_ms, 'graph': use_graph, 'clocks': clock_info, 'cpu_baseline': cpu}
+                'moments_merge_ms': merge_ms, 'moments_merge_bytes': merge_bytes, 'moments_merge_bus_gbs': merge_bus_gbs,
+                'graph': use_graph, 'transitions_per_graph': g_len, 'per_rank_ms_per_step': [x / args.steps for x in per_rank_ms],
+                'host_cores_per_rank': cores_per_rank, 'clocks': clock_info, 'cpu_baseline': cpu}
+        if configs is not None:
+            line['configs'] = configs
         if aten_gpu is not None:
             line['aten_gpu_baseline'] = aten_gpu
         print(json.dumps(line), flush=True)

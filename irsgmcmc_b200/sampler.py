@@ -143,7 +143,7 @@ class SGLDSampler:
         n_part = self.lib.irs_sgld_partials_doubles(ctypes.byref(self._cconf))
         self._partials = torch.zeros(max(int(n_part), 1), device=dev, dtype=torch.float64)
         self._cbuf = None
-        self._graph = None
+        self._graphs = {}   # transitions per replay -> captured CUDA graph
         self.iteration = 0
 
         # posterior moments (Welford): displacement (3,V) and warped image (1,V)
@@ -213,7 +213,7 @@ class SGLDSampler:
         return b
 
     def _invalidate(self):
-        self._cbuf, self._graph = None, None
+        self._cbuf, self._graphs = None, {}
 
     # ------------------------------------------------------------------------------------------------------------------
     # initialisation (reference trainer/trainer.py:529-547, 585-611)
@@ -302,26 +302,34 @@ class SGLDSampler:
         _lib.check(self.lib.irs_sgld_step(ctypes.byref(self._cconf), ctypes.byref(self._cbuf), _lib.stream()))
 
     def capture(self, iters_per_graph=1):
-        """capture `iters_per_graph` transitions into one CUDA graph (all state lives in device memory)"""
+        """capture `iters_per_graph` transitions into one CUDA graph (all state lives in device memory, so a replay needs no
+        host work at all: a long run is a handful of graph launches).  Several graphs of different lengths may coexist;
+        step() replays the longest one that still fits."""
+        k = int(iters_per_graph)
+        if k < 1:
+            raise ValueError('iters_per_graph must be >= 1')
+        if k in self._graphs:
+            return
         self._enqueue()  # warm-up outside capture (function attributes, lazy module load)
         torch.cuda.synchronize()
         self.iteration += 1
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
-            for _ in range(iters_per_graph):
+            for _ in range(k):
                 self._enqueue()
-        self._graph, self._graph_iters = g, iters_per_graph
+        self._graphs[k] = g
 
     def step(self, n=1, use_graph=True):
         """run n transitions; asynchronous"""
-        if use_graph and self._graph is None:
-            self.capture()
+        if use_graph and not self._graphs:
+            self.capture()      # runs one transition itself
             n -= 1
         done = 0
         if use_graph:
-            while n - done >= self._graph_iters:
-                self._graph.replay()
-                done += self._graph_iters
+            for k in sorted(self._graphs, reverse=True):
+                while n - done >= k:
+                    self._graphs[k].replay()
+                    done += k
         while done < n:
             self._enqueue()
             done += 1
