@@ -311,6 +311,7 @@ def main():
     ap.add_argument('--chains', type=int, default=1, help='chains per GPU')
     ap.add_argument('--data', default='lcc', choices=['lcc', 'ssd'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--hyper-mode', default='reference', choices=['reference', 'per_chain', 'frozen'])
     ap.add_argument('--no-graph', action='store_true')
     ap.add_argument('--e2e-steps', type=int, default=0, help='default: min(steps, 50)')
     ap.add_argument('--aten-gpu-baseline', action='store_true', help='(default at N = 1) also time the oracle port of the '
@@ -350,7 +351,7 @@ def main():
     reg = 'RegLoss_LogNormal' if args.data == 'lcc' else 'RegLoss_L2'
     ffd = dict(transformation='SVFFD_3D', cps=(args.cps,) * 3) if args.cps else {}
     cfg = SGLDConfig(data_loss=args.data, reg_loss=reg, w_reg=1.6 if args.data == 'lcc' else 1.4,
-                     reg_learnable=args.data == 'lcc', **ffd)
+                     reg_learnable=args.data == 'lcc', hyper_mode=args.hyper_mode, **ffd)
     if args.cps:   # the variational parameters live on the control grid (reference data_loader/datasets.py:23-27,57-68)
         from irsgmcmc_b200.utils import get_control_grid_size
         gdims = (1, 3, *get_control_grid_size((n, n, n), cfg.cps))

@@ -21,7 +21,8 @@
 extern "C" {
 #endif
 
-#define IRS_ABI_VERSION 3   /* 2: irs_svf_maxabs_floats() sizes the maxabs workspace; 3: cubic B-spline FFD entry points */
+#define IRS_ABI_VERSION 4   /* 2: irs_svf_maxabs_floats() sizes the maxabs workspace; 3: cubic B-spline FFD entry points;
+                               4: irs_sgld_config.hyper_mode (was reserved0), counters sized C + 8 with the ticket at [C] */
 
 #define IRS_OK 0
 #define IRS_ERR_BAD_ARG (-1)
@@ -204,6 +205,9 @@ int irs_welford_std(const float* m2, double count, float* std_out, long long n, 
 #define IRS_HYPER_REG_BETA_POW 59 /* same for the regulariser optimiser */
 #define IRS_HYPER_SCRATCH 64     /* 24 doubles of reduction scratch used inside a step */
 #define IRS_HYPER_SIZE 96
+#define IRS_HYPER_REFERENCE 0
+#define IRS_HYPER_PER_CHAIN 1
+#define IRS_HYPER_FROZEN 2
 
 /* layout of one row of the per-chain `stats` output (doubles) */
 #define IRS_STAT_ALPHA 0         /* virtual decimation factor */
@@ -227,7 +231,12 @@ typedef struct irs_sgld_config {
     int virtual_decimation;
     int use_jitter;
     int gather_radius_max;       /* adjoint gather window limit; larger displacements use the atomic kernel */
-    int reserved0;
+    int hyper_mode;              /* IRS_HYPER_REFERENCE (0): ONE mixture / regulariser parameter set shared by all chains,
+                                  * stepped chain after chain in index order (trainer/trainer.py:316-327,353-354);
+                                  * IRS_HYPER_PER_CHAIN: a parameter block per chain, i.e. every chain is an independent
+                                  * reference run with no_chains = 1 (`hyper` holds C * IRS_HYPER_SIZE doubles);
+                                  * IRS_HYPER_FROZEN: shared parameters, no Adam steps (the reference with all hyper learning
+                                  * rates at zero) -- the last two have no dependency between chains */
     float taps[16];
     double tau;
     double jitter_alpha;
@@ -269,11 +278,12 @@ typedef struct irs_sgld_buffers {
     float* field_b;              /* (C,3,V) scratch */
     float* grad_v;               /* (C,3,V) sigma^2 dL/d css: what SGD applies */
     float* maxabs;               /* irs_svf_maxabs_floats() */
-    double* hyper;               /* IRS_HYPER_SIZE doubles (parameters, optimiser state, scratch) */
+    double* hyper;               /* IRS_HYPER_SIZE doubles (parameters, optimiser state, scratch); C blocks of that size with
+                                  * IRS_HYPER_PER_CHAIN (the iteration counter / Philox offset is block 0's) */
     double* stats;               /* C * IRS_STAT_SIZE doubles */
     float* gmm_table;            /* C * 16 floats: per chain (lw[8], prec[8]) after that chain's update */
     double* partials;            /* irs_sgld_partials_doubles() doubles */
-    unsigned int* counters;      /* C + 8 zero-initialised unsigned ints */
+    unsigned int* counters;      /* C + 8 zero-initialised unsigned ints (left zero on return) */
     /* only with cfg->ffd_cps[0] > 0 */
     float* ffd_dense;            /* (C,3,V) dense velocity field of the control points */
     float* ffd_grad;             /* (C,3,V) its gradient */
@@ -283,7 +293,8 @@ typedef struct irs_sgld_buffers {
 
 size_t irs_sgld_partials_doubles(const irs_sgld_config* cfg);
 
-/* enqueue one transition on `stream` (about 45 + 2 C kernel launches, 7 more with the FFD; capturable in a CUDA graph) */
+/* enqueue one transition on `stream` (about 46 kernel launches for any number of chains, 7 more with the FFD; capturable
+ * in a CUDA graph) */
 int irs_sgld_step(const irs_sgld_config* cfg, const irs_sgld_buffers* buf, void* stream);
 
 /* Profiling aid: one eager transition with a CUDA event between stages; synchronises the stream and writes the

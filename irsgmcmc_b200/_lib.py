@@ -26,6 +26,7 @@ HYPER_GMM_BETA_POW, HYPER_REG_BETA_POW = 57, 59
 STAT_ALPHA, STAT_DATA, STAT_REG, STAT_ENERGY, STAT_NLL_PRE, STAT_REG_COEF = 0, 1, 2, 3, 4, 5
 
 DATA_LCC, DATA_SSD = 0, 1
+HYPER_MODES = {'reference': 0, 'per_chain': 1, 'frozen': 2}
 REG_L2, REG_LOGNORMAL = 0, 1
 
 
@@ -34,7 +35,7 @@ class SgldConfig(ctypes.Structure):
                 ('chain_offset', ctypes.c_int), ('data_term', ctypes.c_int), ('K', ctypes.c_int),
                 ('lcc_s', ctypes.c_int), ('reg_type', ctypes.c_int), ('reg_learnable', ctypes.c_int),
                 ('n_taps', ctypes.c_int), ('svf_steps', ctypes.c_int), ('virtual_decimation', ctypes.c_int),
-                ('use_jitter', ctypes.c_int), ('gather_radius_max', ctypes.c_int), ('reserved0', ctypes.c_int),
+                ('use_jitter', ctypes.c_int), ('gather_radius_max', ctypes.c_int), ('hyper_mode', ctypes.c_int),
                 ('taps', ctypes.c_float * 16),
                 ('tau', ctypes.c_double), ('jitter_alpha', ctypes.c_double), ('w_reg', ctypes.c_double),
                 ('dof', ctypes.c_double),
@@ -120,7 +121,7 @@ def load():
     for name, (restype, argtypes) in SYMBOLS.items():
         fn = getattr(lib, name)
         fn.restype, fn.argtypes = restype, argtypes
-    if lib.irs_abi_version() != 3:
+    if lib.irs_abi_version() != 4:
         raise RuntimeError('libirsgmcmc.so ABI version mismatch')
     _lib = lib
     return lib

@@ -407,6 +407,201 @@ gmm_stats_b_kernel(const float* __restrict__ r, double* __restrict__ hyper, IrsH
     stats_row[IRS_STAT_NLL_PRE] = totals[IRS_SUM_NLL];
 }
 
+// ---- all chains in ONE launch ----------------------------------------------------------------------------------------------
+// The reference walks the chains in order and lets every chain step the SHARED mixture before the next one evaluates it
+// (trainer/trainer.py:316-327): a chain of C dependent reductions.  As 2 C launches that is pure latency for small volumes
+// (64 chains at 64^3: 24 % of the transition).  Here one persistent kernel (one CTA per SM, all resident) walks the chains:
+// per chain every CTA reduces its share, the last CTA to arrive (irs_grid_sum) computes the virtual decimation factor, steps
+// Adam, writes the chain's table and releases a ticket in global memory; the other CTAs wait for the ticket and go on with
+// the next chain under the updated parameters.  The lag-1 products of virtual decimation are formed from residuals
+// re-evaluated at the three forward neighbours (13 mixture evaluations per four voxels instead of 4) -- no residual field
+// round trip, hence ONE grid-wide synchronisation per chain instead of two launches.
+// SERIAL = false: the chains do not depend on each other (hyper_mode per_chain: a parameter block per chain; frozen: no
+// Adam step at all) -- blockIdx.y = chain, no tickets.
+__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u32(unsigned int* p, unsigned int v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+constexpr int WALK_T = 512;        // threads per CTA
+constexpr int WALK_PL = 4;         // planes per brick: 128 threads (= 512 voxels of one plane) per plane
+
+// Sums of one chain over this CTA's share of the volume.  Vector path (W divides 512): the CTA walks over bricks of
+// 4 planes x 512/W rows x W voxels, one float4 per thread; the residuals r of a brick go through shared memory, so the
+// lag-1 products along x, y and z read their forward neighbour from there and only the brick's last row / last plane
+// re-evaluates the mixture at the neighbour (1 + W/512 + 1/4 evaluations per voxel instead of 4).
+template <int KK>
+__device__ __forceinline__ void gmm_chain_accumulate(const IrsGmm& gl, const float* __restrict__ z,
+                                                     const unsigned char* __restrict__ mask, bool vd, IrsDims d, int block,
+                                                     int nblocks, float (&acc)[IRS_SUM_COUNT], float4* __restrict__ R) {
+    const int V = (int)d.V(), sy = d.W, sz = d.W * d.H;
+    auto own = [&](float zi, bool on) {   // all sums of one voxel (branch-free: off-mask results are discarded); returns r
+        float rho[KK], wp;
+        const float lp = irs_gmm_eval_t<KK>(gl, zi, rho, wp);
+        const float z2 = zi * zi, r = on ? z2 * wp : 0.f;
+        acc[IRS_SUM_NLL] -= on ? lp : 0.f;
+        acc[IRS_SUM_RR] += r * r;
+#pragma unroll
+        for (int k = 0; k < KK; ++k) if (k < gl.K) {
+            acc[IRS_SUM_RHO + k] += on ? rho[k] : 0.f;
+            acc[IRS_SUM_Q + k] += on ? rho[k] * z2 * gl.prec[k] : 0.f;
+        }
+        return r;
+    };
+    auto res = [&](float zi) {   // residual only (a forward neighbour outside the brick)
+        float rho[KK], wp;
+        irs_gmm_eval_t<KK>(gl, zi, rho, wp);
+        return zi * zi * wp;
+    };
+    // sum_e r_e * r(neighbour e) with the neighbours at j: the four evaluations run side by side (the loop is bound by the
+    // latency of the exp / log chains, not by issue slots)
+    auto halo4 = [&](int j, float r0, float r1, float r2, float r3) {
+        const uchar4 n4 = *reinterpret_cast<const uchar4*>(mask + j);
+        if (!(n4.x | n4.y | n4.z | n4.w)) return 0.f;
+        const float4 q = __ldg(reinterpret_cast<const float4*>(z + j));
+        const float q0 = res(q.x), q1 = res(q.y), q2 = res(q.z), q3 = res(q.w);
+        return (n4.x ? r0 * q0 : 0.f) + (n4.y ? r1 * q1 : 0.f) + (n4.z ? r2 * q2 : 0.f) + (n4.w ? r3 * q3 : 0.f);
+    };
+    const bool vec = d.W >= 4 && (512 % d.W) == 0 && blockDim.x == WALK_T &&
+                     ((reinterpret_cast<uintptr_t>(z) | reinterpret_cast<uintptr_t>(mask)) & 15) == 0;
+    if (vec) {
+        const int w4 = d.W / 4, rows = 512 / d.W;                 // float4 per row, rows of a plane per brick
+        const int zz = threadIdx.x >> 7, u = threadIdx.x & 127, row = u / w4, x4 = u - row * w4;
+        const int by = (d.H + rows - 1) / rows, bz = (d.D + WALK_PL - 1) / WALK_PL;
+        for (int brick = block; brick < by * bz; brick += nblocks) {
+            const int y = (brick % by) * rows + row, zc = (brick / by) * WALK_PL + zz;
+            const bool valid = y < d.H && zc < d.D;
+            const int i = (zc * d.H + y) * d.W + 4 * x4;
+            float4 r4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (valid) {
+                const uchar4 m4 = *reinterpret_cast<const uchar4*>(mask + i);
+                if (m4.x | m4.y | m4.z | m4.w) {
+                    const float4 z4 = __ldg(reinterpret_cast<const float4*>(z + i));
+                    r4.x = own(z4.x, m4.x != 0);
+                    r4.y = own(z4.y, m4.y != 0);
+                    r4.z = own(z4.z, m4.z != 0);
+                    r4.w = own(z4.w, m4.w != 0);
+                }
+            }
+            if (!vd) continue;
+            R[threadIdx.x] = r4;
+            __syncthreads();
+            if (r4.x != 0.f || r4.y != 0.f || r4.z != 0.f || r4.w != 0.f) {   // an exactly zero residual contributes nothing
+                const float nx = x4 + 1 < w4 ? R[threadIdx.x + 1].x : 0.f;
+                acc[IRS_SUM_RW] += r4.x * r4.y + r4.y * r4.z + r4.z * r4.w + r4.w * nx;
+                if (y < d.H - 1) {
+                    if (row + 1 < rows) {
+                        const float4 q = R[threadIdx.x + w4];
+                        acc[IRS_SUM_RH] += r4.x * q.x + r4.y * q.y + r4.z * q.z + r4.w * q.w;
+                    } else {
+                        acc[IRS_SUM_RH] += halo4(i + sy, r4.x, r4.y, r4.z, r4.w);
+                    }
+                }
+                if (zc < d.D - 1) {
+                    if (zz + 1 < WALK_PL) {
+                        const float4 q = R[threadIdx.x + 128];
+                        acc[IRS_SUM_RD] += r4.x * q.x + r4.y * q.y + r4.z * q.z + r4.w * q.w;
+                    } else {
+                        acc[IRS_SUM_RD] += halo4(i + sz, r4.x, r4.y, r4.z, r4.w);
+                    }
+                }
+            }
+            __syncthreads();   // R is rewritten by the next brick
+        }
+    } else {
+        for (int i = block * blockDim.x + threadIdx.x; i < V; i += nblocks * blockDim.x) {
+            if (!mask[i]) continue;
+            const float r = own(z[i], true);
+            if (!vd) continue;
+            const int x = i % d.W, y = (i / d.W) % d.H, zc = i / sz;
+            if (x < d.W - 1 && mask[i + 1]) acc[IRS_SUM_RW] += r * res(z[i + 1]);
+            if (y < d.H - 1 && mask[i + sy]) acc[IRS_SUM_RH] += r * res(z[i + sy]);
+            if (zc < d.D - 1 && mask[i + sz]) acc[IRS_SUM_RD] += r * res(z[i + sz]);
+        }
+    }
+}
+
+template <bool SERIAL>
+__global__ void __launch_bounds__(WALK_T, 1)
+gmm_chain_walk_kernel(const float* __restrict__ z_all, const unsigned char* __restrict__ mask, double* __restrict__ hyper_all,
+                      long long hyper_stride, IrsHyperCfg cfg, int frozen, double* __restrict__ partials_all,
+                      long long partials_stride, unsigned int* __restrict__ counters, unsigned int* __restrict__ ticket,
+                      double* __restrict__ stats_all, float* __restrict__ tables_all, int C, IrsDims d) {
+    __shared__ IrsGmm g;
+    __shared__ double sh[IRS_SUM_COUNT * 32];
+    __shared__ double total[IRS_SUM_COUNT];
+    __shared__ float4 R[WALK_T];
+    __shared__ double alpha_sh;
+    const long long V = d.V();
+    const int c_first = SERIAL ? 0 : blockIdx.y, c_end = SERIAL ? C : blockIdx.y + 1;
+    const int n_used = 5 + IRS_MAX_K + cfg.K;   // the RHO block is padded to IRS_MAX_K slots; Q slots beyond K stay unused
+    for (int c = c_first; c < c_end; ++c) {
+        double* hyper = hyper_all + (size_t)c * hyper_stride;
+        if (SERIAL && c > 0) {
+            // chain c - 1 has stepped the shared mixture; its table (written before the ticket was released) is the one
+            // this chain evaluates with
+            if (threadIdx.x == 0) while (ld_acquire_u32(ticket) < (unsigned int)c) {}
+            __syncthreads();
+            if (threadIdx.x < 2 * IRS_MAX_K) {
+                const float t = __ldcg(tables_all + (size_t)(c - 1) * 16 + threadIdx.x);
+                if (threadIdx.x < IRS_MAX_K) g.lw[threadIdx.x] = t; else g.prec[threadIdx.x - IRS_MAX_K] = t;
+            }
+            if (threadIdx.x == 0) g.K = cfg.K;
+        } else if (threadIdx.x == 0) {
+            irs_gmm_table(hyper + IRS_HYPER_LOG_STD, hyper + IRS_HYPER_LOGITS, cfg.K, g);
+        }
+        __syncthreads();
+        const IrsGmm gl = g;
+        float acc[IRS_SUM_COUNT];
+#pragma unroll
+        for (int k = 0; k < IRS_SUM_COUNT; ++k) acc[k] = 0.f;
+        const float* z = z_all + (size_t)c * V;
+        if (gl.K <= 4) gmm_chain_accumulate<4>(gl, z, mask, cfg.virtual_decimation != 0, d, blockIdx.x, gridDim.x, acc, R);
+        else gmm_chain_accumulate<IRS_MAX_K>(gl, z, mask, cfg.virtual_decimation != 0, d, blockIdx.x, gridDim.x, acc, R);
+        double blk[IRS_SUM_COUNT];
+        irs_block_sum<IRS_SUM_COUNT>(acc, blk, sh);
+        if (irs_grid_sum<IRS_SUM_COUNT>(blk, partials_all + (size_t)c * partials_stride, counters + c, total, n_used)) {
+            // the last CTA to arrive: virtual decimation factor, Adam step (one lane per parameter), the chain's table
+            if (threadIdx.x < 32) {
+                const int lane = threadIdx.x;
+                const double alpha32 = irs_round_f32(cfg.virtual_decimation ? irs_vd_alpha(total, cfg.n_mask) : 1.0);
+                if (!frozen) {
+                    IrsAdamCtx ctx;
+                    irs_gmm_adam_context(hyper, cfg, total, ctx);
+                    __syncwarp();
+                    if (lane < 2 * cfg.K) irs_gmm_adam_param(hyper, cfg, total, alpha32, ctx, lane);
+                    __syncwarp();
+                    if (lane == 0) irs_gmm_adam_advance(hyper, cfg);
+                    __syncwarp();
+                }
+                float logpi[IRS_MAX_K];
+                irs_log_proportions(hyper + IRS_HYPER_LOGITS, cfg.K, logpi);
+                float* table_out = tables_all + (size_t)c * 16;
+                if (lane < IRS_MAX_K) {   // irs_gmm_table, one lane per component
+                    const float lsk = lane < cfg.K ? (float)hyper[IRS_HYPER_LOG_STD + lane] : 0.f;
+                    table_out[lane] = lane < cfg.K ? logpi[lane] - lsk : -INFINITY;
+                    table_out[IRS_MAX_K + lane] = lane < cfg.K ? expf(-2.0f * lsk) : 0.f;
+                }
+                if (lane == 0) {
+                    double* stats_row = stats_all + (size_t)c * IRS_STAT_SIZE;
+                    stats_row[IRS_STAT_ALPHA] = alpha32;
+                    stats_row[IRS_STAT_NLL_PRE] = total[IRS_SUM_NLL];
+                }
+                if (SERIAL) {
+                    __threadfence();
+                    __syncwarp();
+                    if (lane == 0) st_release_u32(ticket, c + 1 < C ? (unsigned int)(c + 1) : 0u);   // the last chain leaves it zero
+                }
+            }
+        }
+        __syncthreads();   // `g`, `sh`, `total`, `R` are reused by the next chain
+    }
+}
+
 // g_z = alpha_c z sum_k rho_k prec_k on the mask (dL/dz of alpha * NLL with the chain's UPDATED mixture), and the
 // data term alpha_c * NLL_c for logging
 __global__ void __launch_bounds__(256)
@@ -595,6 +790,38 @@ int irs_launch_gmm_stats_step(const float* z, const unsigned char* mask, double*
                                                                  stats_row, table_out, nullptr, V);
     gmm_stats_b_kernel<<<irs_data_blocks(d), 256, 0, st>>>(r_scratch, hyper, cfg, partials, counter, totals, stats_row,
                                                           table_out, d);
+    return (int)cudaGetLastError();
+}
+
+// every chain's mixture statistics / virtual decimation factor / Adam step / table in one launch.
+// hyper_stride = 0: the shared mixture of the reference, chains in order (persistent grid, tickets); otherwise one parameter
+// block per chain (or `frozen`: no Adam step), chains in parallel.  counters: C per-chain counters followed by the ticket.
+int irs_launch_gmm_chain_walk(const float* z, const unsigned char* mask, double* hyper, long long hyper_stride,
+                              const IrsHyperCfg& cfg, int frozen, double* partials, long long partials_stride,
+                              unsigned int* counters, double* stats, float* tables, int C, IrsDims d, cudaStream_t st) {
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms < 1) sms = 148;
+    }
+    const long long per_pass = (long long)WALK_T * 4;          // voxels one CTA covers per sweep iteration
+    long long want = (d.V() + per_pass - 1) / per_pass;
+    const bool serial = hyper_stride == 0 && !frozen;
+    if (serial) {
+        const int G = (int)(want < sms ? want : sms);           // all CTAs resident: they wait for each other
+        if ((long long)G * IRS_SUM_COUNT > partials_stride) return IRS_ERR_WORKSPACE;
+        gmm_chain_walk_kernel<true><<<G, WALK_T, 0, st>>>(z, mask, hyper, 0, cfg, 0, partials, partials_stride, counters,
+                                                          counters + C, stats, tables, C, d);
+    } else {
+        long long per_chain = (2LL * sms + C - 1) / C;          // about two waves of CTAs over all chains
+        if (per_chain < 1) per_chain = 1;
+        if (want > per_chain) want = per_chain;
+        if (want * IRS_SUM_COUNT > partials_stride) return IRS_ERR_WORKSPACE;
+        dim3 grid((unsigned)want, C);
+        gmm_chain_walk_kernel<false><<<grid, WALK_T, 0, st>>>(z, mask, hyper, hyper_stride, cfg, frozen, partials,
+                                                             partials_stride, counters, counters + C, stats, tables, C, d);
+    }
     return (int)cudaGetLastError();
 }
 

@@ -56,10 +56,13 @@ IRS_HD void irs_gmm_table(const double* log_std, const double* logits, int K, Ir
 // propagates NaN, whereas fminf(1, NaN) returns 1 (IEEE minNum) -- hence the explicit select.  A correlation of exactly 0
 // gives -log(0) = +inf -> clamped to 1, in both.
 IRS_HD double irs_vd_alpha(const double* sums, double n_mask) {
-    const double var = sums[IRS_SUM_RR] / n_mask;
+    // corr_a = (sum r r_+ / n) / (sum r^2 / n): n cancels; one fp64 reciprocal instead of seven divisions (this runs on the
+    // critical path between two chains)
+    (void)n_mask;
+    const double inv_rr = 1.0 / sums[IRS_SUM_RR];
     float prod = 1.f;
     for (int a = 0; a < 3; ++a) {
-        const float corr = (float)((sums[IRS_SUM_RD + a] / n_mask) / var);
+        const float corr = (float)(sums[IRS_SUM_RD + a] * inv_rr);
         const float t = -0.63661977236758134f * logf(corr);
         prod *= (t != t) ? t : fminf(1.f, t);
     }
@@ -95,32 +98,59 @@ IRS_HD void irs_adam_bias(double* beta_pow, double b1, double b2, double step_be
 
 // One Adam step on (log_std, logits) with loss  alpha * NLL - sum_k logN(log_std_k; loc, scale) - logDir(log pi; a)
 // (reference trainer/trainer.py:68-77).  `sums` were reduced with the parameters currently in `hyper`.
-IRS_HD void irs_gmm_adam_step(double* hyper, const IrsHyperCfg& cfg, const double* sums, double alpha) {
-    const int K = cfg.K;
-    double* ls = hyper + IRS_HYPER_LOG_STD;
-    double* lg = hyper + IRS_HYPER_LOGITS;
+// Split per parameter so that a warp can update the 2 K parameters side by side (one lane each): every quantity a lane needs
+// is computed from the PRE-update values with the same operations in the same order as the serial loop below, so both give
+// bit-identical results.
+struct IrsAdamCtx {
+    double decay, bc1, bc2, rho_total;
     float logpi[IRS_MAX_K];
-    double g_ls[IRS_MAX_K], g_lg[IRS_MAX_K];
-    irs_log_proportions(lg, K, logpi);
-    double rho_total = 0.0;
-    for (int k = 0; k < K; ++k) rho_total += sums[IRS_SUM_RHO + k];
-    const double inv_s2 = 1.0 / (cfg.gmm_prior_scale * cfg.gmm_prior_scale);
-    for (int k = 0; k < K; ++k) {
-        const double pi_k = (double)expf(logpi[k]);
-        g_ls[k] = alpha * (sums[IRS_SUM_RHO + k] - sums[IRS_SUM_Q + k]) + (ls[k] - cfg.gmm_prior_loc) * inv_s2;
-        g_lg[k] = alpha * (-sums[IRS_SUM_RHO + k] + pi_k * rho_total) - (cfg.dirichlet_alpha - 1.0) * (1.0 - K * pi_k);
-    }
+};
+
+// everything shared by the 2 K updates, from the pre-update state (does not write)
+IRS_HD void irs_gmm_adam_context(const double* hyper, const IrsHyperCfg& cfg, const double* sums, IrsAdamCtx& ctx) {
+    irs_log_proportions(hyper + IRS_HYPER_LOGITS, cfg.K, ctx.logpi);
+    ctx.rho_total = 0.0;
+    for (int k = 0; k < cfg.K; ++k) ctx.rho_total += sums[IRS_SUM_RHO + k];
     const double step0 = hyper[IRS_HYPER_GMM_STEP];
-    const double decay = 1.0 + step0 * cfg.lr_decay;
+    ctx.decay = 1.0 + step0 * cfg.lr_decay;
+    double b1p = hyper[IRS_HYPER_GMM_BETA_POW], b2p = hyper[IRS_HYPER_GMM_BETA_POW + 1];
+    if (step0 == 0.0) { b1p = 1.0; b2p = 1.0; }
+    ctx.bc1 = 1.0 - b1p * cfg.beta1;
+    ctx.bc2 = 1.0 - b2p * cfg.beta2;
+}
+
+// update of parameter `idx`: 0 .. K-1 = log_std[k], K .. 2K-1 = logits[k]
+IRS_HD void irs_gmm_adam_param(double* hyper, const IrsHyperCfg& cfg, const double* sums, double alpha, const IrsAdamCtx& ctx,
+                               int idx) {
+    const int K = cfg.K, k = idx < K ? idx : idx - K;
+    if (idx < K) {
+        double* ls = hyper + IRS_HYPER_LOG_STD;
+        const double inv_s2 = 1.0 / (cfg.gmm_prior_scale * cfg.gmm_prior_scale);
+        const double g = alpha * (sums[IRS_SUM_RHO + k] - sums[IRS_SUM_Q + k]) + (ls[k] - cfg.gmm_prior_loc) * inv_s2;
+        irs_adam_update(ls[k], hyper[IRS_HYPER_M_LOG_STD + k], hyper[IRS_HYPER_V_LOG_STD + k], g, cfg.lr_log_std, ctx.decay,
+                        ctx.bc1, ctx.bc2, cfg.beta1, cfg.beta2, cfg.eps, true);
+    } else {
+        double* lg = hyper + IRS_HYPER_LOGITS;
+        const double pi_k = (double)expf(ctx.logpi[k]);
+        const double g = alpha * (-sums[IRS_SUM_RHO + k] + pi_k * ctx.rho_total) - (cfg.dirichlet_alpha - 1.0) * (1.0 - K * pi_k);
+        irs_adam_update(lg[k], hyper[IRS_HYPER_M_LOGITS + k], hyper[IRS_HYPER_V_LOGITS + k], g, cfg.lr_logits, ctx.decay,
+                        ctx.bc1, ctx.bc2, cfg.beta1, cfg.beta2, cfg.eps, true);
+    }
+}
+
+// step counter and the running powers of beta (after every parameter has been updated)
+IRS_HD void irs_gmm_adam_advance(double* hyper, const IrsHyperCfg& cfg) {
+    const double step0 = hyper[IRS_HYPER_GMM_STEP];
     double bc1, bc2;
     irs_adam_bias(hyper + IRS_HYPER_GMM_BETA_POW, cfg.beta1, cfg.beta2, step0, bc1, bc2);
-    for (int k = 0; k < K; ++k) {
-        irs_adam_update(ls[k], hyper[IRS_HYPER_M_LOG_STD + k], hyper[IRS_HYPER_V_LOG_STD + k], g_ls[k],
-                        cfg.lr_log_std, decay, bc1, bc2, cfg.beta1, cfg.beta2, cfg.eps, true);
-        irs_adam_update(lg[k], hyper[IRS_HYPER_M_LOGITS + k], hyper[IRS_HYPER_V_LOGITS + k], g_lg[k],
-                        cfg.lr_logits, decay, bc1, bc2, cfg.beta1, cfg.beta2, cfg.eps, true);
-    }
     hyper[IRS_HYPER_GMM_STEP] = step0 + 1.0;
+}
+
+IRS_HD void irs_gmm_adam_step(double* hyper, const IrsHyperCfg& cfg, const double* sums, double alpha) {
+    IrsAdamCtx ctx;
+    irs_gmm_adam_context(hyper, cfg, sums, ctx);
+    for (int idx = 0; idx < 2 * cfg.K; ++idx) irs_gmm_adam_param(hyper, cfg, sums, alpha, ctx, idx);
+    irs_gmm_adam_advance(hyper, cfg);
 }
 
 // Regulariser: per-chain loss value, the coefficient c_c = dL/dy_c that multiplies dE/dv in the field gradient, and one

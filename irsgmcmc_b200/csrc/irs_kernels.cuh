@@ -111,6 +111,9 @@ int irs_data_blocks(IrsDims d);
 int irs_launch_gmm_stats_step(const float* z, const unsigned char* mask, double* hyper, const IrsHyperCfg& cfg,
                               double* partials, unsigned int* counter, double* stats_row, float* table_out,
                               const double* alpha_fixed, float* r_scratch, double* totals, IrsDims d, cudaStream_t st);
+int irs_launch_gmm_chain_walk(const float* z, const unsigned char* mask, double* hyper, long long hyper_stride,
+                              const IrsHyperCfg& cfg, int frozen, double* partials, long long partials_stride,
+                              unsigned int* counters, double* stats, float* tables, int C, IrsDims d, cudaStream_t st);
 int irs_launch_vd_alpha(const float* z, const unsigned char* mask, double* hyper, const IrsHyperCfg& cfg,
                         double* partials, unsigned int* counter, double* stats_row, IrsDims d, cudaStream_t st);
 int irs_launch_gmm_init_params(double* hyper, const double* moments, int K, cudaStream_t st);

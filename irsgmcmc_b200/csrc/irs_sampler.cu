@@ -4,6 +4,8 @@
 // One call enqueues the whole iteration for all chains of this GPU on one stream; every scalar (virtual decimation
 // factors, mixture / regulariser hyper-parameters and their Adam state, the Philox offset) stays in device memory, so
 // the sequence has no host synchronisation and can be captured in a CUDA graph and replayed.
+#include <cstdlib>
+
 #include "irs_kernels.cuh"
 
 namespace {
@@ -18,20 +20,26 @@ ssd_residual_kernel(const float* __restrict__ fixed, const float* __restrict__ w
 }
 
 // regulariser loss / coefficient / Adam step for all chains, then advance the Philox offset
-__global__ void __launch_bounds__(128) reg_hyper_kernel(double* hyper, IrsHyperCfg cfg, int C, double* stats) {
+// mode: IRS_HYPER_REFERENCE (chain-summed gradients, one step on the shared parameters), IRS_HYPER_PER_CHAIN (every chain
+// steps its own block), IRS_HYPER_FROZEN (losses and coefficients only)
+__global__ void __launch_bounds__(128) reg_hyper_kernel(double* hyper, IrsHyperCfg cfg, int C, double* stats, int mode) {
     __shared__ double s0[128], s1[128];
     double g0 = 0.0, g1 = 0.0;
     for (int c = threadIdx.x; c < C; c += blockDim.x) {   // chains in parallel: each needs a log / exp in fp64
         double a, b;
-        irs_reg_chain_terms(hyper, cfg, stats + (size_t)c * IRS_STAT_SIZE, a, b);
+        double* h = mode == IRS_HYPER_PER_CHAIN ? hyper + (size_t)c * IRS_HYPER_SIZE : hyper;
+        irs_reg_chain_terms(h, cfg, stats + (size_t)c * IRS_STAT_SIZE, a, b);
+        if (mode == IRS_HYPER_PER_CHAIN) irs_reg_adam(h, cfg, a, b);
         g0 += a; g1 += b;
     }
     s0[threadIdx.x] = g0; s1[threadIdx.x] = g1;
     __syncthreads();
     if (threadIdx.x != 0) return;
-    g0 = 0.0; g1 = 0.0;
-    for (int t = 0; t < blockDim.x; ++t) { g0 += s0[t]; g1 += s1[t]; }   // fixed order: deterministic
-    irs_reg_adam(hyper, cfg, g0, g1);
+    if (mode == IRS_HYPER_REFERENCE) {
+        g0 = 0.0; g1 = 0.0;
+        for (int t = 0; t < blockDim.x; ++t) { g0 += s0[t]; g1 += s1[t]; }   // fixed order: deterministic
+        irs_reg_adam(hyper, cfg, g0, g1);
+    }
     hyper[IRS_HYPER_ITER] += 1.0;
 }
 
@@ -86,6 +94,7 @@ int check_config(const irs_sgld_config* c) {
     if (c->n_taps < 0 || c->n_taps > IRS_MAX_TAPS || (c->n_taps > 0 && c->n_taps % 2 == 0)) return IRS_ERR_BAD_ARG;
     if (c->svf_steps < 1 || c->svf_steps > IRS_MAX_SVF_STEPS) return IRS_ERR_BAD_ARG;
     if (!(c->n_mask >= 2.0) || !(c->tau >= 0.0) || c->gather_radius_max < 0) return IRS_ERR_BAD_ARG;
+    if (c->hyper_mode < IRS_HYPER_REFERENCE || c->hyper_mode > IRS_HYPER_FROZEN) return IRS_ERR_BAD_ARG;
     if (c->ffd_cps[0] != 0 || c->ffd_cps[1] != 0 || c->ffd_cps[2] != 0) {
         const int n[3] = {c->D, c->H, c->W};
         for (int a = 0; a < 3; ++a) {
@@ -99,6 +108,17 @@ int check_config(const irs_sgld_config* c) {
 }
 
 inline bool has_ffd(const irs_sgld_config* c) { return c->ffd_cps[0] > 0; }
+// one persistent launch for the mixture step of all chains (irs_launch_gmm_chain_walk) instead of two launches per chain.
+// Always for the chain-parallel hyper modes.  In the reference mode (chains in order on the shared mixture) the walk wins where
+// a chain is small and the two launches are pure latency (measured, 64 chains: 64^3 1.45 vs 1.77 ms; 128^3 3.13 vs 2.56 ms --
+// there one CTA per SM under-fills the machine), hence the volume threshold.  IRS_GMM_WALK=0 / 1 forces a side (development).
+inline bool gmm_walk_enabled(const irs_sgld_config* c) {
+    static int env = -2;
+    if (env == -2) { const char* e = getenv("IRS_GMM_WALK"); env = e ? (atoi(e) != 0 ? 1 : 0) : -1; }
+    if (c->hyper_mode != IRS_HYPER_REFERENCE) return true;
+    if (env >= 0) return env == 1;
+    return (long long)c->D * c->H * c->W <= 96LL * 96 * 96;
+}
 // the grid the chain state lives on: the control grid with the FFD, the image grid otherwise
 inline IrsDims state_dims(const irs_sgld_config* c) {
     return has_ffd(c) ? IrsDims{c->ffd_grid[0], c->ffd_grid[1], c->ffd_grid[2]} : IrsDims{c->D, c->H, c->W};
@@ -127,7 +147,7 @@ extern "C" int irs_sgld_launches_per_step(const irs_sgld_config* c) {
     n += c->svf_steps > 4 ? 4 : c->svf_steps - 1; // cell maps behind the last four steps (exit at once below one voxel)
     n += 1;                                      // warp
     n += c->data_term == IRS_DATA_LCC ? 2 : 1;   // LCC boxes / SSD residual
-    n += c->C * (c->virtual_decimation ? 2 : 1); // per-chain mixture statistics (+ VD lag sums) + Adam
+    n += gmm_walk_enabled(c) ? 1 : c->C * (c->virtual_decimation ? 2 : 1);   // mixture statistics + VD factor + Adam of all chains
     n += 1;                                      // dL/dz
     n += c->data_term == IRS_DATA_LCC ? 2 : 0;   // LCC adjoint boxes
     n += 1;                                      // warp grid gradient
@@ -219,11 +239,17 @@ static int sgld_step_impl(const irs_sgld_config* cfg, const irs_sgld_buffers* b,
     mark(tm, st);
     // (6) per chain, in order: VD factor, Adam step on the shared mixture          trainer.py:316-318
     const size_t per_chain = (size_t)irs_data_blocks(d) * IRS_SUM_COUNT;
-    for (int c = 0; c < C; ++c) {
-        IRS_TRY(irs_launch_gmm_stats_step(b->z + (size_t)c * V, b->mask, b->hyper, hc, b->partials + c * per_chain,
-                                          b->counters + c, b->stats + (size_t)c * IRS_STAT_SIZE,
-                                          b->gmm_table + (size_t)c * 16, nullptr, b->scratch2 + (size_t)c * V,
-                                          b->hyper + IRS_HYPER_SCRATCH, d, st));
+    if (gmm_walk_enabled(cfg)) {
+        IRS_TRY(irs_launch_gmm_chain_walk(b->z, b->mask, b->hyper, cfg->hyper_mode == IRS_HYPER_PER_CHAIN ? IRS_HYPER_SIZE : 0,
+                                          hc, cfg->hyper_mode == IRS_HYPER_FROZEN, b->partials, (long long)per_chain,
+                                          b->counters, b->stats, b->gmm_table, C, d, st));
+    } else {
+        for (int c = 0; c < C; ++c) {
+            IRS_TRY(irs_launch_gmm_stats_step(b->z + (size_t)c * V, b->mask, b->hyper, hc, b->partials + c * per_chain,
+                                              b->counters + c, b->stats + (size_t)c * IRS_STAT_SIZE,
+                                              b->gmm_table + (size_t)c * 16, nullptr, b->scratch2 + (size_t)c * V,
+                                              b->hyper + IRS_HYPER_SCRATCH, d, st));
+        }
     }
 
     mark(tm, st);
@@ -244,7 +270,7 @@ static int sgld_step_impl(const irs_sgld_config* cfg, const irs_sgld_buffers* b,
 
     mark(tm, st);
     // (9) regulariser loss, coefficient and hyper-parameter Adam step              trainer.py:311,334-339,353-354
-    reg_hyper_kernel<<<1, 128, 0, st>>>(b->hyper, hc, C, b->stats);
+    reg_hyper_kernel<<<1, 128, 0, st>>>(b->hyper, hc, C, b->stats, cfg->hyper_mode);
     IRS_LAUNCH_CHECK();
 
     mark(tm, st);

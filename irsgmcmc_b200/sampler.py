@@ -28,7 +28,7 @@ class SGLDConfig:
                  uniform_noise=True, uniform_noise_magnitude=0.1, virtual_decimation=True, lr_log_std=0.2,
                  lr_logits=0.2, lr_reg=0.01, lr_decay=1e-3, betas=(0.9, 0.999), adam_eps=1e-8,
                  gmm_scale_prior=(0.0, 2.3), dirichlet_alpha=0.5, reg_scale_prior=(2.8, 5.0), gather_radius_max=2,
-                 seed=123, transformation='SVF_3D', cps=None):
+                 seed=123, transformation='SVF_3D', cps=None, hyper_mode='reference'):
         if data_loss not in ('lcc', 'ssd'):
             raise ValueError(f'unknown data loss: {data_loss}')
         if transformation not in ('SVF_3D', 'SVFFD_3D'):
@@ -37,6 +37,11 @@ class SGLDConfig:
             if cps is None or len(cps) != 3 or not all(1 <= int(c) <= 8 for c in cps):
                 raise ValueError('SVFFD_3D needs cps = three control point spacings between 1 and 8')
             cps = tuple(int(c) for c in cps)
+        # 'reference': one mixture / regulariser parameter set shared by all chains, stepped chain after chain (the reference's
+        # loop, trainer/trainer.py:316-327,353-354); 'per_chain': every chain owns its parameters (= an independent reference run
+        # with one chain each); 'frozen': shared parameters, no Adam steps.  The last two have no dependency between chains.
+        if hyper_mode not in _lib.HYPER_MODES:
+            raise ValueError(f'unknown hyper_mode: {hyper_mode} (one of {sorted(_lib.HYPER_MODES)})')
         if reg_loss not in ('RegLoss_LogNormal', 'RegLoss_L2'):
             raise ValueError(f'unknown regularisation loss: {reg_loss}')
         self.__dict__.update(locals())
@@ -124,7 +129,9 @@ class SGLDSampler:
             self._ffd_scratch = torch.empty(C, 3, gD, gH, gW, **f32)
             self._ffd_work = torch.empty(int(self.lib.irs_ffd_work_floats(C, gD, gH, gW, D, H, W)), **f32)
         self._maxabs = torch.zeros(int(self.lib.irs_svf_maxabs_floats(C, D, H, W, cfg.svf_steps)), **f32)
-        self.hyper = torch.zeros(_lib.HYPER_SIZE, device=dev, dtype=torch.float64)
+        self.per_chain = cfg.hyper_mode == 'per_chain'
+        # (HYPER_SIZE,) shared block; (C, HYPER_SIZE) with hyper_mode='per_chain' (block 0 carries the iteration counter)
+        self.hyper = torch.zeros((C, _lib.HYPER_SIZE) if self.per_chain else (_lib.HYPER_SIZE,), device=dev, dtype=torch.float64)
         self.stats = torch.zeros(C, _lib.STAT_SIZE, device=dev, dtype=torch.float64)
         self._gmm_table = torch.zeros(C, 16, **f32)
         self._counters = torch.zeros(C + 8, device=dev, dtype=torch.int32)
@@ -134,10 +141,10 @@ class SGLDSampler:
         self.dof = 3.0 * V
         if cfg.reg_loss == 'RegLoss_LogNormal':
             loc, log_scale = lognormal_init(cfg.w_reg, self.dof)
-            self.hyper[_lib.HYPER_REG_P] = loc
-            self.hyper[_lib.HYPER_REG_P + 1] = log_scale
+            self.hyper[..., _lib.HYPER_REG_P] = loc
+            self.hyper[..., _lib.HYPER_REG_P + 1] = log_scale
         else:
-            self.hyper[_lib.HYPER_REG_P] = float(np.float32(math.log(cfg.w_reg)))
+            self.hyper[..., _lib.HYPER_REG_P] = float(np.float32(math.log(cfg.w_reg)))
 
         self._cconf = self._make_config()
         n_part = self.lib.irs_sgld_partials_doubles(ctypes.byref(self._cconf))
@@ -177,6 +184,7 @@ class SGLDSampler:
         c.virtual_decimation = int(cfg.virtual_decimation)
         c.use_jitter = int(cfg.uniform_noise)
         c.gather_radius_max = cfg.gather_radius_max
+        c.hyper_mode = _lib.HYPER_MODES[cfg.hyper_mode]
         c.tau, c.jitter_alpha, c.w_reg, c.dof = cfg.tau, cfg.uniform_noise_magnitude, cfg.w_reg, self.dof
         c.lr_log_std, c.lr_logits, c.lr_reg0, c.lr_reg1 = cfg.lr_log_std, cfg.lr_logits, cfg.lr_reg, cfg.lr_reg
         c.lr_decay, (c.beta1, c.beta2), c.adam_eps = cfg.lr_decay, cfg.betas, cfg.adam_eps
@@ -249,7 +257,7 @@ class SGLDSampler:
         K = self.cfg.no_components
         if sigma_hat is not None:
             ls = torch.linspace(math.log(sigma_hat / 100.0), math.log(sigma_hat * 5.0), steps=K)
-            self.hyper[_lib.HYPER_LOG_STD:_lib.HYPER_LOG_STD + K] = ls.double().to(self.device)
+            self.hyper[..., _lib.HYPER_LOG_STD:_lib.HYPER_LOG_STD + K] = ls.double().to(self.device)
             return
         if v_sample is None:
             v_sample = self.v[:1]
@@ -257,6 +265,8 @@ class SGLDSampler:
         b = self._buffers()
         _lib.check(self.lib.irs_sgld_gmm_init(ctypes.byref(self._cconf), ctypes.byref(b), _lib.ptr(v_sample), warm_up,
                                               _lib.stream()))
+        if self.per_chain:   # every chain starts from the same initialised mixture (and its warm-up Adam state)
+            self.hyper[1:] = self.hyper[0]
 
     # ------------------------------------------------------------------------------------------------------------------
     # checkpoint / resume (the reference has none -- a run that dies starts over)
@@ -425,13 +435,15 @@ class SGLDSampler:
                 'alpha': s[:, _lib.STAT_ALPHA].float(), 'reg_energy': s[:, _lib.STAT_ENERGY].float()}
 
     def gmm_parameters(self):
+        """(log_std, logits) of the mixture: (K,) each, or (C, K) with hyper_mode='per_chain'"""
         K = self.cfg.no_components
         h = self.hyper.cpu()
-        return h[_lib.HYPER_LOG_STD:_lib.HYPER_LOG_STD + K].float(), h[_lib.HYPER_LOGITS:_lib.HYPER_LOGITS + K].float()
+        return (h[..., _lib.HYPER_LOG_STD:_lib.HYPER_LOG_STD + K].float(),
+                h[..., _lib.HYPER_LOGITS:_lib.HYPER_LOGITS + K].float())
 
     def reg_parameters(self):
         h = self.hyper.cpu()
-        return h[_lib.HYPER_REG_P:_lib.HYPER_REG_P + 2]
+        return h[..., _lib.HYPER_REG_P:_lib.HYPER_REG_P + 2]
 
     def warp_segmentation(self, seg=None, transformation=None):
         """nearest-neighbour warp of the moving segmentation with the current transformations (trainer.py:419)"""

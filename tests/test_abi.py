@@ -32,7 +32,7 @@ def test_python_binding_covers_the_header(built):
 def test_version_and_error_strings(built):
     from irsgmcmc_b200 import _lib
     lib = _lib.load()
-    assert lib.irs_abi_version() == 3
+    assert lib.irs_abi_version() == 4
     assert lib.irs_error_string(0) == b'ok'
     assert b'bad argument' in lib.irs_error_string(-1) and b'unsupported' in lib.irs_error_string(-2)
 

@@ -318,3 +318,82 @@ def test_second_device_or_fresh_context_launch_configuration(built):
         outs.append(s.v.cpu())
     torch.cuda.set_device(0)
     assert torch.equal(outs[0], outs[1])
+
+
+# ---- hyper_mode: the chain-parallel alternatives to the reference's sequential shared-mixture loop ------------------------
+def _mode_sampler(mode, C, n, fixed, moving, vp, v0, chain_offset=0, **kw):
+    from irsgmcmc_b200.sampler import SGLDSampler, SGLDConfig
+    s = SGLDSampler(fixed, moving, C, SGLDConfig(hyper_mode=mode, **kw), device=DEV, chain_offset=chain_offset)
+    s.set_state(v0, torch.exp(0.5 * vp['log_var']))
+    s.init_gmm(sigma_hat=0.7)
+    return s
+
+
+@pytest.mark.parametrize('data,reg', [('lcc', 'RegLoss_LogNormal'), ('ssd', 'RegLoss_L2')])
+def test_hyper_mode_per_chain_equals_independent_single_chain_runs(built, data, reg):
+    """hyper_mode='per_chain': every chain owns its mixture / regulariser parameters and Adam state, i.e. chain c of a C-chain
+    sampler is the reference's loop (trainer/trainer.py:316-327,353-354) run with no_chains = 1 on that chain"""
+    from irsgmcmc_b200.data_loader.synthetic import make_pair
+    n, C, iters = 20, 3, 3
+    fixed, moving, vp = make_pair(n)
+    torch.manual_seed(3)
+    v0 = 0.8 * torch.randn(C, 3, n, n, n)
+    eps = [torch.randn(C, 3, n, n, n) for _ in range(iters)]
+    ju = [torch.rand(C, 3, n, n, n) for _ in range(iters)]
+    kw = dict(data_loss=data, reg_loss=reg, w_reg=1.6 if data == 'lcc' else 1.4)
+    multi = _mode_sampler('per_chain', C, n, fixed, moving, vp, v0, **kw)
+    singles = [_mode_sampler('reference', 1, n, fixed, moving, vp, v0[c:c + 1], **kw) for c in range(C)]
+    for it in range(iters):
+        multi.set_noise(eps[it], ju[it])
+        multi.step(1, use_graph=False)
+        for c, s in enumerate(singles):
+            s.set_noise(eps[it][c:c + 1], ju[it][c:c + 1])
+            s.step(1, use_graph=False)
+    torch.cuda.synchronize()
+    ls, lg = multi.gmm_parameters()
+    assert ls.shape == (C, multi.cfg.no_components)
+    for c, s in enumerate(singles):
+        assert rel(multi.v[c], s.v[0]) < 1e-5, (c, rel(multi.v[c], s.v[0]))
+        sl, sg = s.gmm_parameters()
+        assert rel(ls[c], sl) < 1e-5 and (lg[c] - sg).abs().max() < 1e-5
+        assert rel(multi.reg_parameters()[c], s.reg_parameters()) < 1e-6
+        assert rel(multi.stats[c], s.stats[0]) < 1e-5
+    # the chains really differ (the shared-mixture mode would have coupled them)
+    assert (ls[0] - ls[1]).abs().max() > 1e-6 or data == 'ssd'
+
+
+def test_hyper_mode_frozen_equals_reference_with_zero_learning_rates(built):
+    from irsgmcmc_b200.data_loader.synthetic import make_pair
+    n, C, iters = 20, 3, 3
+    fixed, moving, vp = make_pair(n)
+    torch.manual_seed(4)
+    v0 = 0.8 * torch.randn(C, 3, n, n, n)
+    frozen = _mode_sampler('frozen', C, n, fixed, moving, vp, v0)
+    ref = _mode_sampler('reference', C, n, fixed, moving, vp, v0, lr_log_std=0.0, lr_logits=0.0, lr_reg=0.0)
+    h0 = frozen.hyper.clone()
+    for it in range(iters):
+        eps, ju = torch.randn(C, 3, n, n, n), torch.rand(C, 3, n, n, n)
+        for s in (frozen, ref):
+            s.set_noise(eps, ju)
+            s.step(1, use_graph=False)
+    torch.cuda.synchronize()
+    assert rel(frozen.v, ref.v) < 1e-6 and rel(frozen.stats, ref.stats) < 1e-6
+    K = frozen.cfg.no_components
+    assert torch.equal(frozen.hyper[1:1 + K], h0[1:1 + K]) and torch.equal(frozen.hyper[9:9 + K], h0[9:9 + K])
+    assert torch.equal(frozen.hyper[50:52], h0[50:52]) and float(frozen.hyper[56]) == iters
+
+
+def test_many_chain_walk_is_deterministic_and_graph_safe(built):
+    """the persistent chain-walk kernel (tickets in global memory) under graph replay: 24 chains, bit-identical twice"""
+    from irsgmcmc_b200.data_loader.synthetic import make_pair
+    n, C = 16, 24
+    fixed, moving, vp = make_pair(n)
+    outs = []
+    for use_graph in (False, True):
+        torch.manual_seed(0)
+        s = _mode_sampler('reference', C, n, fixed, moving, vp, 0.5 * torch.randn(C, 3, n, n, n))
+        s.step(4, use_graph=use_graph)
+        torch.cuda.synchronize()
+        outs.append((s.v.clone(), s.hyper.clone(), s.stats.clone()))
+        assert int(s._counters.abs().sum()) == 0   # per-chain counters and the ticket are left zero
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][2], outs[1][2])
