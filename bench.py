@@ -380,20 +380,24 @@ def main():
     n_warm = -(-n_warm // g_len) * g_len
     sampler.step(n_warm, use_graph=use_graph)
     barrier()
-    clocks = ClockSampler(local_rank) if rank == 0 else None
+    # every rank samples its own GPU's clocks (the timed region is one graph replay: the poller cannot delay it); rank 0's
+    # record is the line's `clocks`, the per-rank medians show whether a slow rank is a slow GPU
+    clocks = ClockSampler(local_rank)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     sampler.step(args.steps, use_graph=use_graph)
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
-    clock_info = clocks.stop() if clocks else None
+    clock_info = clocks.stop()
     t = torch.tensor([ms], device=dev, dtype=torch.float64)
-    per_rank_ms = [ms]
+    per_rank_ms, per_rank_mhz = [ms], [clock_info.get('sm_mhz')]
     if world > 1:
-        gathered = [torch.zeros_like(t) for _ in range(world)]
-        dist.all_gather(gathered, t)
-        per_rank_ms = [float(x.item()) for x in gathered]
+        mine = torch.tensor([ms, float(clock_info.get('sm_mhz') or 0)], device=dev, dtype=torch.float64)
+        gathered = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(gathered, mine)
+        per_rank_ms = [float(x[0].item()) for x in gathered]
+        per_rank_mhz = [int(x[1].item()) for x in gathered]
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t.item())
     value = world * C * V * args.steps / (ms_max * 1e-3)
@@ -545,7 +549,7 @@ def main():
                                   'frac': step_gbs / peak},
                 'stage_ms': {k: round(v, 4) for k, v in stage_ms.items()},
                 'moments_merge_ms': merge_ms, 'moments_merge_bytes': merge_bytes, 'moments_merge_bus_gbs': merge_bus_gbs,
-                'graph': use_graph, 'transitions_per_graph': g_len, 'per_rank_ms_per_step': [x / args.steps for x in per_rank_ms],
+                'graph': use_graph, 'transitions_per_graph': g_len, 'per_rank_ms_per_step': [x / args.steps for x in per_rank_ms], 'per_rank_sm_mhz': per_rank_mhz,
                 'host_cores_per_rank': cores_per_rank, 'clocks': clock_info, 'cpu_baseline': cpu}
         if configs is not None:
             line['configs'] = configs

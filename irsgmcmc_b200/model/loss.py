@@ -121,9 +121,10 @@ class GMM(DataLoss):
         return _MixtureLogPdf.apply(z, self.log_std, self.logits)
 
     def log_pdf_VD(self, z_scaled):
-        # only reached through rescale_residuals in the reference; kept for API completeness (small torch expression)
-        E = 0.5 * z_scaled ** 2
-        return torch.logsumexp((self.log_proportions - self.log_std - self._log_sqrt_2pi) - E, dim=-1)
+        """The reference reaches this only from rescale_residuals (utils/util.py:330-347), whose inner autograd pass is
+        replaced here by the closed form r = z^2 sum_k rho_k / sigma_k^2 evaluated in a kernel (ops.gmm_log_pdf).  There is
+        no PyTorch path to fall back to."""
+        raise NotImplementedError('GMM.log_pdf_VD: use utils.util.rescale_residuals (closed form, CUDA kernel)')
 
     def forward(self, z):
         return self.reduce(z)
@@ -179,10 +180,10 @@ class RegLoss(nn.Module, ABC):
             self.diff_op = diff_op()
 
     def forward(self, input, *args, **kwargs):
-        if type(self.diff_op) is GradientOperator:
-            y = _Energy.apply(input)   # fused: never materialises the (N,3,D,H,W,3) gradient tensor
-        else:
-            y = torch.sum(self.diff_op(input) ** 2, dim=tuple(range(1, input.dim() + 1)))
+        if type(self.diff_op) is not GradientOperator:
+            raise NotImplementedError('RegLoss: only GradientOperator has a CUDA kernel (the energy and its gradient are one '
+                                      'fused stencil; the reference ships no other working operator)')
+        y = _Energy.apply(input)   # fused: never materialises the (N,3,D,H,W,3) gradient tensor
         return self._loss(y, *args, **kwargs)
 
     @abstractmethod

@@ -14,6 +14,13 @@ which calls the adjoint op (the closed forms of SURVEY Appendix A, no scatter at
     GMM.map, one image side (model/loss.py:102-111)                       irsgmcmc::lcc_normalise, ::lcc_normalise_bwd
     RegLoss.forward energy (model/loss.py:152-161)                        irsgmcmc::reg_energy, ::reg_energy_grad
     Cubic_B_spline_FFD_3D.forward (utils/transformation.py:132-152)       irsgmcmc::ffd, ::ffd_adjoint
+    SGLD.apply + SobolevGrad.apply (utils/functions.py:76-109)            irsgmcmc::langevin_proposal (Philox or explicit noise)
+    GMM.log_pdf + autograd (model/loss.py:87-93)                          irsgmcmc::gmm_log_pdf, ::gmm_log_pdf_param_grads
+    rescale_residuals + calc_VD_factor (utils/util.py:330-347,446-485)    irsgmcmc::vd_factor
+    calc_posterior_statistics (utils/util.py:114-120)                     irsgmcmc::welford_update (in place), ::welford_std
+    calc_no_non_diffeomorphic_voxels (utils/util.py:209-212)              irsgmcmc::log_det_jacobian
+    calc_DSC_GPU (utils/util.py:123-148)                                  irsgmcmc::dice_counts
+    Trainer._SGLD_transition (trainer/trainer.py:291-356)                 irsgmcmc::sgld_step (the fused transition, in place)
 
 The drop-in modules (utils/, model/) and the fused sampler use the same launchers; this module adds the dispatcher-visible
 surface the north star asks for and nothing else.
@@ -242,5 +249,175 @@ def _ffd_backward(ctx, g):
 
 ffd.register_autograd(_ffd_backward, setup_context=_ffd_setup)
 
+
+
+# ---- Langevin proposal + Sobolev smoothing ------------------------------------------------------------------------------------
+@_op('langevin_proposal')
+def langevin_proposal(v: Tensor, sigma: Optional[Tensor], eps: Optional[Tensor], coef: float, taps: Sequence[float], seed: int,
+                      iteration: int, chain0: int) -> Tensor:
+    """S * (v + coef sigma eps): eps explicit, or Philox4x32-10 N(0,1) keyed (seed, chain0 + chain, iteration, voxel)"""
+    from .utils.functions import langevin_sobolev
+    return langevin_sobolev(v.contiguous(), None if sigma is None else sigma.contiguous(), coef, [float(t) for t in taps],
+                            None if eps is None else eps.contiguous(), seed, iteration, chain0)
+
+
+@langevin_proposal.register_fake
+def _(v, sigma, eps, coef, taps, seed, iteration, chain0):
+    return torch.empty_like(v)
+
+
+def _langevin_setup(ctx, inputs, output):
+    ctx.has_sigma = inputs[1] is not None
+    if ctx.has_sigma:
+        ctx.save_for_backward(inputs[1])
+
+
+def _langevin_backward(ctx, g):
+    # SGLD.backward = sigma^2 * g (utils/functions.py:82-84), SobolevGrad.backward = identity (:107-109)
+    g_v = g * ctx.saved_tensors[0] ** 2 if ctx.has_sigma else g
+    return g_v, None, None, None, None, None, None, None
+
+
+langevin_proposal.register_autograd(_langevin_backward, setup_context=_langevin_setup)
+
+
+# ---- mixture log-density, virtual decimation ------------------------------------------------------------------------------------
+@_op('gmm_log_pdf')
+def gmm_log_pdf(z: Tensor, log_std: Tensor, logits: Tensor) -> Tuple[Tensor, Tensor]:
+    """(log pdf, d log pdf / dz) per element of z; the mixture parameters may live on either device (K scalars)"""
+    logp, dz, _ = ops.gmm_log_pdf(z.reshape(-1).contiguous(), log_std, logits, want_dz=True)
+    return logp.view(z.shape), dz.view(z.shape)
+
+
+@gmm_log_pdf.register_fake
+def _(z, log_std, logits):
+    return torch.empty_like(z), torch.empty_like(z)
+
+
+@_op('gmm_log_pdf_param_grads')
+def gmm_log_pdf_param_grads(z: Tensor, log_std: Tensor, logits: Tensor, weights: Tensor) -> Tensor:
+    """float64 (16,): sum_i w_i d log pdf_i / d log_std_k in [0, K), sum_i w_i rho_k(z_i) in [8, 8 + K)"""
+    _, _, gp = ops.gmm_log_pdf(z.reshape(-1).contiguous(), log_std, logits, weights=weights.reshape(-1).contiguous(),
+                               want_param_grads=True)
+    return gp
+
+
+@gmm_log_pdf_param_grads.register_fake
+def _(z, log_std, logits, weights):
+    return z.new_empty(2 * _lib.MAX_K, dtype=torch.float64)
+
+
+def _gmm_setup(ctx, inputs, output):
+    z, log_std, logits = inputs
+    ctx.save_for_backward(z, output[1], log_std.detach().clone(), logits.detach().clone())
+    ctx.set_materialize_grads(False)
+
+
+def _gmm_backward(ctx, g_logp, g_dz):
+    if g_dz is not None:
+        raise NotImplementedError('irsgmcmc::gmm_log_pdf: only the log-density is differentiable')
+    if g_logp is None:
+        return None, None, None
+    z, dz, log_std, logits = ctx.saved_tensors
+    K = log_std.numel()
+    g_z = g_logp * dz if ctx.needs_input_grad[0] else None
+    g_ls = g_lg = None
+    if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
+        gp = torch.ops.irsgmcmc.gmm_log_pdf_param_grads(z, log_std, logits, g_logp.contiguous())
+        pi = torch.softmax(logits + 1e-2, dim=0)           # K scalars; d logp / d logits_j = rho_j - pi_j
+        g_ls = gp[:K].to(log_std.dtype).to(log_std.device)
+        g_lg = (gp[8:8 + K].to(logits.device) - pi.double() * g_logp.double().sum().to(logits.device)).to(logits.dtype)
+    return g_z, g_ls, g_lg
+
+
+gmm_log_pdf.register_autograd(_gmm_backward, setup_context=_gmm_setup)
+
+
+@_op('vd_factor')
+def vd_factor(z: Tensor, mask: Tensor, log_std: Tensor, logits: Tensor) -> Tensor:
+    """virtual decimation factor of one chain, float64 scalar tensor"""
+    return ops.vd_factor(z.contiguous(), mask.contiguous(), log_std, logits).reshape(())
+
+
+@vd_factor.register_fake
+def _(z, mask, log_std, logits):
+    return z.new_empty((), dtype=torch.float64)
+
+
+# ---- posterior moments ------------------------------------------------------------------------------------------------------------
+@torch.library.custom_op(f'{_NS}::welford_update', mutates_args=('mean', 'm2'), device_types='cuda')
+def welford_update(sample: Tensor, count_before: int, mean: Tensor, m2: Tensor) -> None:
+    """fold sample[0..n) into the running (mean, M2) that already hold count_before samples"""
+    ops.welford_update(sample.contiguous(), count_before, mean, m2)
+
+
+@welford_update.register_fake
+def _(sample, count_before, mean, m2):
+    return None
+
+
+@_op('welford_std')
+def welford_std(m2: Tensor, count: int) -> Tensor:
+    """unbiased standard deviation sqrt(M2 / (count - 1)) like torch.std (utils/util.py:117)"""
+    return ops.welford_std(m2.contiguous(), count)
+
+
+@welford_std.register_fake
+def _(m2, count):
+    return torch.empty_like(m2)
+
+
+# ---- per-sample evaluation ----------------------------------------------------------------------------------------------------------
+@_op('log_det_jacobian')
+def log_det_jacobian(T: Tensor) -> Tuple[Tensor, Tensor]:
+    """(number of folded voxels per sample int32 (C,), log det J (C,D,H,W)) of a normalised transformation (C,3,D,H,W)"""
+    return ops.log_det_jacobian(T.contiguous())
+
+
+@log_det_jacobian.register_fake
+def _(T):
+    return T.new_empty(T.shape[0], dtype=torch.int32), T.new_empty(T.shape[0], T.shape[2], T.shape[3], T.shape[4])
+
+
+@_op('dice_counts')
+def dice_counts(seg_a: Tensor, seg_b: Tensor, labels: Sequence[int]) -> Tensor:
+    """int32 (C, n_labels, 3): |A = l|, |B = l|, |A = l and B = l| (seg_a may be one volume shared by all samples)"""
+    return ops.dice_counts(seg_a.contiguous(), seg_b.contiguous(), list(labels))
+
+
+@dice_counts.register_fake
+def _(seg_a, seg_b, labels):
+    return seg_b.new_empty(seg_b.shape[0], len(labels), 3, dtype=torch.int32)
+
+
+# ---- the fused transition -------------------------------------------------------------------------------------------------------------
+_SAMPLERS = {}
+
+
+def register_sampler(sampler) -> int:
+    """handle of an SGLDSampler for irsgmcmc::sgld_step (the op mutates that sampler's buffers)"""
+    handle = id(sampler)
+    _SAMPLERS[handle] = sampler
+    return handle
+
+
+@torch.library.custom_op(f'{_NS}::sgld_step', mutates_args=('v', 'hyper', 'stats'), device_types='cuda')
+def sgld_step(v: Tensor, hyper: Tensor, stats: Tensor, handle: int, n: int) -> None:
+    """n fused SGLD transitions (irs_sgld_step) of the sampler registered under `handle`; v / hyper / stats must be that
+    sampler's state tensors (they are what the launch mutates; its other buffers are workspace)"""
+    s = _SAMPLERS.get(handle)
+    if s is None:
+        raise RuntimeError('irsgmcmc::sgld_step: unknown sampler handle (torch_ops.register_sampler)')
+    if v.data_ptr() != s.v.data_ptr() or hyper.data_ptr() != s.hyper.data_ptr() or stats.data_ptr() != s.stats.data_ptr():
+        raise RuntimeError('irsgmcmc::sgld_step: v / hyper / stats are not the state tensors of that sampler')
+    s.step(n, use_graph=False)
+
+
+@sgld_step.register_fake
+def _(v, hyper, stats, handle, n):
+    return None
+
+
 OPS = ('warp3d', 'warp3d_bwd_grid', 'warp3d_nearest', 'svf_exp', 'svf_exp_bwd', 'sobolev_smooth', 'lcc_normalise',
-       'lcc_normalise_bwd', 'reg_energy', 'reg_energy_grad', 'ffd', 'ffd_adjoint')
+       'lcc_normalise_bwd', 'reg_energy', 'reg_energy_grad', 'ffd', 'ffd_adjoint', 'langevin_proposal', 'gmm_log_pdf',
+       'gmm_log_pdf_param_grads', 'vd_factor', 'welford_update', 'welford_std', 'log_det_jacobian', 'dice_counts', 'sgld_step')

@@ -397,8 +397,9 @@ class Trainer:
 
     # -- the loop around it (reference trainer.py:358-476) -------------------------------------------------------------
     def _run_MCMC(self, data_loss=None, reg_loss=None, speed_test_iters=100):
-        """burn-in + sampling; returns {'mean','std_dev', 'im_mean','im_std', 'n', 'DSC', 'no_non_diffeomorphic_voxels',
-        'samples_per_sec'}; posterior statistics are over the kept samples of ALL ranks"""
+        """burn-in + sampling; returns {'mean','std_dev', 'im_mean','im_std', 'n', 'DSC', 'ASD', 'no_non_diffeomorphic_voxels',
+        'samples_per_sec'}; posterior statistics are over the kept samples of ALL ranks.  'ASD' (average surface distance,
+        reference utils/util.py:171-176 through SimpleITK on the host) is reported as unavailable: the string says why."""
         if self.SGLD_params is None:
             self._SGLD_init()
         s = self.sampler
@@ -440,7 +441,9 @@ class Trainer:
             self._pull_hyper(data_loss, reg_loss)
         mom = s.posterior_moments()
         result = {'mean': mom['displacement_mean'], 'std_dev': mom['displacement_std'], 'im_mean': mom['im_mean'],
-                  'im_std': mom['im_std'], 'n': mom['n'], 'DSC': dsc, 'no_non_diffeomorphic_voxels': folded}
+                  'im_std': mom['im_std'], 'n': mom['n'], 'DSC': dsc, 'no_non_diffeomorphic_voxels': folded,
+                  'ASD': 'unavailable: SimpleITK LabelContour / SignedMaurerDistanceMap (reference utils/util.py:171-176) is a '
+                         'host-side dependency this package does not carry; Dice is computed on the GPU per kept sample'}
         if speed_test_iters:  # the reference's built-in speed test: transitions + one segmentation warp each (:467-476)
             torch.cuda.synchronize()
             t0 = time.perf_counter()

@@ -93,15 +93,17 @@ def calc_det_J(nabla):
 
 
 def calc_no_non_diffeomorphic_voxels(transformation, diff_op):
-    """number of voxels with a NaN log det J per sample, and log det J (reference :209-212); one fused kernel when the
-    operator is the forward-difference GradientOperator (no (N,3,D,H,W,3) gradient tensor is materialised)"""
+    """number of voxels with a NaN log det J per sample, and log det J (reference :209-212): one fused kernel over the
+    forward-difference GradientOperator (no (N,3,D,H,W,3) gradient tensor is materialised).  There is no PyTorch path:
+    another operator, a CPU tensor or another dtype raises."""
     from .diff_op import GradientOperator
-    if type(diff_op) is GradientOperator and transformation.is_cuda and transformation.dtype == torch.float32:
-        counts, log_det_J = ops.log_det_jacobian(transformation.detach().contiguous())
-        return counts.cpu().numpy(), log_det_J
-    nabla = diff_op(transformation, transformation=True)
-    log_det_J = calc_det_J(nabla).log()
-    return torch.isnan(log_det_J).sum(dim=(1, 2, 3)).cpu().numpy(), log_det_J
+    if type(diff_op) is not GradientOperator:
+        raise NotImplementedError('calc_no_non_diffeomorphic_voxels: only GradientOperator has a CUDA kernel '
+                                  '(the reference ships no other working operator, utils/diff_op.py)')
+    if not transformation.is_cuda or transformation.dtype != torch.float32:
+        raise NotImplementedError('calc_no_non_diffeomorphic_voxels needs a float32 CUDA tensor: irsgmcmc_b200 has no CPU path')
+    counts, log_det_J = ops.log_det_jacobian(transformation.detach().contiguous())
+    return counts.cpu().numpy(), log_det_J
 
 
 def calc_norm(field):
@@ -120,17 +122,22 @@ def calc_posterior_statistics(samples, device='cuda:0'):
 
 @torch.no_grad()
 def calc_DSC_GPU(no_samples, seg_fixed, seg_moving, structures_dict):
-    """Dice score per sample and structure (reference :123-148), one pass per structure over all samples"""
-    labels = list(structures_dict.values())
+    """Dice score per sample and structure (reference :123-148): one pass over the volumes for all samples and up to 32
+    structures at a time (the reference loops samples x structures).  int16 CUDA segmentations only -- no PyTorch path."""
+    labels = [int(x) for x in structures_dict.values()]
     a, b = seg_fixed[:no_samples], seg_moving[:no_samples].contiguous()
-    if a.is_cuda and a.dtype == torch.int16 and 0 not in labels and len(labels) <= 32:
-        # one pass over the volumes for all structures and samples (the reference loops samples x structures)
-        a = a[:1].contiguous() if a.stride(0) == 0 else a.contiguous()
-        cnt = ops.dice_counts(a, b, labels).double().cpu()
-        return (2.0 * cnt[..., 2] / (cnt[..., 0] + cnt[..., 1])).float().numpy()
-    DSC = torch.zeros(no_samples, len(labels))
-    a, b = a.flatten(1), b.flatten(1)
-    for j, label in enumerate(labels):
-        fa, fb = a == label, b == label
-        DSC[:, j] = (2.0 * (fa & fb).sum(1).float() / (fa.sum(1) + fb.sum(1)).float()).cpu()
-    return DSC.numpy()
+    if not (a.is_cuda and b.is_cuda) or a.dtype != torch.int16 or b.dtype != torch.int16:
+        raise NotImplementedError('calc_DSC_GPU needs int16 CUDA segmentations: irsgmcmc_b200 has no CPU path')
+    if 0 in labels:
+        raise NotImplementedError('calc_DSC_GPU: label 0 is the background of the counting kernel')
+    a = a[:1].contiguous() if a.stride(0) == 0 else a.contiguous()
+    cnt = torch.cat([ops.dice_counts(a, b, labels[i:i + 32]) for i in range(0, len(labels), 32)], dim=1).double().cpu()
+    return (2.0 * cnt[..., 2] / (cnt[..., 0] + cnt[..., 1])).float().numpy()
+
+
+def calc_metrics(*args, **kwargs):
+    """The reference's calc_metrics (:151-206) adds the average surface distance per structure through SimpleITK's
+    LabelContour / SignedMaurerDistanceMap filters on the host.  SimpleITK is not a dependency of this package and the
+    surface distance is not on the GPU path: Dice is calc_DSC_GPU, ASD is reported as unavailable by the Trainer."""
+    raise NotImplementedError('ASD needs SimpleITK (host-side contour distance maps): unavailable in irsgmcmc_b200; '
+                              'use calc_DSC_GPU for the Dice scores')

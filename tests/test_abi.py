@@ -102,6 +102,26 @@ def test_product_fails_loudly_without_cuda(built):
         SGLDSampler(fixed, moving, 1)
 
 
+def test_no_eager_torch_fallbacks_in_the_product():
+    """the volume-sized helpers either launch kernels or raise -- no silent PyTorch path"""
+    import irsgmcmc_b200.model.loss as M
+    import irsgmcmc_b200.utils.util as U
+    from irsgmcmc_b200.utils.diff_op import DifferentialOperator, GradientOperator
+    seg = torch.zeros(2, 1, 4, 4, 4, dtype=torch.int16)
+    with pytest.raises(NotImplementedError):
+        U.calc_DSC_GPU(2, seg, seg, {'a': 10})                     # CPU tensors
+    with pytest.raises(NotImplementedError):
+        U.calc_no_non_diffeomorphic_voxels(torch.zeros(1, 3, 4, 4, 4), GradientOperator())   # CPU tensor
+    with pytest.raises(NotImplementedError):
+        U.calc_no_non_diffeomorphic_voxels(torch.zeros(1, 3, 4, 4, 4), DifferentialOperator())
+    with pytest.raises(NotImplementedError):
+        U.calc_metrics()
+    with pytest.raises(NotImplementedError):
+        M.GMM(4, 2).log_pdf_VD(torch.zeros(3, 4))
+    with pytest.raises(NotImplementedError):
+        M.RegLoss_L2(1.4, diff_op=None, dims=(4, 4, 4))(torch.zeros(1, 3, 4, 4, 4))   # identity operator: no kernel
+
+
 def test_product_does_not_import_the_oracle():
     import subprocess
     import sys
