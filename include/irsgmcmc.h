@@ -319,6 +319,42 @@ int irs_sgld_gmm_init(const irs_sgld_config* cfg, const irs_sgld_buffers* buf, c
 int irs_masked_mean_std(const float* z, const unsigned char* mask, long long n, double* out, double* partials,
                         unsigned int* counter, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------------------
+ * VI warm start: one iteration of Trainer._run_VI (reference trainer/trainer.py:119-171) as a fused device sequence.
+ * q(v) = N(mu, diag(exp(log_var)) + u u^T).  Per iteration (reference lines in brackets):
+ *   delta = eps sigma + x u, samples mu + delta and mu - delta                       [utils/sampler.py:4-21, trainer.py:133]
+ *   both samples through the SGLD step's operators (no Langevin noise, tau = 0) as two chains on the shared mixture, in
+ *   order: Sobolev, integration, warp, residual map, VD factor, mixture Adam step, data / regulariser terms and their
+ *   gradients with respect to the samples                                          [trainer.py:79-117, 135-136]
+ *   entropy terms and their gradients in closed form (Sherman-Morrison)              [model/loss.py:350-372, trainer.py:153-154]
+ *   loss = mean data + mean reg - entropy; Adam on mu, log_var, u (lr / (1 + step lr_decay)) and, with half the summed
+ *   gradient (the mean over the two samples), on the regulariser's hyper-parameters  [trainer.py:157-171]
+ * cfg must describe C = 2 chains with tau = 0 and hyper_mode = IRS_HYPER_REFERENCE; buf->sigma must be NULL; buf->v and
+ * buf->grad_v receive the two samples and the gradients of (data + reg) with respect to them. */
+#define IRS_VI_STATE_SIZE 16
+#define IRS_VI_STEP 0        /* Adam step counter = iteration number (Philox offset of eps and x) */
+#define IRS_VI_BETA_POW 1    /* beta1^t, beta2^t */
+#define IRS_VI_X 3           /* the scalar N(0,1) of the rank-1 term used by the last iteration */
+#define IRS_VI_SUMS 4        /* sum a^2, sum a u_n, sum u_n^2, sum log_var   (a = eps + x u_n, u_n = u / sigma) */
+#define IRS_VI_ENTROPY 8     /* sample term (model/loss.py:360-372), then the log-determinant term (:350-358) */
+
+typedef struct irs_vi_buffers {
+    float* mu;                   /* (1,3,Vs) variational parameters on the state grid, updated in place */
+    float* log_var;
+    float* u;
+    float* adam_m[3];            /* Adam first / second moments of mu, log_var, u (same shapes) */
+    float* adam_v[3];
+    float* eps_store;            /* (1,3,Vs): the N(0,1) field of this iteration (kept from sampling to the update) */
+    double* vi_state;            /* IRS_VI_STATE_SIZE doubles, zero-initialised */
+    double* partials;            /* reduction scratch: 4 * 592 doubles */
+    unsigned int* counter;       /* one zero-initialised unsigned int */
+    const float* eps;            /* optional explicit N(0,1) numbers (1,3,Vs) instead of Philox (parity tests) */
+    const float* x;              /* optional explicit scalar N(0,1) (device pointer) */
+    double lr_mu, lr_log_var, lr_u, lr_decay, beta1, beta2, adam_eps;
+} irs_vi_buffers;
+
+int irs_vi_step(const irs_sgld_config* cfg, const irs_sgld_buffers* buf, const irs_vi_buffers* vi, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

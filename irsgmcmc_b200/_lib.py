@@ -64,6 +64,18 @@ class SgldBuffers(ctypes.Structure):
                 ('ffd_work', ctypes.c_void_p)]
 
 
+class ViBuffers(ctypes.Structure):
+    _fields_ = [('mu', ctypes.c_void_p), ('log_var', ctypes.c_void_p), ('u', ctypes.c_void_p),
+                ('adam_m', ctypes.c_void_p * 3), ('adam_v', ctypes.c_void_p * 3), ('eps_store', ctypes.c_void_p),
+                ('vi_state', ctypes.c_void_p), ('partials', ctypes.c_void_p), ('counter', ctypes.c_void_p),
+                ('eps', ctypes.c_void_p), ('x', ctypes.c_void_p),
+                ('lr_mu', ctypes.c_double), ('lr_log_var', ctypes.c_double), ('lr_u', ctypes.c_double),
+                ('lr_decay', ctypes.c_double), ('beta1', ctypes.c_double), ('beta2', ctypes.c_double),
+                ('adam_eps', ctypes.c_double)]
+
+
+VI_STATE_SIZE, VI_STEP, VI_BETA_POW, VI_X, VI_SUMS, VI_ENTROPY = 16, 0, 1, 3, 4, 8
+
 # name -> (restype, argtypes); every symbol include/irsgmcmc.h declares
 _vp, _i, _ll, _f, _d, _ull, _sz = (ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_float, ctypes.c_double,
                                    ctypes.c_ulonglong, ctypes.c_size_t)
@@ -104,6 +116,7 @@ SYMBOLS = {
     'irs_sgld_launches_per_step': (_i, [ctypes.POINTER(SgldConfig)]),
     'irs_sgld_gmm_init': (_i, [ctypes.POINTER(SgldConfig), ctypes.POINTER(SgldBuffers), _vp, _i, _vp]),
     'irs_masked_mean_std': (_i, [_vp, _vp, _ll, _vp, _vp, _vp, _vp]),
+    'irs_vi_step': (_i, [ctypes.POINTER(SgldConfig), ctypes.POINTER(SgldBuffers), ctypes.POINTER(ViBuffers), _vp]),
 }
 
 _lib = None

@@ -14,6 +14,7 @@ struct IrsHyperCfg {
     double gmm_prior_loc, gmm_prior_scale, dirichlet_alpha;
     double reg_prior_loc, reg_prior_scale, w_reg, dof, w_reg_prior_shape, w_reg_prior_rate;
     double n_mask;
+    double reg_grad_scale;   // factor on the chain-summed hyper-gradients of the regulariser (1; 0.5 for the VI mean of two samples)
 };
 
 // layout of the per-chain reduction produced by the statistics pass

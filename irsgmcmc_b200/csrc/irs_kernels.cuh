@@ -69,6 +69,9 @@ struct IrsRng {
     int chain0;
 };
 
+// --- irs_sampler.cu: the fused transition with the chain-summed regulariser hyper-gradients scaled (VI: mean of two samples) ---
+int irs_sgld_step_scaled(const irs_sgld_config* cfg, const irs_sgld_buffers* b, void* stream, double reg_grad_scale);
+
 // --- irs_warp.cu: voxel-unit warps used by the fused step ------------------------------------------------------------
 int irs_launch_warp_vox_fwd(const float* img, const float* u, IrsRng jit, float alpha, int use_jitter, float* out, int C,
                             IrsDims d, cudaStream_t st);

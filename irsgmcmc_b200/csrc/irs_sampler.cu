@@ -38,7 +38,7 @@ __global__ void __launch_bounds__(128) reg_hyper_kernel(double* hyper, IrsHyperC
     if (mode == IRS_HYPER_REFERENCE) {
         g0 = 0.0; g1 = 0.0;
         for (int t = 0; t < blockDim.x; ++t) { g0 += s0[t]; g1 += s1[t]; }   // fixed order: deterministic
-        irs_reg_adam(hyper, cfg, g0, g1);
+        irs_reg_adam(hyper, cfg, g0 * cfg.reg_grad_scale, g1 * cfg.reg_grad_scale);
     }
     hyper[IRS_HYPER_ITER] += 1.0;
 }
@@ -80,6 +80,7 @@ IrsHyperCfg hyper_cfg(const irs_sgld_config* c) {
     h.w_reg = c->w_reg; h.dof = c->dof;
     h.w_reg_prior_shape = c->w_reg_prior_shape; h.w_reg_prior_rate = c->w_reg_prior_rate;
     h.n_mask = c->n_mask;
+    h.reg_grad_scale = 1.0;
     return h;
 }
 
@@ -168,7 +169,8 @@ inline void mark(StageTimer* t, cudaStream_t st) {
 }
 }  // namespace
 
-static int sgld_step_impl(const irs_sgld_config* cfg, const irs_sgld_buffers* b, void* stream, StageTimer* tm) {
+static int sgld_step_impl(const irs_sgld_config* cfg, const irs_sgld_buffers* b, void* stream, StageTimer* tm,
+                          double reg_grad_scale = 1.0) {
     IRS_TRY(check_config(cfg));
     if (!b || !b->v || !b->fixed || !b->moving || !b->mask || !b->css || !b->hist || !b->im_warped || !b->z ||
         !b->scratch1 || !b->field_a || !b->field_b || !b->grad_v || !b->maxabs || !b->hyper || !b->stats ||
@@ -187,7 +189,8 @@ static int sgld_step_impl(const irs_sgld_config* cfg, const irs_sgld_buffers* b,
     const float* velocity = ffd ? b->ffd_dense : b->css;   // what scaling and squaring integrates
     const long long V = d.V();
     const size_t F = (size_t)C * 3 * V;
-    const IrsHyperCfg hc = hyper_cfg(cfg);
+    IrsHyperCfg hc = hyper_cfg(cfg);
+    hc.reg_grad_scale = reg_grad_scale;
     const double* iter_ptr = b->hyper + IRS_HYPER_ITER;
 
     mark(tm, st);
@@ -290,6 +293,10 @@ static int sgld_step_impl(const irs_sgld_config* cfg, const irs_sgld_buffers* b,
 
 extern "C" int irs_sgld_step(const irs_sgld_config* cfg, const irs_sgld_buffers* b, void* stream) {
     return sgld_step_impl(cfg, b, stream, nullptr);
+}
+
+int irs_sgld_step_scaled(const irs_sgld_config* cfg, const irs_sgld_buffers* b, void* stream, double reg_grad_scale) {
+    return sgld_step_impl(cfg, b, stream, nullptr, reg_grad_scale);
 }
 
 // Profiling aid (not for graph capture; synchronises): runs one transition eagerly with a CUDA event between the

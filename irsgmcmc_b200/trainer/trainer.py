@@ -126,8 +126,8 @@ class Trainer:
             return [reg_loss.loc, reg_loss.log_scale]
         return [reg_loss.log_w_reg]
 
-    def _push_adam(self, optimizer, params, step_slot, m_slots, v_slots, beta_slot):
-        h = self.sampler.hyper
+    def _push_adam(self, optimizer, params, step_slot, m_slots, v_slots, beta_slot, sampler=None):
+        h = (sampler or self.sampler).hyper
         betas = optimizer.param_groups[0]['betas']
         step = t = 0
         for p, ms, vs in zip(params, m_slots, v_slots):
@@ -144,8 +144,8 @@ class Trainer:
         h[beta_slot] = betas[0] ** t       # the device multiplies these running products by beta once per step
         h[beta_slot + 1] = betas[1] ** t
 
-    def _pull_adam(self, optimizer, params, step_slot, m_slots, v_slots):
-        h = self.sampler.hyper.cpu()
+    def _pull_adam(self, optimizer, params, step_slot, m_slots, v_slots, sampler=None):
+        h = (sampler or self.sampler).hyper.cpu()
         step = int(round(float(h[step_slot])))
         for p, ms, vs in zip(params, m_slots, v_slots):
             k = p.numel()
@@ -155,9 +155,10 @@ class Trainer:
             st['exp_avg'] = h[ms:ms + k].to(p.dtype).view_as(p).to(p.device)
             st['exp_avg_sq'] = h[vs:vs + k].to(p.dtype).view_as(p).to(p.device)
 
-    def _push_hyper(self, data_loss, reg_loss, optimizer_GMM=None, optimizer_reg=None):
+    def _push_hyper(self, data_loss, reg_loss, optimizer_GMM=None, optimizer_reg=None, sampler=None):
         from .. import _lib as L
-        s, K = self.sampler, self.sampler.cfg.no_components
+        s = sampler or self.sampler
+        K = s.cfg.no_components
         optimizer_GMM = optimizer_GMM if optimizer_GMM is not None else getattr(self, 'optimizer_GMM', None)
         optimizer_reg = optimizer_reg if optimizer_reg is not None else getattr(self, 'optimizer_reg', None)
         if data_loss is not None:
@@ -166,22 +167,23 @@ class Trainer:
             if optimizer_GMM is not None:
                 self._push_adam(optimizer_GMM, [data_loss.log_std, data_loss.logits], L.HYPER_GMM_STEP,
                                 [L.HYPER_M_LOG_STD, L.HYPER_M_LOGITS], [L.HYPER_V_LOG_STD, L.HYPER_V_LOGITS],
-                                L.HYPER_GMM_BETA_POW)
+                                L.HYPER_GMM_BETA_POW, sampler=s)
         if reg_loss is not None:
             params = self._reg_params(reg_loss)
             for i, p in enumerate(params):
                 s.hyper[L.HYPER_REG_P + i] = p.detach().double()
             if optimizer_reg is not None and getattr(reg_loss, 'learnable', False):
                 self._push_adam(optimizer_reg, params, L.HYPER_REG_STEP, [L.HYPER_REG_M + i for i in range(len(params))],
-                                [L.HYPER_REG_V + i for i in range(len(params))], L.HYPER_REG_BETA_POW)
+                                [L.HYPER_REG_V + i for i in range(len(params))], L.HYPER_REG_BETA_POW, sampler=s)
 
     @torch.no_grad()
-    def _pull_hyper(self, data_loss, reg_loss, optimizer_GMM=None, optimizer_reg=None, with_optimizers=True):
+    def _pull_hyper(self, data_loss, reg_loss, optimizer_GMM=None, optimizer_reg=None, with_optimizers=True, sampler=None):
         """device state -> modules.  with_optimizers=False copies the parameters only (device-to-device, no host
         synchronisation: what _SGLD_transition does after every step); the optimiser state needs the step counters on the
         host and is mirrored at the end of _run_MCMC / on request"""
         from .. import _lib as L
-        s, K = self.sampler, self.sampler.cfg.no_components
+        s = sampler or self.sampler
+        K = s.cfg.no_components
         if with_optimizers:
             optimizer_GMM = optimizer_GMM if optimizer_GMM is not None else getattr(self, 'optimizer_GMM', None)
             optimizer_reg = optimizer_reg if optimizer_reg is not None else getattr(self, 'optimizer_reg', None)
@@ -192,16 +194,16 @@ class Trainer:
             data_loss.logits.copy_(s.hyper[L.HYPER_LOGITS:L.HYPER_LOGITS + K].to(data_loss.logits.dtype))
             if optimizer_GMM is not None:
                 self._pull_adam(optimizer_GMM, [data_loss.log_std, data_loss.logits], L.HYPER_GMM_STEP,
-                                [L.HYPER_M_LOG_STD, L.HYPER_M_LOGITS], [L.HYPER_V_LOG_STD, L.HYPER_V_LOGITS])
+                                [L.HYPER_M_LOG_STD, L.HYPER_M_LOGITS], [L.HYPER_V_LOG_STD, L.HYPER_V_LOGITS], sampler=s)
         if reg_loss is not None:
             params = self._reg_params(reg_loss)
             for i, p in enumerate(params):
                 p.copy_(s.hyper[L.HYPER_REG_P + i].to(p.dtype))
             if optimizer_reg is not None and getattr(reg_loss, 'learnable', False):
                 self._pull_adam(optimizer_reg, params, L.HYPER_REG_STEP, [L.HYPER_REG_M + i for i in range(len(params))],
-                                [L.HYPER_REG_V + i for i in range(len(params))])
+                                [L.HYPER_REG_V + i for i in range(len(params))], sampler=s)
 
-    # -- VI warm start (reference trainer.py:79-223), on the drop-in modules through autograd ------------------------
+    # -- VI warm start (reference trainer.py:79-223): fused device path, and the drop-in modules through autograd -------
     def _build_VI_modules(self):
         """the objects the reference's ConfigParser would create for VI from the JSON (parse_config.py:110-148,215-249)"""
         from .. import model as M
@@ -289,13 +291,54 @@ class Trainer:
                 loss_terms['w_reg_prior'] = m['w_reg_prior'](reg_loss.log_w_reg)
         return loss_terms, output, aux
 
-    def _run_VI(self, var_params_q_v=None, no_iters=None, modules=None, lr=None, noise=None):
+    def _run_VI_fused(self, var_params_q_v=None, no_iters=None, modules=None, lr=None, noise=None, history=True):
+        """_run_VI on the fused device path (irsgmcmc_b200/vi.py, csrc/irs_vi.cu): no autograd, no eager field arithmetic.
+        `history=False` enqueues all iterations without a host synchronisation (CUDA-graph replays)."""
+        from ..vi import VIWarmStart
+        tr = self.config['trainer']
+        no_iters = int(tr.get('no_iters_VI', 0)) if no_iters is None else no_iters
+        var_params_q_v = var_params_q_v or self.var_params_q_v
+        m = modules or self._build_VI_modules()
+        a = self.config.get('optimizer_q_v', {}).get('args', {})
+        lr = lr or {'mu': a.get('lr_mu', 0.01), 'log_var': a.get('lr_log_var', 0.01), 'u': a.get('lr_u', 0.01)}
+        vi = VIWarmStart(self.fixed, self.moving, var_params_q_v, self.sampler.cfg, device=self.device, lr_mu=lr['mu'],
+                         lr_log_var=lr['log_var'], lr_u=lr['u'], lr_decay=a.get('lr_decay', 1e-3))
+        # the mixture / regulariser parameters and the optimiser state of the stage before (mixture initialisation)
+        self._push_hyper(m['data_loss'], m['reg_loss'], m['optimizer_GMM'], m.get('optimizer_reg'), sampler=vi.sampler)
+        hist = []
+        if noise is None and not history:
+            vi.step(no_iters)
+        else:
+            for it in range(no_iters):
+                if noise is not None:
+                    eps, x, j1, j2 = next(noise)
+                    vi.set_noise(eps, x, None if j1 is None else torch.cat((j1, j2), 0))
+                vi.step(1, use_graph=noise is None)
+                if history:
+                    lt = vi.loss_terms()
+                    entropy = lt['entropy_sample'] + lt['entropy_log_det']
+                    # `loss` without the hyper-prior constants of the eager path's history (they carry no field gradient)
+                    hist.append({'data_samples': lt['data'], 'reg_samples': lt['reg'], 'alpha_samples': lt['alpha'],
+                                 'entropy': entropy, 'alpha': lt['alpha'][0], 'data': lt['data'].mean(), 'reg': lt['reg'].mean(),
+                                 'loss': lt['data'].mean() + lt['reg'].mean() - entropy})
+        self._pull_hyper(m['data_loss'], m['reg_loss'], m['optimizer_GMM'], m.get('optimizer_reg'), sampler=vi.sampler)
+        self.var_params_q_v = {k: v.detach().clone() for k, v in vi.var_params().items()}
+        self._vi_modules, self._vi = m, vi
+        self.optimizer_GMM, self.optimizer_reg = m['optimizer_GMM'], m.get('optimizer_reg')
+        self._gmm_pushed = False
+        return self.var_params_q_v, m, hist
+
+    def _run_VI(self, var_params_q_v=None, no_iters=None, modules=None, lr=None, noise=None, fused=True):
         """
         fit the Gaussian variational posterior q(v) (reference trainer.py:119-223): per iteration two antithetic samples,
         loss = data + reg - entropy, Adam on (mu, log_var, u) and on the regulariser hyper-parameters; the shared mixture
         is stepped inside each sample's loss.  Returns (var_params_q_v, modules, history of loss terms).
+        `fused` (default): the device path of _run_VI_fused; False: the drop-in modules through autograd (what a user of the
+        reference's classes gets; also the check of the fused path).
         `noise`: optional iterator of (eps, x, jitter1, jitter2) for exact parity tests.
         """
+        if fused:
+            return self._run_VI_fused(var_params_q_v, no_iters, modules, lr, noise)
         from ..optimizers import Adam
         tr = self.config['trainer']
         no_iters = int(tr.get('no_iters_VI', 0)) if no_iters is None else no_iters
@@ -337,9 +380,11 @@ class Trainer:
                 m['optimizer_reg'].step()
             optimizer_q_v.step()
             history.append({'data': data_term.detach(), 'reg': reg_term.detach(), 'entropy': entropy_term.detach(),
-                            'loss': loss.detach(), 'alpha': aux['alpha']})
+                            'loss': loss.detach(), 'alpha': aux['alpha'],
+                            'data_samples': torch.stack((lt1['data'].detach(), lt2['data'].detach())),
+                            'reg_samples': torch.stack((lt1['reg'].detach(), lt2['reg'].detach()))})
         self.var_params_q_v = {k: v.detach() for k, v in vp.items()}
-        self._vi_modules = m
+        self._vi_modules, self._optimizer_q_v, self._vp_leaves = m, optimizer_q_v, vp
         # one optimiser per hyper-parameter group for the whole run (reference trainer.py:62-66): MCMC continues with them
         self.optimizer_GMM, self.optimizer_reg = m['optimizer_GMM'], m.get('optimizer_reg')
         self._gmm_pushed = False   # the next transition pushes the parameters AND the optimiser state VI left behind

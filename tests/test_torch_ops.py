@@ -170,3 +170,86 @@ def test_gpu_lcc_energy_and_ffd_ops_match_the_launchers(pkg):
     dm = m(cm)
     (dm * Gd).sum().backward()
     assert torch.equal(dense, dm) and torch.equal(cp.grad, cm.grad)
+
+
+@pytest.mark.gpu
+def test_gpu_mixture_proposal_and_evaluation_ops(pkg):
+    """the ops added in round 2 against the oracle and the wrappers they share kernels with"""
+    U, ops = pkg
+    import irsgmcmc_b200.model.loss as M
+    n, C, K = 16, 2, 4
+    gen = torch.Generator(device=DEV).manual_seed(7)
+    # -- mixture log-density with autograd to z, log_std, logits: against torch autograd of the oracle's expression
+    z0 = torch.randn(C, 1, n, n, n, device=DEV, generator=gen)
+    ls0, lg0 = torch.linspace(-2.0, 0.5, K, device=DEV), torch.tensor([0.1, -0.2, 0.3, 0.0], device=DEV)
+    Gp = torch.randn(C, 1, n, n, n, device=DEV, generator=gen)
+    z, ls, lg = (t.clone().requires_grad_(True) for t in (z0, ls0, lg0))
+    logp, dz = torch.ops.irsgmcmc.gmm_log_pdf(z, ls, lg)
+    (logp * Gp).sum().backward()
+    zr, lsr, lgr = (t.double().cpu().clone().requires_grad_(True) for t in (z0, ls0, lg0))
+    ref = O.gmm_log_pdf(zr.reshape(-1), lsr, lgr).view(z0.shape)
+    (ref * Gp.double().cpu()).sum().backward()
+    assert rel(logp, ref) < 1e-5 and rel(z.grad, zr.grad) < 1e-5
+    assert rel(ls.grad, lsr.grad) < 1e-4 and rel(lg.grad, lgr.grad) < 1e-4
+    # -- virtual decimation factor
+    mask = torch.rand(1, 1, n, n, n, device=DEV, generator=gen) > 0.3
+    alpha = torch.ops.irsgmcmc.vd_factor(z0[:1], mask, ls0, lg0)
+    assert alpha.dtype == torch.float64 and abs(float(alpha) - float(ops.vd_factor(z0[:1], mask, ls0, lg0))) == 0.0
+    # -- Langevin proposal: explicit noise against the oracle, Philox reproducible, backward = sigma^2 g
+    taps = [float(t) for t in O.sobolev_taps(3, 0.5).astype('float32')]
+    v0 = torch.randn(C, 3, n, n, n, device=DEV, generator=gen)
+    sigma = 0.5 + torch.rand(1, 3, n, n, n, device=DEV, generator=gen)
+    eps = torch.randn(C, 3, n, n, n, device=DEV, generator=gen)
+    G = torch.randn(C, 3, n, n, n, device=DEV, generator=gen)
+    v = v0.clone().requires_grad_(True)
+    out = torch.ops.irsgmcmc.langevin_proposal(v, sigma, eps, 0.9, taps, 0, 0, 0)
+    (out * G).sum().backward()
+    ref = O.sobolev_smooth((v0 + 0.9 * sigma * eps).cpu(), O.sobolev_taps(3, 0.5).astype('float32'))
+    assert rel(out, ref) < 1e-5 and torch.equal(v.grad, G * sigma ** 2)
+    a = torch.ops.irsgmcmc.langevin_proposal(v0, sigma, None, 0.9, taps, 11, 3, 5)
+    b = torch.ops.irsgmcmc.langevin_proposal(v0, sigma, None, 0.9, taps, 11, 3, 5)
+    c = torch.ops.irsgmcmc.langevin_proposal(v0, sigma, None, 0.9, taps, 11, 4, 5)
+    assert torch.equal(a, b) and not torch.equal(a, c)
+    # -- Welford moments (in place) against torch.mean / torch.std
+    samples = torch.randn(7, 3, n, n, n, device=DEV, generator=gen) * 2 + 1
+    mean, m2 = torch.zeros(3, n, n, n, device=DEV), torch.zeros(3, n, n, n, device=DEV)
+    torch.ops.irsgmcmc.welford_update(samples[:4], 0, mean, m2)
+    torch.ops.irsgmcmc.welford_update(samples[4:], 4, mean, m2)
+    assert rel(mean, samples.mean(0)) < 1e-6 and rel(torch.ops.irsgmcmc.welford_std(m2, 7), samples.std(0)) < 1e-5
+    # -- det J and Dice counts
+    T, _ = U.SVF_3D((n, n, n)).to(DEV)(_field(C, n, 2.0, 9))
+    counts, log_det = torch.ops.irsgmcmc.log_det_jacobian(T.detach())
+    c2, l2 = ops.log_det_jacobian(T.detach().contiguous())
+    assert torch.equal(counts, c2) and torch.equal(log_det, l2) and log_det.shape == (C, n, n, n)
+    sa = (torch.rand(1, 1, n, n, n, device=DEV, generator=gen) * 4).short()
+    sb = (torch.rand(C, 1, n, n, n, device=DEV, generator=gen) * 4).short()
+    dc = torch.ops.irsgmcmc.dice_counts(sa, sb, [1, 2, 3])
+    for i, lab in enumerate([1, 2, 3]):
+        for c_ in range(C):
+            assert tuple(dc[c_, i].tolist()) == (int((sa == lab).sum()), int((sb[c_] == lab).sum()),
+                                                  int(((sa[0] == lab) & (sb[c_] == lab)).sum()))
+
+
+@pytest.mark.gpu
+def test_gpu_fused_step_op_is_the_sampler_step(built):
+    from irsgmcmc_b200 import torch_ops
+    from irsgmcmc_b200.sampler import SGLDSampler, SGLDConfig
+    from irsgmcmc_b200.data_loader.synthetic import make_pair
+    n, C = 16, 2
+    fixed, moving, vp = make_pair(n)
+    outs = []
+    for through_op in (False, True):
+        torch.manual_seed(0)
+        s = SGLDSampler(fixed, moving, C, SGLDConfig(), device=DEV)
+        s.set_state(0.5 * torch.randn(C, 3, n, n, n), torch.exp(0.5 * vp['log_var']))
+        s.init_gmm(sigma_hat=0.7)
+        if through_op:
+            h = torch_ops.register_sampler(s)
+            torch.ops.irsgmcmc.sgld_step(s.v, s.hyper, s.stats, h, 3)
+            with pytest.raises(RuntimeError):
+                torch.ops.irsgmcmc.sgld_step(s.v.clone(), s.hyper, s.stats, h, 1)
+        else:
+            s.step(3, use_graph=False)
+        torch.cuda.synchronize()
+        outs.append((s.v.clone(), s.hyper.clone(), s.stats.clone()))
+    assert all(torch.equal(a, b) for a, b in zip(*outs))
