@@ -202,7 +202,7 @@ def graph_length(steps):
 
 
 def run_config(tag, n, chains, data, world, rank, dev, peak, barrier, seg_dice=False, moments=False, flush_l2=False,
-               target_ms=1200.0):
+               target_ms=1200.0, vi=False, cpu_vi=False):
     """
     One entry of the `configs` sub-record: a BASELINE.json configuration other than the headline, measured in the same run with
     the same rules (CUDA events on the launching stream, barrier + synchronize on both sides, max over ranks, >= 3 warm-up
@@ -282,6 +282,33 @@ def run_config(tag, n, chains, data, world, rank, dev, peak, barrier, seg_dice=F
         out['per_step_extras'] = 'transformation + nearest-neighbour int16 segmentation warp + Dice counts (15 structures)'
         out['dice_mean_last_sample'] = sum(dice) / len(dice)
         out['asd'] = 'unavailable (SimpleITK contour distance, not on the GPU path)'
+    if vi:
+        # configs[0] says "VI warm start then 1 SGLD chain": the VI iteration of reference trainer.py:119-171 on the fused device
+        # path (two antithetic samples through the step's operators + closed-form entropy + field-sized Adam), graph replays
+        from irsgmcmc_b200.vi import VIWarmStart
+        w = VIWarmStart(fixed, moving, vp, cfg, device=dev)
+        w.sampler.hyper.copy_(sampler.hyper)
+        w.step(5)
+        barrier()
+        n_vi = 50
+        e0.record(); w.step(n_vi); e1.record()
+        barrier()
+        ms_vi = allmax(e0.elapsed_time(e1)) / n_vi
+        out['vi'] = {'ms_per_iteration': ms_vi, 'iterations_per_s': 1e3 / ms_vi, 'iterations_timed': n_vi,
+                     'gpu_launches_per_iteration': w.sampler.launches_per_step() + 3}
+        if rank == 0 and cpu_vi:
+            import time as _t
+            from oracle import sgld_oracle as O
+            st = O.State(O.Config(data=data, K=4 if lcc else 1, reg='lognormal' if lcc else 'l2', w_reg=1.6 if lcc else 1.4),
+                         torch.zeros(1, 3, n, n, n), torch.ones(1, 3, n, n, n), (n, n, n))
+            st.init_gmm(0.7)
+            torch.set_num_threads(os.cpu_count() or 1)
+            t0 = _t.perf_counter()
+            O.vi_iteration(st, fixed, moving, vp, torch.randn(1, 3, n, n, n), torch.randn(1), torch.rand(1, 3, n, n, n),
+                           torch.rand(1, 3, n, n, n))
+            out['vi']['cpu_port_ms_per_iteration'] = 1e3 * (_t.perf_counter() - t0)
+            out['vi']['cpu_port_threads'] = torch.get_num_threads()
+        del w
     if moments:
         sampler.accumulate()
         sampler.posterior_moments()          # warm: buffers allocated, NCCL channels for this size set up
@@ -498,7 +525,8 @@ def main():
     default_headline = args.size == 128 and args.chains == 1 and args.data == 'lcc' and not args.cps and use_graph
     if default_headline and not args.no_configs:
         configs = []
-        todo = [dict(tag='configs[0]: 64^3 SSD + RegLoss_L2, 1 chain per GPU', n=64, chains=1, data='ssd', flush_l2=True, target_ms=300.0),
+        todo = [dict(tag='configs[0]: 64^3 SSD + RegLoss_L2, VI warm start iterations and 1 SGLD chain per GPU', n=64, chains=1, data='ssd',
+                     flush_l2=True, target_ms=300.0, vi=True, cpu_vi=not args.no_cpu_baseline),
                 dict(tag=f'configs[2]: 128^3 LCC, 64 chains sharded over {world} GPU(s) (strong scaling), Welford + NCCL merge',
                      n=128, chains=max(64 // world, 1), data='lcc', moments=True),
                 dict(tag='configs[3]: 256^3 LCC, 1 chain per GPU, segmentation warp + Dice per transition', n=256, chains=1,

@@ -5,7 +5,8 @@ Kept from the reference: the method names and signatures on the hot path (`_SGLD
 reg_loss) -> (loss_terms, output, aux)`, `_run_MCMC`, the chain / mixture initialisation), the attribute names read from
 the `trainer` section of the JSON config (`no_chains`, `MCMC_init`, `no_iters_burn_in`, `no_samples_MCMC`,
 `log_period_MCMC`, `uniform_noise`), the kept-sample rule and the folding guard.  Dropped (out of
-scope): TensorBoard / NIfTI / VTK writers, MetricTracker, SimpleITK surface distances, the data loader.
+scope): TensorBoard, MetricTracker, SimpleITK surface distances, the data loader.  Kept samples and the posterior statistics can
+be written as NIfTI-1 / legacy VTK (`save_dir`; irsgmcmc_b200/logger/writers.py).
 
 What differs by design: one transition is one CUDA-graph replay with no host synchronisation; the per-iteration
 `.item()` logging of the reference (trainer.py:391-412) is replaced by on-device statistics read back on request;
@@ -61,7 +62,7 @@ def sampler_config_from_json(config):
 
 class Trainer:
     def __init__(self, config, fixed, moving, var_params_q_v=None, structures_dict=None, device=None,
-                 chain_offset=None, logger=None):
+                 chain_offset=None, logger=None, save_dir=None, im_spacing=(1.0, 1.0, 1.0)):
         """
         config: the reference's JSON config as a dict;  fixed / moving: {'im','mask','seg'} with shape (1,1,D,H,W)
         With torch.distributed initialised, `no_chains` is the TOTAL number of chains; this rank owns a contiguous shard.
@@ -79,6 +80,9 @@ class Trainer:
         self.Sobolev_grad = config.get('Sobolev_grad', {}).get('enabled', False)
         self.structures_dict = structures_dict or {}
         self.logger = logger
+        # save_dir: kept samples and the posterior statistics are written there as .nii.gz / .vtk with the reference's file
+        # names (logger/logger.py:215-238); None = nothing touches the disk
+        self.save_dir, self.im_spacing = save_dir, im_spacing
 
         world = torch.distributed.get_world_size() if torch.distributed.is_available() and torch.distributed.is_initialized() else 1
         if self.no_chains_total < world:   # every rank sees the same numbers: all of them raise, nobody hangs in a collective
@@ -474,8 +478,13 @@ class Trainer:
                     seg_w = s.warp_segmentation(transformation=T)
                     seg_f = self.fixed['seg'].to(s.device).expand(self.no_chains, -1, -1, -1, -1)
                     dsc.append(calc_DSC_GPU(self.no_chains, seg_f, seg_w, self.structures_dict))
-                n_folded, _ = calc_no_non_diffeomorphic_voxels(T, diff_op)
+                n_folded, log_det_J = calc_no_non_diffeomorphic_voxels(T, diff_op)
                 folded.append(n_folded)
+                if self.save_dir is not None:
+                    from ..logger import save_sample
+                    for c in range(self.no_chains):
+                        save_sample(self.save_dir, self.im_spacing, it, s.im_warped[c:c + 1], s.displacement[c:c + 1],
+                                    log_det_J[c:c + 1], model='MCMC', chain_no=s.chain_offset + c)
                 bad = bool((n_folded > 0.001 * self.no_voxels).any())
                 if parallel.any_rank(bad, s.device):   # reference trainer.py:441-445 (exits the process there)
                     # the flag is all-reduced first: every rank leaves together instead of one raising while the others
@@ -489,6 +498,12 @@ class Trainer:
                   'im_std': mom['im_std'], 'n': mom['n'], 'DSC': dsc, 'no_non_diffeomorphic_voxels': folded,
                   'ASD': 'unavailable: SimpleITK LabelContour / SignedMaurerDistanceMap (reference utils/util.py:171-176) is a '
                          'host-side dependency this package does not carry; Dice is computed on the GPU per kept sample'}
+        if self.save_dir is not None and (not torch.distributed.is_initialized() or torch.distributed.get_rank() == 0):
+            from ..logger import save_field_to_disk   # reference logger/logger.py:104-126 (mean / std of the displacement)
+            import os
+            os.makedirs(self.save_dir, exist_ok=True)
+            save_field_to_disk(mom['displacement_mean'] * self.im_spacing[0], os.path.join(self.save_dir, 'displacement_mean.vtk'), self.im_spacing)
+            save_field_to_disk(mom['displacement_std'] * self.im_spacing[0], os.path.join(self.save_dir, 'displacement_std_dev.vtk'), self.im_spacing)
         if speed_test_iters:  # the reference's built-in speed test: transitions + one segmentation warp each (:467-476)
             torch.cuda.synchronize()
             t0 = time.perf_counter()

@@ -247,7 +247,10 @@ def test_trainer_facade(pkg):
     torch.manual_seed(5)
     fixed, moving, vp = make_pair(n)
     structures = {f's{l}': l for l in STRUCTURE_LABELS}
-    t = Trainer(_reference_style_config(C), fixed, moving, vp, structures_dict=structures, device=torch.device(DEV))
+    import tempfile
+    save_dir = tempfile.mkdtemp()
+    t = Trainer(_reference_style_config(C), fixed, moving, vp, structures_dict=structures, device=torch.device(DEV),
+                save_dir=save_dir, im_spacing=(2.0, 2.0, 2.0))
     gmm = M.GMM(4, 2).to(DEV)
     gmm.init_parameters(0.7)
     reg = M.RegLoss_LogNormal(w_reg=1.6, diff_op='GradientOperator', dims=(n, n, n), learnable=True).to(DEV)
@@ -265,6 +268,17 @@ def test_trainer_facade(pkg):
     assert res['n'] == 3 * C and res['mean'].shape == (3, n, n, n) and torch.isfinite(res['std_dev']).all()
     assert len(res['DSC']) == 3 and res['DSC'][0].shape == (C, len(structures))
     assert res['samples_per_sec'] > 0
+    assert isinstance(res['ASD'], str) and res['ASD'].startswith('unavailable')
+    # kept samples and posterior statistics on disk with the reference's names (logger/logger.py:215-238)
+    import os
+    from irsgmcmc_b200.logger import load_field_from_disk, load_im_from_disk
+    names = sorted(os.listdir(save_dir))
+    assert 'chain_0_sample_0000008_displacement.vtk' in names and 'chain_1_sample_0000016_im_moving_warped.nii.gz' in names
+    assert 'chain_1_sample_0000012_log_det_J.nii.gz' in names and len(names) == 3 * C * 3 + 2
+    mean, sp = load_field_from_disk(os.path.join(save_dir, 'displacement_mean.vtk'))
+    assert np.allclose(mean, 2.0 * res['mean'].cpu().numpy(), atol=1e-6) and sp == [2.0, 2.0, 2.0]
+    im, _ = load_im_from_disk(os.path.join(save_dir, 'chain_0_sample_0000016_im_moving_warped.nii.gz'))
+    assert im.shape == (n, n, n) and np.isfinite(im).all()
 
 
 # ---- section 8f "next" rows: evaluation kernels and the VI warm start ---------------------------------------------------

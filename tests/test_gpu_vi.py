@@ -95,3 +95,48 @@ def test_fused_vi_runs_in_a_graph_and_is_deterministic(built):
         assert torch.equal(x, y)
     assert float(res[0][4][0]) == 5 and float(res[0][3][56]) == 5     # Adam step counter, Philox offset of the jitter
     assert not torch.equal(res[0][0].cpu(), vp0['mu'])
+
+
+@pytest.mark.parametrize('reg_key', ['lognormal', 'l2'])
+def test_fused_vi_iteration_vs_oracle(built, reg_key):
+    """one fused VI iteration against the oracle's restatement of reference trainer/trainer.py:130-171 (oracle.vi_iteration,
+    fp32 and fp64): loss terms, gradients w.r.t. (mu, log_var, u) read back from Adam's first moments, the mixture after its
+    two steps and the regulariser's hyper-parameters after theirs"""
+    from oracle import sgld_oracle as O
+    from tests.util import grad_ok
+    from irsgmcmc_b200.sampler import SGLDConfig
+    from irsgmcmc_b200.vi import VIWarmStart
+    from irsgmcmc_b200.data_loader.synthetic import make_pair
+    n = 16
+    torch.manual_seed(31)
+    fixed, moving, vp0 = make_pair(n)
+    s = (1, 3, n, n, n)
+    vp0 = {'mu': 0.3 * torch.randn(s), 'log_var': vp0['log_var'] + 0.1 * torch.randn(s), 'u': vp0['u'] + 0.05 * torch.randn(s)}
+    eps, x = torch.randn(s), torch.randn(1)
+    j1, j2 = torch.rand(s), torch.rand(s)
+    cfg = SGLDConfig(reg_loss='RegLoss_LogNormal' if reg_key == 'lognormal' else 'RegLoss_L2', w_reg=1.6, reg_learnable=True)
+    vi = VIWarmStart(fixed, moving, vp0, cfg, device=DEV)
+    vi.sampler.init_gmm(sigma_hat=0.7)
+    vi.set_noise(eps, x, torch.cat((j1, j2), 0))
+    vi.step(1, use_graph=False)
+    torch.cuda.synchronize()
+    lt = vi.loss_terms()
+    res = {}
+    for dtype in (torch.float32, torch.float64):
+        st = O.State(O.Config(reg=reg_key, w_reg=1.6, exact_grid=dtype == torch.float64), torch.zeros(1, 3, n, n, n, dtype=dtype),
+                     torch.ones(1, 3, n, n, n, dtype=dtype), (n, n, n), dtype)
+        st.init_gmm(0.7)
+        cast = lambda d_: {k: (v.to(dtype) if v.dtype == torch.float32 else v) for k, v in d_.items()}
+        terms, grads = O.vi_iteration(st, cast(fixed), cast(moving), {k: v.to(dtype) for k, v in vp0.items()}, eps.to(dtype),
+                                      x.to(dtype), j1.to(dtype), j2.to(dtype))
+        res[dtype] = (terms, grads, st)
+    t64, g64, st64 = res[torch.float64]
+    _, g32, _ = res[torch.float32]
+    assert abs(lt['entropy_sample'] + lt['entropy_log_det'] - float(t64['entropy'])) < 1e-5 * abs(float(t64['entropy']))
+    assert abs(float(lt['alpha'][0]) - float(t64['alpha'][0])) < 1e-4 and abs(float(lt['alpha'][1]) - float(t64['alpha'][1])) < 1e-4
+    for i, k in enumerate(('mu', 'log_var', 'u')):
+        assert grad_ok(vi._m[i] / 0.1, g32[k], g64[k], f'fused VI grad {k} ({reg_key})')
+    ls, lg = vi.sampler.gmm_parameters()
+    assert rel(ls, st64.log_std) < 1e-4 and (lg.double() - st64.logits.double()).abs().max() < 1e-4
+    want = torch.stack((st64.loc, st64.log_scale)) if reg_key == 'lognormal' else st64.log_w_reg.view(1)
+    assert rel(vi.sampler.reg_parameters()[:want.numel()], want) < 1e-6

@@ -1,0 +1,44 @@
+"""NIfTI-1 / legacy-VTK sample writers (reference logger/logger.py:35-102,215-238)"""
+import gzip
+import struct
+
+import numpy as np
+import torch
+
+
+def test_nifti_round_trip_and_header(tmp_path):
+    from irsgmcmc_b200.logger import load_im_from_disk, save_im_to_disk
+    rng = np.random.default_rng(0)
+    for arr in (rng.random((5, 6, 7), dtype=np.float32), rng.integers(0, 60, (4, 3, 2)).astype(np.int16),
+                rng.random((3, 3, 3)) > 0.5):
+        for name in ('a.nii', 'a.nii.gz'):
+            p = tmp_path / name
+            save_im_to_disk(torch.from_numpy(arr), str(p), spacing=torch.tensor([1.5, 2.0, 2.5]))
+            back, sp = load_im_from_disk(str(p))
+            assert back.shape == arr.shape and np.array_equal(back, arr.astype(back.dtype)) and np.allclose(sp, (1.5, 2.0, 2.5))
+    raw = gzip.open(tmp_path / 'a.nii.gz', 'rb').read()
+    assert struct.unpack_from('<i', raw, 0)[0] == 348 and raw[344:348] == b'n+1\0' and raw[123] == 2   # units: mm
+    assert struct.unpack_from('<h', raw, 254)[0] == 2 and struct.unpack_from('<f', raw, 108)[0] == 352.0
+    # data are in NIfTI (first index fastest) order
+    x = np.arange(24, dtype=np.float32).reshape(2, 3, 4)
+    save_im_to_disk(x, str(tmp_path / 'o.nii'))
+    raw = open(tmp_path / 'o.nii', 'rb').read()
+    assert np.array_equal(np.frombuffer(raw, '<f4', 3, 352), [x[0, 0, 0], x[1, 0, 0], x[0, 1, 0]])
+
+
+def test_vtk_field_round_trip_and_sample_names(tmp_path):
+    from irsgmcmc_b200.logger import load_field_from_disk, save_field_to_disk, save_grid_to_disk, save_sample
+    f = np.random.default_rng(1).standard_normal((3, 4, 5, 6)).astype(np.float32)
+    p = tmp_path / 'f.vtk'
+    save_field_to_disk(torch.from_numpy(f), str(p), spacing=(1.0, 2.0, 3.0))
+    back, sp = load_field_from_disk(str(p))
+    assert np.array_equal(back, f) and sp == [1.0, 2.0, 3.0]
+    head = open(p, 'rb').read(200).decode('ascii', 'ignore')
+    assert head.startswith('# vtk DataFile Version 3.0') and 'DATASET STRUCTURED_POINTS' in head and 'DIMENSIONS 4 5 6' in head
+    save_grid_to_disk(torch.from_numpy(f), str(tmp_path / 'g.vtk'))
+    assert b'DATASET STRUCTURED_GRID' in open(tmp_path / 'g.vtk', 'rb').read(120)
+    paths = save_sample(str(tmp_path / 's'), (2.0, 2.0, 2.0), 12, torch.rand(1, 1, 4, 5, 6), torch.from_numpy(f)[None],
+                        torch.rand(1, 4, 5, 6), model='MCMC', chain_no=3)
+    assert paths['displacement'].endswith('chain_3_sample_0000012_displacement.vtk')
+    d, _ = load_field_from_disk(paths['displacement'])
+    assert np.allclose(d, 2.0 * f)      # scaled by spacing[0] like the reference (logger/logger.py:223)
