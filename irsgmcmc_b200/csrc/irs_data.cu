@@ -10,7 +10,7 @@ namespace {
 
 constexpr int TX = 32, TY = 8;  // in-plane tile of the box filters; 256 threads = TX x TY
 
-enum { BOX_FWD_MEAN = 0, BOX_FWD_VAR = 1, BOX_BWD_VAR = 2, BOX_BWD_MEAN = 3 };
+enum { BOX_FWD_MEAN = 0, BOX_FWD_VAR = 1, BOX_BWD_VAR = 2, BOX_BWD_MEAN = 3, BOX_BWD_MEAN_WARP = 4 };
 
 // weight of input offset o for output position j in the ADJOINT of a replicate-padded box of half width S:
 // the out-of-range window positions of a border voxel were clamped onto it in the forward pass (fold)
@@ -27,6 +27,8 @@ __device__ __forceinline__ float adj_weight(int j, int o, int n, int S) {
 //   FWD_VAR  : in0 = a (pre: a^2), in1 = zF  -> out0 = rs = 1/sqrt(box/k^3 + 1e-10), out1 = z = zF - a rs  (zF null: a rs)
 //   BWD_VAR  : in0 = g, in1 = a, in2 = rs (pre: -g a rs^3 / 2) -> out0 = ga = g rs + 2 a adjbox/k^3        (g = sign * in0)
 //   BWD_MEAN : in0 = ga                      -> out0 = ga - adjbox/k^3
+//   BWD_MEAN_WARP : the same value g, then out0 (C,3,V) = g * out0 in place: out0 holds the warp's spatial gradient
+//              (irs_launch_warp_vox_fwd), the product is dL/du -- the warp adjoint as an epilogue
 // Plane-marching form: a CTA owns a 32 x 8 column of voxels and walks along a z segment.  Per plane: tile + halo S in
 // x / y goes through registers into a double-buffered shared-memory plane (pre-operation applied), x pass -> shared
 // memory, y pass -> one register per thread, and the z pass is a ring of 2S+1 registers; the next plane's global loads
@@ -37,7 +39,7 @@ __global__ void __launch_bounds__(256)
 box_march_kernel(const float* __restrict__ in0, const float* __restrict__ in1, const float* __restrict__ in2, float sign,
                  float* __restrict__ out0, float* __restrict__ out1, int seg_len, IrsDims d) {
     constexpr int EX = TX + 2 * S, EY = TY + 2 * S, NP = EX * EY, NE = (NP + 255) / 256, NT = 2 * S + 1;
-    constexpr bool BWD = (MODE == BOX_BWD_VAR || MODE == BOX_BWD_MEAN);
+    constexpr bool BWD = (MODE == BOX_BWD_VAR || MODE == BOX_BWD_MEAN || MODE == BOX_BWD_MEAN_WARP);
     __shared__ float P[2][NP];        // plane tile + halo (pre-operation applied), double-buffered
     __shared__ float X[EY * TX];      // x-pass result
 
@@ -164,8 +166,12 @@ box_march_kernel(const float* __restrict__ in0, const float* __restrict__ in1, c
                 if (out1 != nullptr) out1[gi] = in1 != nullptr ? in1[gi - off] - zn : zn;
             } else if (MODE == BOX_BWD_VAR) {
                 out0[gi] = sign * in0[gi] * in2[gi] + 2.0f * in1[gi] * box;
-            } else {
+            } else if (MODE == BOX_BWD_MEAN) {
                 out0[gi] = in0[gi] - box;
+            } else {
+                const float g = in0[gi] - box;
+                float* w = out0 + 3 * off + (size_t)gz * HW + gy * d.W + gx;
+                w[0] = g * w[0]; w[V] = g * w[V]; w[2 * (size_t)V] = g * w[2 * (size_t)V];
             }
         }
         if (p < p_last) stage(buf ^ 1);
@@ -770,8 +776,9 @@ int irs_launch_lcc_fwd(const float* im, const float* zF, int s, float* a, float*
 }
 
 int irs_launch_lcc_bwd(const float* g_z, float g_sign, const float* a, const float* rs, int s, float* work, float* g_im,
-                       int C, IrsDims d, cudaStream_t st) {
+                       int C, IrsDims d, cudaStream_t st, float* warp_grad) {
     IRS_TRY(launch_box<BOX_BWD_VAR>(g_z, a, rs, g_sign, work, nullptr, s, C, d, st));
+    if (warp_grad != nullptr) return launch_box<BOX_BWD_MEAN_WARP>(work, nullptr, nullptr, 1.f, warp_grad, nullptr, s, C, d, st);
     return launch_box<BOX_BWD_MEAN>(work, nullptr, nullptr, 1.f, g_im, nullptr, s, C, d, st);
 }
 

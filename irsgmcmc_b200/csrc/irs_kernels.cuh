@@ -73,8 +73,11 @@ struct IrsRng {
 int irs_sgld_step_scaled(const irs_sgld_config* cfg, const irs_sgld_buffers* b, void* stream, double reg_grad_scale);
 
 // --- irs_warp.cu: voxel-unit warps used by the fused step ------------------------------------------------------------
+// grad != nullptr: also writes d out / d position (C,3,V) -- the warp's adjoint becomes a multiplication (irs_launch_lcc_bwd's
+// epilogue, or irs_launch_warp_apply_grad)
 int irs_launch_warp_vox_fwd(const float* img, const float* u, IrsRng jit, float alpha, int use_jitter, float* out, int C,
-                            IrsDims d, cudaStream_t st);
+                            IrsDims d, cudaStream_t st, float* grad = nullptr);
+int irs_launch_warp_apply_grad(const float* g_out, float sign, float* grad, int C, IrsDims d, cudaStream_t st);
 int irs_launch_warp_vox_bwd(const float* img, const float* u, IrsRng jit, float alpha, int use_jitter,
                             const float* g_out, float g_sign, float* g_u, int C, IrsDims d, cudaStream_t st);
 
@@ -108,8 +111,9 @@ int irs_launch_ffd(const float* in, float* out, bool adjoint, const float (*kern
 // --- irs_data.cu ------------------------------------------------------------------------------------------------------
 int irs_launch_lcc_fwd(const float* im, const float* zF, int s, float* a, float* rs, float* z, int C, IrsDims d,
                        cudaStream_t st);
+// warp_grad != nullptr: g_im is not written; the last box pass multiplies it into warp_grad (C,3,V) in place = dL/du
 int irs_launch_lcc_bwd(const float* g_z, float g_sign, const float* a, const float* rs, int s, float* work, float* g_im,
-                       int C, IrsDims d, cudaStream_t st);
+                       int C, IrsDims d, cudaStream_t st, float* warp_grad = nullptr);
 int irs_data_blocks(IrsDims d);
 int irs_launch_gmm_stats_step(const float* z, const unsigned char* mask, double* hyper, const IrsHyperCfg& cfg,
                               double* partials, unsigned int* counter, double* stats_row, float* table_out,

@@ -227,7 +227,8 @@ static int sgld_step_impl(const irs_sgld_config* cfg, const irs_sgld_buffers* b,
     // (4) warp the moving image at T (+ jitter)                                   trainer.py:296-300
     IrsRng rng_j{b->jitter_unit, cfg->seed, iter_ptr, 0ull, cfg->chain_offset};
     const float alpha = (float)cfg->jitter_alpha;
-    IRS_TRY(irs_launch_warp_vox_fwd(b->moving, disp, rng_j, alpha, cfg->use_jitter, b->im_warped, C, d, st));
+    // ... and leave the warp's spatial gradient in field_a (free between the smoothing and the adjoint): stage 8 multiplies
+    IRS_TRY(irs_launch_warp_vox_fwd(b->moving, disp, rng_j, alpha, cfg->use_jitter, b->im_warped, C, d, st, b->field_a));
 
     mark(tm, st);
     // (5) residual map                                                            trainer.py:307
@@ -261,14 +262,13 @@ static int sgld_step_impl(const irs_sgld_config* cfg, const irs_sgld_buffers* b,
                                 d, st));
 
     mark(tm, st);
-    // (8) back through the residual map and the warp -> dL/du_n
+    // (8) back through the residual map and the warp -> dL/du_n = dL/dM_w * grad M(p): the product is the epilogue of the
+    // last adjoint box pass (utils/registration.py:29-30 backward without a second gather)
     if (cfg->data_term == IRS_DATA_LCC) {
-        IRS_TRY(irs_launch_lcc_bwd(b->scratch1, -1.f, b->lcc_a, b->lcc_rs, cfg->lcc_s, b->scratch2, b->scratch1, C, d, st));
-        IRS_TRY(irs_launch_warp_vox_bwd(b->moving, disp, rng_j, alpha, cfg->use_jitter, b->scratch1, 1.f, b->field_a, C,
-                                        d, st));
+        IRS_TRY(irs_launch_lcc_bwd(b->scratch1, -1.f, b->lcc_a, b->lcc_rs, cfg->lcc_s, b->scratch2, b->scratch1, C, d, st,
+                                   b->field_a));
     } else {
-        IRS_TRY(irs_launch_warp_vox_bwd(b->moving, disp, rng_j, alpha, cfg->use_jitter, b->scratch1, -1.f, b->field_a, C,
-                                        d, st));
+        IRS_TRY(irs_launch_warp_apply_grad(b->scratch1, -1.f, b->field_a, C, d, st));
     }
 
     mark(tm, st);

@@ -96,16 +96,44 @@ __device__ __forceinline__ void position_from_u(const float* __restrict__ u, con
     }
 }
 
+// GRAD: also leaves d out / d position (zero where the position sits on / outside the border) in grad (C,3,V): the adjoint of
+// the warp is then a multiplication by the incoming gradient -- an epilogue of the residual map's adjoint -- instead of a second
+// gather kernel that re-derives the position, re-generates the jitter and re-gathers the eight corners.
+template <bool GRAD>
 __global__ void __launch_bounds__(256)
 warp_vox_fwd_kernel(const float* __restrict__ img, const float* __restrict__ u, IrsRng jit, float alpha, int use_jitter,
-                    float* __restrict__ out, IrsDims d) {
+                    float* __restrict__ out, float* __restrict__ grad, IrsDims d) {
     const int V = (int)d.V();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= V) return;
     const int c = blockIdx.y;
     float px, py, pz;
     position_from_u(u + (size_t)c * 3 * V, jit, alpha, use_jitter, V, i, c, d, px, py, pz);
-    out[(size_t)c * V + i] = irs_body_warp_fwd(img, px, py, pz, d);
+    if (!GRAD) {
+        out[(size_t)c * V + i] = irs_body_warp_fwd(img, px, py, pz, d);
+    } else {
+        const float mx = irs_inside(px, d.W), my = irs_inside(py, d.H), mz = irs_inside(pz, d.D);
+        px = irs_clampf(px, 0.f, (float)(d.W - 1));
+        py = irs_clampf(py, 0.f, (float)(d.H - 1));
+        pz = irs_clampf(pz, 0.f, (float)(d.D - 1));
+        const IrsCell cell = irs_cell(px, py, pz, d);
+        float dx, dy, dz;
+        out[(size_t)c * V + i] = irs_interp_grad(cell, [&](int k) { return __ldg(img + k); }, dx, dy, dz);
+        float* g = grad + (size_t)c * 3 * V;
+        g[i] = dx * mx; g[V + i] = dy * my; g[2 * V + i] = dz * mz;
+    }
+}
+
+// g_u = (sign g_out) * grad, in place over grad (SSD: the residual map's adjoint is a sign)
+__global__ void __launch_bounds__(256)
+warp_apply_grad_kernel(const float* __restrict__ g_out, float sign, float* __restrict__ grad, IrsDims d) {
+    const int V = (int)d.V();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= V) return;
+    const int c = blockIdx.y;
+    const float go = sign * g_out[(size_t)c * V + i];
+    float* g = grad + (size_t)c * 3 * V;
+    g[i] = go * g[i]; g[V + i] = go * g[V + i]; g[2 * V + i] = go * g[2 * V + i];
 }
 
 __global__ void __launch_bounds__(256)
@@ -166,9 +194,16 @@ extern "C" int irs_warp3d_nearest_u8(const unsigned char* seg, long long seg_cs,
 }
 
 int irs_launch_warp_vox_fwd(const float* img, const float* u, IrsRng jit, float alpha, int use_jitter, float* out, int C,
-                            IrsDims d, cudaStream_t st) {
+                            IrsDims d, cudaStream_t st, float* grad) {
     dim3 grid((unsigned)((d.V() + 255) / 256), C);
-    warp_vox_fwd_kernel<<<grid, 256, 0, st>>>(img, u, jit, alpha, use_jitter, out, d);
+    if (grad != nullptr) warp_vox_fwd_kernel<true><<<grid, 256, 0, st>>>(img, u, jit, alpha, use_jitter, out, grad, d);
+    else warp_vox_fwd_kernel<false><<<grid, 256, 0, st>>>(img, u, jit, alpha, use_jitter, out, nullptr, d);
+    return (int)cudaGetLastError();
+}
+
+int irs_launch_warp_apply_grad(const float* g_out, float sign, float* grad, int C, IrsDims d, cudaStream_t st) {
+    dim3 grid((unsigned)((d.V() + 255) / 256), C);
+    warp_apply_grad_kernel<<<grid, 256, 0, st>>>(g_out, sign, grad, d);
     return (int)cudaGetLastError();
 }
 
