@@ -446,7 +446,7 @@ def main():
     ev = [torch.cuda.Event(), torch.cuda.Event()]
 
     def e2e_step(i):
-        sampler.commit_images()                                  # staged pair -> resident buffers, fixed-side LCC terms
+        sampler.commit_images()                                  # the uploaded pair becomes the resident set (pointer swap)
         sampler.prefetch_images(h_fixed, h_moving, h_mask)       # next step's pair: pinned host -> device, overlapped
         sampler.step(1, use_graph=use_graph)
         h_stats2[i & 1].copy_(sampler.stats, non_blocking=True)  # loss terms / alpha / energy of every chain
@@ -566,7 +566,8 @@ def main():
                 'iterations_per_s': args.steps / (ms_max * 1e-3), 'higher_is_better': True, 'scaling': 'weak',
                 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': workload_config(args, C, n),
                 'e2e': {'value': e2e_value, 'unit': 'voxel-steps/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
-                        'steps': e2e_steps, 'pipeline': 'double-buffered upload on a copy stream; per-step read-back pipelined by one step',
+                        'steps': e2e_steps, 'pipeline': 'two resident image sets: the upload of the next pair runs on a copy stream while this step computes, '
+                                    'committing it is a pointer swap (a CUDA graph per set); per-step read-back pipelined by one step',
                         'serial_value': e2e_serial_value},
                 'gpu_launches': sampler.launches_per_step() * args.steps,
                 'roofline': {'bound': 'hbm', 'kernel': 'svf_step_bwd_tma2_kernel', 'achieved': achieved, 'peak': peak,

@@ -149,8 +149,11 @@ class SGLDSampler:
         self._cconf = self._make_config()
         n_part = self.lib.irs_sgld_partials_doubles(ctypes.byref(self._cconf))
         self._partials = torch.zeros(max(int(n_part), 1), device=dev, dtype=torch.float64)
-        self._cbuf = None
-        self._graphs = {}   # transitions per replay -> captured CUDA graph
+        # launch arguments and captured graphs exist per IMAGE SET: the input pipeline alternates between two resident sets of
+        # (fixed, moving, mask, fixed-side LCC terms) so that committing an uploaded pair is a pointer swap, not a copy
+        self._set = 0
+        self._cbufs = [None, None]
+        self._graph_sets = [{}, {}]   # per set: transitions per replay -> captured CUDA graph
         self.iteration = 0
 
         # posterior moments (Welford): displacement (3,V) and warped image (1,V)
@@ -220,8 +223,20 @@ class SGLDSampler:
             b.ffd_scratch, b.ffd_work = p(self._ffd_scratch), p(self._ffd_work)
         return b
 
+    @property
+    def _cbuf(self):
+        return self._cbufs[self._set]
+
+    @_cbuf.setter
+    def _cbuf(self, value):
+        self._cbufs[self._set] = value
+
+    @property
+    def _graphs(self):
+        return self._graph_sets[self._set]
+
     def _invalidate(self):
-        self._cbuf, self._graphs = None, {}
+        self._cbufs, self._graph_sets = [None, None], [{}, {}]
 
     # ------------------------------------------------------------------------------------------------------------------
     # initialisation (reference trainer/trainer.py:529-547, 585-611)
@@ -395,18 +410,29 @@ class SGLDSampler:
             self._stage_ready.record(cs)
 
     @torch.no_grad()
-    def commit_images(self):
-        """Make the pair uploaded by prefetch_images() the current one: device-to-device copies into the resident buffers
-        whose addresses the captured graph holds (images, mask, fixed-side LCC terms)."""
+    def commit_images(self, swap=True):
+        """Make the pair uploaded by prefetch_images() the current one.  swap (default): the staging buffers BECOME the
+        resident set and the old resident set becomes the next staging area -- no device-to-device copies; launch
+        arguments and CUDA graphs are kept per set (the first transition on a set captures its graph).  swap=False copies
+        into the resident buffers instead (one set of graphs)."""
         if getattr(self, '_stage', None) is None:
             raise RuntimeError('commit_images() without a preceding prefetch_images()')
         cur = torch.cuda.current_stream()
         cur.wait_event(self._stage_ready)
-        self.fixed_im.copy_(self._stage[0], non_blocking=True)
-        self.moving_im.copy_(self._stage[1], non_blocking=True)
-        self.mask.copy_(self._stage[2], non_blocking=True)
-        if self.cfg.data_loss == 'lcc':
-            self.fixed_term.copy_(self._stage_term, non_blocking=True)
+        if swap:
+            (self.fixed_im, self.moving_im, self.mask), self._stage = self._stage, (self.fixed_im, self.moving_im, self.mask)
+            if self.cfg.data_loss == 'lcc':
+                self.fixed_term, self._stage_term = self._stage_term, self.fixed_term
+            else:
+                self.fixed_term = self.fixed_im
+            self._set ^= 1
+        else:
+            self.fixed_im.copy_(self._stage[0], non_blocking=True)
+            self.moving_im.copy_(self._stage[1], non_blocking=True)
+            self.mask.copy_(self._stage[2], non_blocking=True)
+            if self.cfg.data_loss == 'lcc':
+                self.fixed_term.copy_(self._stage_term, non_blocking=True)
+        # the next prefetch overwrites what is now the staging set: it must wait for the transitions enqueued so far
         self._stage_free.record(cur)
 
     # ------------------------------------------------------------------------------------------------------------------
