@@ -224,7 +224,7 @@ def run_config(tag, n, chains, data, world, rank, dev, peak, barrier, seg_dice=F
     cfg = SGLDConfig(data_loss=data, reg_loss='RegLoss_LogNormal' if lcc else 'RegLoss_L2', w_reg=1.6 if lcc else 1.4,
                      reg_learnable=lcc)
     sampler = SGLDSampler(fixed, moving, chains, cfg, device=dev, chain_offset=rank * chains)
-    sampler.init_chains('VI', vp, generator=torch.Generator(device=dev).manual_seed(123 + rank))
+    sampler.init_chains('VI', vp, generator=torch.Generator(device=dev).manual_seed(123))   # same draw on every rank (see main)
     sampler.init_gmm()
     seg_f = fixed['seg'].to(dev) if seg_dice else None
     counts = None
@@ -339,6 +339,7 @@ def main():
     ap.add_argument('--data', default='lcc', choices=['lcc', 'ssd'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--hyper-mode', default='reference', choices=['reference', 'per_chain', 'frozen'])
+    ap.add_argument('--as-rank', type=int, default=None, help='development: use the chain ids / seeds of this rank on one GPU')
     ap.add_argument('--no-graph', action='store_true')
     ap.add_argument('--e2e-steps', type=int, default=0, help='default: min(steps, 50)')
     ap.add_argument('--aten-gpu-baseline', action='store_true', help='(default at N = 1) also time the oracle port of the '
@@ -374,7 +375,9 @@ def main():
 
     n, C = args.size, args.chains
     V = n ** 3
-    fixed, moving, vp = make_pair(n)
+    if cores_per_rank:
+        torch.set_num_threads(cores_per_rank)   # host-side tensor code must not oversubscribe this rank's cores
+    fixed, moving, vp = make_pair(n, device=dev)   # filtering on the GPU; the pair itself lives on the host like a loader's
     reg = 'RegLoss_LogNormal' if args.data == 'lcc' else 'RegLoss_L2'
     ffd = dict(transformation='SVFFD_3D', cps=(args.cps,) * 3) if args.cps else {}
     cfg = SGLDConfig(data_loss=args.data, reg_loss=reg, w_reg=1.6 if args.data == 'lcc' else 1.4,
@@ -383,8 +386,15 @@ def main():
         from irsgmcmc_b200.utils import get_control_grid_size
         gdims = (1, 3, *get_control_grid_size((n, n, n), cfg.cps))
         vp = {'mu': torch.zeros(gdims), 'log_var': torch.full(gdims, math.log(0.5 ** 2)), 'u': torch.full(gdims, 0.1)}
-    sampler = SGLDSampler(fixed, moving, C, cfg, device=dev, chain_offset=rank * C)
-    gen = torch.Generator(device=dev).manual_seed(123 + rank)
+    # Weak scaling = the same work on every GPU: all ranks start from the SAME draw of q(v) (seed 123) and differ in their
+    # Langevin / jitter streams (Philox keyed by the global chain id).  With a different draw per rank the forward squaring steps
+    # differ by up to 16 % between ranks through the sign pattern of the velocity field alone (the rank-1 term x u of the draw
+    # makes the signs more or less coherent, which changes the shared-memory bank conflicts of the gather; same max |u|, same
+    # kernels: profiles/r2_rank_data_dependence.txt) -- the N > 1 curve then measures the luck of the draws, not the system.
+    # --as-rank R (development) reproduces rank R's old per-rank draw on one GPU.
+    data_rank = rank if args.as_rank is None else args.as_rank
+    sampler = SGLDSampler(fixed, moving, C, cfg, device=dev, chain_offset=data_rank * C)
+    gen = torch.Generator(device=dev).manual_seed(123 + (0 if args.as_rank is None else args.as_rank))
     sampler.init_chains('VI', vp, generator=gen)
     sampler.init_gmm()
     use_graph = not args.no_graph
@@ -405,11 +415,18 @@ def main():
         sampler.capture(g_len)
     n_warm = max(args.warmup, 20)
     n_warm = -(-n_warm // g_len) * g_len
-    sampler.step(n_warm, use_graph=use_graph)
-    barrier()
-    # every rank samples its own GPU's clocks (the timed region is one graph replay: the poller cannot delay it); rank 0's
-    # record is the line's `clocks`, the per-rank medians show whether a slow rank is a slow GPU
+    # every rank samples its own GPU's clocks (the regions are graph replays: the poller cannot delay them).  The sampler
+    # starts before the warm-up -- the same transitions, back to back with the timed ones -- because nvidia-smi needs ~0.1 s to
+    # deliver its first line and a 20-transition region lasts 18 ms; rank 0's record is the line's `clocks`, the per-rank
+    # medians show whether a slow rank is a slow GPU
     clocks = ClockSampler(local_rank)
+    t_load = time.perf_counter()
+    while True:    # at least the asked warm-up, and at least 0.6 s under load so that the clock samples are taken under load
+        sampler.step(n_warm, use_graph=use_graph)
+        torch.cuda.synchronize()
+        if time.perf_counter() - t_load > 0.6:
+            break
+    barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     sampler.step(args.steps, use_graph=use_graph)
@@ -526,7 +543,7 @@ def main():
     if default_headline and not args.no_configs:
         configs = []
         todo = [dict(tag='configs[0]: 64^3 SSD + RegLoss_L2, VI warm start iterations and 1 SGLD chain per GPU', n=64, chains=1, data='ssd',
-                     flush_l2=True, target_ms=300.0, vi=True, cpu_vi=not args.no_cpu_baseline),
+                     flush_l2=True, target_ms=300.0, vi=True, cpu_vi=world == 1 and not args.no_cpu_baseline),
                 dict(tag=f'configs[2]: 128^3 LCC, 64 chains sharded over {world} GPU(s) (strong scaling), Welford + NCCL merge',
                      n=128, chains=max(64 // world, 1), data='lcc', moments=True),
                 dict(tag='configs[3]: 256^3 LCC, 1 chain per GPU, segmentation warp + Dice per transition', n=256, chains=1,
@@ -544,8 +561,8 @@ def main():
                     raise
 
     cpu = None
-    if rank == 0 and not args.no_cpu_baseline:
-        n_cpu = n if n <= 128 else 128
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:   # the contract: rank 0 at N = 1 only (at N > 1 the ranks are
+        n_cpu = n if n <= 128 else 128                          # pinned to a share of the cores: a CPU baseline there is meaningless)
         v_cpu, ms_cpu, threads = oracle_transition_rate(n_cpu, 2, 0, 1, args.data, args.cps)
         cpu = {'value': v_cpu, 'unit': 'voxel-steps/s', 'cores': threads, 'kind': 'port',
                'sample': f'2 oracle transitions (oracle/sgld_oracle.py, torch CPU fp32, {threads} threads) at {n_cpu}^3, '
@@ -578,6 +595,7 @@ def main():
                                   'frac': step_gbs / peak},
                 'stage_ms': {k: round(v, 4) for k, v in stage_ms.items()},
                 'moments_merge_ms': merge_ms, 'moments_merge_bytes': merge_bytes, 'moments_merge_bus_gbs': merge_bus_gbs,
+                'svf_max_abs_u_per_step': [round(float(x), 4) for x in sampler._maxabs[:cfg.svf_steps].tolist()],
                 'graph': use_graph, 'transitions_per_graph': g_len, 'per_rank_ms_per_step': [x / args.steps for x in per_rank_ms], 'per_rank_sm_mhz': per_rank_mhz,
                 'host_cores_per_rank': cores_per_rank, 'clocks': clock_info, 'cpu_baseline': cpu}
         if configs is not None:

@@ -441,6 +441,21 @@ constexpr int WALK_PL = 4;         // planes per brick: 128 threads (= 512 voxel
 // lag-1 products along x, y and z read their forward neighbour from there and only the brick's last row / last plane
 // re-evaluates the mixture at the neighbour (1 + W/512 + 1/4 evaluations per voxel instead of 4).
 template <int KK>
+__device__ __noinline__ float gmm_halo4(const IrsGmm& gl, const float* __restrict__ z, const unsigned char* __restrict__ mask, int j,
+                                        float r0, float r1, float r2, float r3) {
+    const uchar4 n4 = *reinterpret_cast<const uchar4*>(mask + j);
+    if (!(n4.x | n4.y | n4.z | n4.w)) return 0.f;
+    const float4 q = __ldg(reinterpret_cast<const float4*>(z + j));
+    float rho[KK], w0, w1, w2, w3;
+    irs_gmm_eval_t<KK>(gl, q.x, rho, w0);
+    irs_gmm_eval_t<KK>(gl, q.y, rho, w1);
+    irs_gmm_eval_t<KK>(gl, q.z, rho, w2);
+    irs_gmm_eval_t<KK>(gl, q.w, rho, w3);
+    return (n4.x ? r0 * (q.x * q.x * w0) : 0.f) + (n4.y ? r1 * (q.y * q.y * w1) : 0.f) + (n4.z ? r2 * (q.z * q.z * w2) : 0.f) +
+           (n4.w ? r3 * (q.w * q.w * w3) : 0.f);
+}
+
+template <int KK>
 __device__ __forceinline__ void gmm_chain_accumulate(const IrsGmm& gl, const float* __restrict__ z,
                                                      const unsigned char* __restrict__ mask, bool vd, IrsDims d, int block,
                                                      int nblocks, float (&acc)[IRS_SUM_COUNT], float4* __restrict__ R) {
@@ -463,15 +478,9 @@ __device__ __forceinline__ void gmm_chain_accumulate(const IrsGmm& gl, const flo
         irs_gmm_eval_t<KK>(gl, zi, rho, wp);
         return zi * zi * wp;
     };
-    // sum_e r_e * r(neighbour e) with the neighbours at j: the four evaluations run side by side (the loop is bound by the
-    // latency of the exp / log chains, not by issue slots)
-    auto halo4 = [&](int j, float r0, float r1, float r2, float r3) {
-        const uchar4 n4 = *reinterpret_cast<const uchar4*>(mask + j);
-        if (!(n4.x | n4.y | n4.z | n4.w)) return 0.f;
-        const float4 q = __ldg(reinterpret_cast<const float4*>(z + j));
-        const float q0 = res(q.x), q1 = res(q.y), q2 = res(q.z), q3 = res(q.w);
-        return (n4.x ? r0 * q0 : 0.f) + (n4.y ? r1 * q1 : 0.f) + (n4.z ? r2 * q2 : 0.f) + (n4.w ? r3 * q3 : 0.f);
-    };
+    // sum_e r_e * r(neighbour e) with the neighbours at j (brick faces only: kept out of line so that the kernel carries one
+    // copy of the four side-by-side evaluations instead of two per path -- the code had outgrown the instruction cache)
+    auto halo4 = [&](int j, float r0, float r1, float r2, float r3) { return gmm_halo4<KK>(gl, z, mask, j, r0, r1, r2, r3); };
     const bool vec = d.W >= 4 && (512 % d.W) == 0 && blockDim.x == WALK_T &&
                      ((reinterpret_cast<uintptr_t>(z) | reinterpret_cast<uintptr_t>(mask)) & 15) == 0;
     if (vec) {
@@ -531,7 +540,7 @@ __device__ __forceinline__ void gmm_chain_accumulate(const IrsGmm& gl, const flo
     }
 }
 
-template <bool SERIAL>
+template <bool SERIAL, int KK>
 __global__ void __launch_bounds__(WALK_T, 1)
 gmm_chain_walk_kernel(const float* __restrict__ z_all, const unsigned char* __restrict__ mask, double* __restrict__ hyper_all,
                       long long hyper_stride, IrsHyperCfg cfg, int frozen, double* __restrict__ partials_all,
@@ -566,8 +575,7 @@ gmm_chain_walk_kernel(const float* __restrict__ z_all, const unsigned char* __re
 #pragma unroll
         for (int k = 0; k < IRS_SUM_COUNT; ++k) acc[k] = 0.f;
         const float* z = z_all + (size_t)c * V;
-        if (gl.K <= 4) gmm_chain_accumulate<4>(gl, z, mask, cfg.virtual_decimation != 0, d, blockIdx.x, gridDim.x, acc, R);
-        else gmm_chain_accumulate<IRS_MAX_K>(gl, z, mask, cfg.virtual_decimation != 0, d, blockIdx.x, gridDim.x, acc, R);
+        gmm_chain_accumulate<KK>(gl, z, mask, cfg.virtual_decimation != 0, d, blockIdx.x, gridDim.x, acc, R);
         double blk[IRS_SUM_COUNT];
         irs_block_sum<IRS_SUM_COUNT>(acc, blk, sh);
         if (irs_grid_sum<IRS_SUM_COUNT>(blk, partials_all + (size_t)c * partials_stride, counters + c, total, n_used)) {
@@ -818,16 +826,25 @@ int irs_launch_gmm_chain_walk(const float* z, const unsigned char* mask, double*
     if (serial) {
         const int G = (int)(want < sms ? want : sms);           // all CTAs resident: they wait for each other
         if ((long long)G * IRS_SUM_COUNT > partials_stride) return IRS_ERR_WORKSPACE;
-        gmm_chain_walk_kernel<true><<<G, WALK_T, 0, st>>>(z, mask, hyper, 0, cfg, 0, partials, partials_stride, counters,
-                                                          counters + C, stats, tables, C, d);
+        if (cfg.K <= 4)
+            gmm_chain_walk_kernel<true, 4><<<G, WALK_T, 0, st>>>(z, mask, hyper, 0, cfg, 0, partials, partials_stride, counters,
+                                                                 counters + C, stats, tables, C, d);
+        else
+            gmm_chain_walk_kernel<true, IRS_MAX_K><<<G, WALK_T, 0, st>>>(z, mask, hyper, 0, cfg, 0, partials, partials_stride,
+                                                                         counters, counters + C, stats, tables, C, d);
     } else {
         long long per_chain = (2LL * sms + C - 1) / C;          // about two waves of CTAs over all chains
         if (per_chain < 1) per_chain = 1;
         if (want > per_chain) want = per_chain;
         if (want * IRS_SUM_COUNT > partials_stride) return IRS_ERR_WORKSPACE;
         dim3 grid((unsigned)want, C);
-        gmm_chain_walk_kernel<false><<<grid, WALK_T, 0, st>>>(z, mask, hyper, hyper_stride, cfg, frozen, partials,
-                                                             partials_stride, counters, counters + C, stats, tables, C, d);
+        if (cfg.K <= 4)
+            gmm_chain_walk_kernel<false, 4><<<grid, WALK_T, 0, st>>>(z, mask, hyper, hyper_stride, cfg, frozen, partials,
+                                                                    partials_stride, counters, counters + C, stats, tables, C, d);
+        else
+            gmm_chain_walk_kernel<false, IRS_MAX_K><<<grid, WALK_T, 0, st>>>(z, mask, hyper, hyper_stride, cfg, frozen, partials,
+                                                                            partials_stride, counters, counters + C, stats,
+                                                                            tables, C, d);
     }
     return (int)cudaGetLastError();
 }

@@ -714,7 +714,7 @@ constexpr size_t svf_fwd_tile_smem_compact(int R) {
 }
 
 // maxabs_prev = max |u_{k-1}| of the previous step (nullptr for the first): |u_k| <= 2 max |u_{k-1}|, so the TMA ring is
-// taken when that bound is below 1, the wider non-TMA ring otherwise
+// taken when that bound is below three voxels (see `small` below), the wider non-TMA ring otherwise
 // CTAS = resident CTAs per SM the kernel is compiled for (register cap 65536 / 256 / CTAS).  ENERGY (first step only):
 // also reduces the regulariser energy of the input field per chain -- block sums in double, partials[blockIdx.x], the
 // last block of the chain adds them in block order (deterministic) -> energy[chain * energy_stride].
@@ -739,7 +739,12 @@ svf_step_fwd_tma_kernel(const __grid_constant__ CUtensorMap tmap, const float* _
     const int x0t = bx * TILE_X, y0t = by * TILE_Y, zs = bz * seg_len, ze = min(zs + seg_len, d.D);
     const float* in = in_all + (size_t)blockIdx.y * 3 * V;
     float* out = out_all + (size_t)blockIdx.y * 3 * V;
-    const bool small = maxabs_prev == nullptr || 2.f * __ldg(maxabs_prev) < 0.999f;   // always true for the first step
+    // The TMA body is exact for any field: a voxel whose |u| reaches one voxel takes the global gather on its own.  It is the
+    // faster choice as long as such voxels are a minority (they are spatially coherent, so whole warps go one way or the other):
+    // measured, a step whose bound 2 max|u_{k-1}| just exceeds one voxel cost 3x in the wide-ring kernel although only a few
+    // voxels were affected (16 % of the whole forward pass on a 128^3 chain).  Only when the bound says that displacements of
+    // several voxels are common does the wide ring (R = 2, then global gathers) take the whole step.
+    const bool small = maxabs_prev == nullptr || 2.f * __ldg(maxabs_prev) < 3.0f;   // always true for the first step
     float m, e_acc = 0.f;
     if (small) m = svf_fwd_tma_body<FWD_BW, ENERGY>(&tmap, in, in_scale, out, d, blockIdx.y, x0t, y0t, zs, ze, smem, e_acc);
     else m = svf_fwd_tile_body_cold(in, in_scale, out, d, x0t, y0t, zs, ze, smem);
