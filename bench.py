@@ -27,8 +27,8 @@ BYTES_PER_VOXEL_STEP_LCC = 895.0  # 175 + 60 * n_svf
 BYTES_PER_VOXEL_STEP_SSD = 875.0
 SVF_BWD_BYTES_PER_VOXEL = 36.0    # read g_{k+1} 12 + u_k 12, write g_k 12
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE svf_step_bwd_tma2_kernel launch from the committed ncu --set full capture
-# (profiles/r1_ncu_final_summary.txt; 128^3, one chain).  Below the algorithmic 75.5 MB: the 24 MB result stays in the L2.
-NCU_TRAFFIC_BYTES = {(128, 1, 'lcc'): 50.777e6 + 3.067e6}
+# (profiles/r2_ncu_final_summary.txt; 128^3, one chain).  Below the algorithmic 75.5 MB: the 24 MB result stays in the L2.
+NCU_TRAFFIC_BYTES = {(128, 1, 'lcc'): 50.900e6 + 4.270e6}
 
 
 def measured_peaks():
@@ -241,8 +241,8 @@ def run_config(tag, n, chains, data, world, rank, dev, peak, barrier, seg_dice=F
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    for _ in range(3):
-        one()
+    for _ in range(20):     # the same warm-up as the headline (>= 20 transitions): the speed of the SVF kernels depends on the state
+        one()               # of the chain (sign pattern of the field), so every configuration is timed equally far from its start
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record(); one(); one(); e1.record()
@@ -270,7 +270,7 @@ def run_config(tag, n, chains, data, world, rank, dev, peak, barrier, seg_dice=F
     value = world * chains * V * K / (ms * 1e-3)
     bytes_step = BYTES_PER_VOXEL_STEP_LCC if lcc else BYTES_PER_VOXEL_STEP_SSD
     out = {'config': tag, 'volume': [n, n, n], 'data_term': 'LCC+GMM(K=4)' if lcc else 'SSD(K=1)',
-           'chains_per_gpu': chains, 'chains_total': chains * world, 'steps': K, 'warmup': 5,
+           'chains_per_gpu': chains, 'chains_total': chains * world, 'steps': K, 'warmup': 22,
            'ms_per_step': ms / K, 'voxel_steps_per_s': value, 'iterations_per_s': K / (ms * 1e-3),
            'step_roofline_frac': bytes_step * (value / world) / 1e9 / peak, 'bytes_per_voxel_step': bytes_step,
            'gpu_launches_per_step': sampler.launches_per_step() + (3 if seg_dice else 0),
