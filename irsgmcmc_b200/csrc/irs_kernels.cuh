@@ -95,6 +95,9 @@ int irs_launch_langevin(const float* v, const float* sigma, long long sigma_cs, 
                         int C, IrsDims d, cudaStream_t st);
 int irs_launch_smooth3(const float* in, float* work, float* out, const IrsTaps& taps, int C, IrsDims d,
                        cudaStream_t st);
+// out = S * (v + coef sigma eps); work: (C,3,V) scratch
+int irs_launch_langevin_smooth3(const float* v, const float* sigma, long long sigma_cs, float coef, IrsRng rng, float* work,
+                                float* out, const IrsTaps& taps, int C, IrsDims d, cudaStream_t st);
 int irs_launch_reg_energy(const float* v, double* energy, long long energy_stride, double* partials,
                           unsigned int* counters, int C, IrsDims d, cudaStream_t st);
 int irs_reg_energy_blocks(IrsDims d);

@@ -109,6 +109,13 @@ int check_config(const irs_sgld_config* c) {
 }
 
 inline bool has_ffd(const irs_sgld_config* c) { return c->ffd_cps[0] > 0; }
+// mirrors the choice of irs_launch_langevin_smooth3 (the state grid: the control grid with the FFD); pointer alignment is assumed
+inline bool langevin_fused(const irs_sgld_config* c) {
+    static int env = -1;
+    if (env < 0) { const char* e = getenv("IRS_LANGEVIN_FUSED"); env = (e && atoi(e) == 0) ? 0 : 1; }
+    const int W = has_ffd(c) ? c->ffd_grid[2] : c->W;
+    return env == 1 && W % 4 == 0 && (c->n_taps == 3 || c->n_taps == 5 || c->n_taps == 7);
+}
 // one persistent launch for the mixture step of all chains (irs_launch_gmm_chain_walk) instead of two launches per chain.
 // Always for the chain-parallel hyper modes.  In the reference mode (chains in order on the shared mixture) the walk wins where
 // a chain is small and the two launches are pure latency (measured, 64 chains: 64^3 1.45 vs 1.77 ms; 128^3 3.13 vs 2.56 ms --
@@ -140,8 +147,8 @@ extern "C" size_t irs_sgld_partials_doubles(const irs_sgld_config* cfg) {
 
 extern "C" int irs_sgld_launches_per_step(const irs_sgld_config* c) {
     if (check_config(c) != IRS_OK) return -1;
-    int n = 1;                                   // langevin
-    n += c->n_taps > 0 ? 3 : 0;                  // Sobolev z, y, x
+    int n = 1;                                   // langevin (fused with the x / y smoothing when the field can be vectorised)
+    n += c->n_taps > 0 ? (langevin_fused(c) ? 1 : 3) : 0;   // Sobolev: z pass only / z, y, x
     n += (c->W % 4 == 0 && !has_ffd(c)) ? 0 : 1; // regulariser energy (an epilogue of the first squaring step otherwise)
     n += has_ffd(c) ? 6 : 0;                     // B-spline FFD: three axis passes forward, three for the adjoint
     n += c->svf_steps;                           // scaling and squaring
@@ -201,8 +208,7 @@ static int sgld_step_impl(const irs_sgld_config* cfg, const irs_sgld_buffers* b,
         IrsTaps taps;
         taps.n = cfg->n_taps;
         for (int t = 0; t < cfg->n_taps; ++t) taps.w[t] = cfg->taps[t];
-        IRS_TRY(irs_launch_langevin(b->v, b->sigma, b->sigma_chain_stride, coef, rng_l, smooth_work, C, ds, st));
-        IRS_TRY(irs_launch_smooth3(smooth_work, smooth_work, b->css, taps, C, ds, st));
+        IRS_TRY(irs_launch_langevin_smooth3(b->v, b->sigma, b->sigma_chain_stride, coef, rng_l, smooth_work, b->css, taps, C, ds, st));
     } else {
         IRS_TRY(irs_launch_langevin(b->v, b->sigma, b->sigma_chain_stride, coef, rng_l, b->css, C, ds, st));
     }
@@ -344,8 +350,7 @@ extern "C" int irs_sgld_gmm_init(const irs_sgld_config* cfg, const irs_sgld_buff
         IrsTaps taps;
         taps.n = cfg->n_taps;
         for (int t = 0; t < cfg->n_taps; ++t) taps.w[t] = cfg->taps[t];
-        IRS_TRY(irs_launch_langevin(v_sample, nullptr, 0, 0.f, none, smooth_work, 1, ds, st));
-        IRS_TRY(irs_launch_smooth3(smooth_work, smooth_work, b->css, taps, 1, ds, st));
+        IRS_TRY(irs_launch_langevin_smooth3(v_sample, nullptr, 0, 0.f, none, smooth_work, b->css, taps, 1, ds, st));
     } else {
         IRS_TRY(irs_launch_langevin(v_sample, nullptr, 0, 0.f, none, b->css, 1, ds, st));
     }

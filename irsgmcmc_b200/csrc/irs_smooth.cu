@@ -1,6 +1,9 @@
 // irs_smooth.cu -- Langevin proposal, Sobolev smoothing, diffusion regulariser, preconditioned SGD update
 // (reference utils/functions.py:76-109, utils/util.py:48-58,394-404, utils/diff_op.py:78-96, model/loss.py:152-161,
 //  trainer/trainer.py:351)
+#include <cstdlib>
+#include <mutex>
+
 #include "irs_kernels.cuh"
 
 namespace {
@@ -175,6 +178,142 @@ langevin_vec_kernel(const float* __restrict__ v, const float* __restrict__ sigma
         }
     }
     st4(oc + i, a[0]); st4(oc + V + i, a[1]); st4(oc + 2 * V + i, a[2]);
+}
+
+// ---- Langevin proposal + x and y smoothing in ONE kernel ---------------------------------------------------------------------
+// A CTA owns TY full rows of one z-plane (all three components): the noisy state v + coef sigma eps of those rows plus a halo
+// of s rows on either side goes to shared memory (the halo rows regenerate their Philox numbers -- a voxel's noise is a pure
+// function of (seed, chain, iteration, voxel) -- 2 s / TY more generator work, against a whole pass over the field saved),
+// is smoothed along x in place (one float4 per thread per round, neighbours read before anybody writes) and along y on the way
+// out.  The z pass that follows is the only other pass: 12 + 12 (+ halo) read, 12 written here, 12 + 12 there, instead of four
+// passes of 24 B.  Separable smoothing passes commute (replicate padding acts per axis), so x, y, z instead of the reference's
+// z, y, x changes the result at rounding level only (checked against the oracle at 1e-5 like before).
+template <int NT, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
+langevin_xy_kernel(const float* __restrict__ v, const float* __restrict__ sigma, long long sigma_cs, float coef, IrsRng rng,
+                   float* __restrict__ out, IrsTaps taps, int TY, IrsDims d) {
+    extern __shared__ __align__(16) float S[];   // [3][R][W], R = TY + 2 s
+    constexpr int s = (NT - 1) / 2;
+    const int V = (int)d.V(), W = d.W, W4 = W / 4, R = TY + 2 * s, CS = R * W;
+    const int tiles_y = (d.H + TY - 1) / TY;
+    const int z = blockIdx.x / tiles_y, y0 = (blockIdx.x - z * tiles_y) * TY;
+    const int c = blockIdx.y;
+    const float* vc = v + (size_t)c * 3 * V;
+    const int units = R * W4;
+    const unsigned long long it = (coef != 0.f && rng.explicit_values == nullptr)
+                                      ? (rng.iter_ptr ? (unsigned long long)(*rng.iter_ptr) : rng.iter) : 0ull;
+    // ---- noisy state of rows y0 - s .. y0 + TY - 1 + s (clamped = replicate padding along y) ----
+    for (int u = threadIdx.x; u < units; u += blockDim.x) {
+        const int r = u / W4, x4 = u - r * W4;
+        const int gy = irs_clampi(y0 - s + r, 0, d.H - 1);
+        const int i = (z * d.H + gy) * W + 4 * x4;
+        float4 a[3] = {ld4(vc + i), ld4(vc + V + i), ld4(vc + 2 * V + i)};
+        if (coef != 0.f) {
+            float e[4][3];
+            if (rng.explicit_values != nullptr) {
+                const float* ec = rng.explicit_values + (size_t)c * 3 * V;
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch) {
+                    const float4 t = ld4(ec + ch * V + i);
+                    e[0][ch] = t.x; e[1][ch] = t.y; e[2][ch] = t.z; e[3][ch] = t.w;
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) irs_normal3(rng.seed, (uint32_t)(i + k), (uint32_t)(rng.chain0 + c), it, e[k]);
+            }
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) {
+                float4 sg = make_float4(1.f, 1.f, 1.f, 1.f);
+                if (sigma != nullptr) sg = ld4(sigma + (size_t)c * sigma_cs + (size_t)ch * V + i);
+                a[ch].x += coef * sg.x * e[0][ch]; a[ch].y += coef * sg.y * e[1][ch];
+                a[ch].z += coef * sg.z * e[2][ch]; a[ch].w += coef * sg.w * e[3][ch];
+            }
+        }
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) *reinterpret_cast<float4*>(S + ch * CS + r * W + 4 * x4) = a[ch];
+    }
+    __syncthreads();
+    // ---- x pass, in place: every thread reads the three aligned float4 of its unit, then all write ----
+    for (int base = 0; base < units; base += blockDim.x) {
+        const int u = base + threadIdx.x;
+        const bool valid = u < units;
+        float4 o[3];
+        if (valid) {
+            const int r = u / W4, x4 = u - r * W4;
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) {
+                const float* row = S + ch * CS + r * W;
+                const float4 cc = *reinterpret_cast<const float4*>(row + 4 * x4);
+                const float4 l = x4 > 0 ? *reinterpret_cast<const float4*>(row + 4 * x4 - 4) : make_float4(cc.x, cc.x, cc.x, cc.x);
+                const float4 rr = x4 + 1 < W4 ? *reinterpret_cast<const float4*>(row + 4 * x4 + 4) : make_float4(cc.w, cc.w, cc.w, cc.w);
+                const float w[12] = {l.x, l.y, l.z, l.w, cc.x, cc.y, cc.z, cc.w, rr.x, rr.y, rr.z, rr.w};
+                float q[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int t = 0; t < NT; ++t) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) q[k] += taps.w[t] * w[4 + k + t - s];
+                }
+                o[ch] = make_float4(q[0], q[1], q[2], q[3]);
+            }
+        }
+        __syncthreads();
+        if (valid) {
+            const int r = u / W4, x4 = u - r * W4;
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) *reinterpret_cast<float4*>(S + ch * CS + r * W + 4 * x4) = o[ch];
+        }
+        __syncthreads();
+    }
+    // ---- y pass on the way out ----
+    float* oc = out + (size_t)c * 3 * V;
+    for (int u = threadIdx.x; u < TY * W4; u += blockDim.x) {
+        const int ry = u / W4, x4 = u - ry * W4, y = y0 + ry;
+        if (y >= d.H) continue;
+        const int i = (z * d.H + y) * W + 4 * x4;
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+            const float* col = S + ch * CS + ry * W + 4 * x4;
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int t = 0; t < NT; ++t) acc = fma4(taps.w[t], *reinterpret_cast<const float4*>(col + t * W), acc);
+            st4(oc + ch * V + i, acc);
+        }
+    }
+}
+
+template <int NT>
+static int launch_langevin_xy_nt(const float* v, const float* sigma, long long sigma_cs, float coef, const IrsRng& rng,
+                                 float* work, float* out, const IrsTaps& taps, int C, IrsDims d, cudaStream_t st) {
+    constexpr int s = (NT - 1) / 2;
+    static int ty_env = -1, t_env = -1;
+    if (ty_env < 0) { const char* e = getenv("IRS_LANGEVIN_TY"); ty_env = e ? atoi(e) : 0; }
+    if (t_env < 0) { const char* e = getenv("IRS_LANGEVIN_T"); t_env = e ? atoi(e) : 0; }
+    int TY = ty_env > 0 ? ty_env : 32;
+    while (TY > 8 && (size_t)3 * (TY + 2 * s) * d.W * 4 > 100 * 1024) TY -= 8;
+    if (TY > d.H) TY = d.H;
+    const size_t smem = (size_t)3 * (TY + 2 * s) * d.W * 4;
+    if (smem > 200 * 1024) return IRS_ERR_UNSUPPORTED;
+    const bool small_cta = t_env == 256;
+    static std::mutex mu;
+    static bool ready[64] = {};
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (!ready[dev & 63]) {
+            cudaError_t e = cudaFuncSetAttribute(langevin_xy_kernel<NT, 512, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            if (e == cudaSuccess)
+                e = cudaFuncSetAttribute(langevin_xy_kernel<NT, 256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            if (e != cudaSuccess) return (int)e;
+            ready[dev & 63] = true;
+        }
+    }
+    dim3 grid((unsigned)(((d.H + TY - 1) / TY) * d.D), C);
+    if (small_cta) langevin_xy_kernel<NT, 256, 4><<<grid, 256, smem, st>>>(v, sigma, sigma_cs, coef, rng, work, taps, TY, d);
+    else langevin_xy_kernel<NT, 512, 2><<<grid, 512, smem, st>>>(v, sigma, sigma_cs, coef, rng, work, taps, TY, d);
+    dim3 vgrid((unsigned)((d.V() / 4 + 255) / 256), C * 3);
+    smooth_axis_vec_kernel<2, NT><<<vgrid, 256, 0, st>>>(work, out, taps, d);
+    return (int)cudaGetLastError();
 }
 
 // d energy / d v for four consecutive x voxels of one channel (row neighbours from the aligned neighbours l, r)
@@ -431,6 +570,24 @@ int irs_launch_smooth3(const float* in, float* work, float* out, const IrsTaps& 
     return (int)cudaGetLastError();
 }
 
+// Langevin proposal + separable smoothing: two kernels (noise + x + y on shared-memory rows, then z) when the field can be
+// vectorised, the four-pass sequence otherwise.  IRS_LANGEVIN_FUSED=0 keeps the four passes (development switch).
+int irs_launch_langevin_smooth3(const float* v, const float* sigma, long long sigma_cs, float coef, IrsRng rng, float* work,
+                                float* out, const IrsTaps& taps, int C, IrsDims d, cudaStream_t st) {
+    static int fused = -1;
+    if (fused < 0) { const char* e = getenv("IRS_LANGEVIN_FUSED"); fused = (e && atoi(e) == 0) ? 0 : 1; }
+    if (fused && vec_ok(d, v, sigma, out, rng.explicit_values) && vec_ok(d, work) && (sigma_cs % 4) == 0 &&
+        (taps.n == 3 || taps.n == 5 || taps.n == 7) && (size_t)3 * (8 + taps.n - 1) * d.W * 4 <= 200 * 1024) {
+        switch (taps.n) {
+            case 3: return launch_langevin_xy_nt<3>(v, sigma, sigma_cs, coef, rng, work, out, taps, C, d, st);
+            case 5: return launch_langevin_xy_nt<5>(v, sigma, sigma_cs, coef, rng, work, out, taps, C, d, st);
+            default: return launch_langevin_xy_nt<7>(v, sigma, sigma_cs, coef, rng, work, out, taps, C, d, st);
+        }
+    }
+    IRS_TRY(irs_launch_langevin(v, sigma, sigma_cs, coef, rng, work, C, d, st));
+    return irs_launch_smooth3(work, work, out, taps, C, d, st);
+}
+
 int irs_reg_energy_blocks(IrsDims d) {
     long long b = (d.V() + 255) / 256;
     return (int)(b < 592 ? b : 592);  // 4 CTAs per SM x 148 SMs
@@ -472,10 +629,7 @@ extern "C" int irs_langevin_sobolev(const float* v, const float* sigma, long lon
     IrsTaps taps;
     taps.n = n_taps;
     for (int t = 0; t < n_taps; ++t) taps.w[t] = taps_host[t];
-    IRS_TRY(irs_launch_langevin(v, sigma, sigma_cs, coef, rng, work, C, d, st));
-    // z pass reads `work`, so route: work -> out -> work -> out needs a third buffer; instead do work -> out (z),
-    // out -> work (y), work -> out (x)
-    return irs_launch_smooth3(work, work, out, taps, C, d, st);
+    return irs_launch_langevin_smooth3(v, sigma, sigma_cs, coef, rng, work, out, taps, C, d, st);
 }
 
 extern "C" int irs_diff_fwd(const float* v, float* nabla, int transformation, int C, int D, int H, int W,
