@@ -152,7 +152,7 @@ extern "C" int irs_sgld_launches_per_step(const irs_sgld_config* c) {
     n += (c->W % 4 == 0 && !has_ffd(c)) ? 0 : 1; // regulariser energy (an epilogue of the first squaring step otherwise)
     n += has_ffd(c) ? 6 : 0;                     // B-spline FFD: three axis passes forward, three for the adjoint
     n += c->svf_steps;                           // scaling and squaring
-    n += c->svf_steps > 4 ? 4 : c->svf_steps - 1; // cell maps behind the last four steps (exit at once below one voxel)
+    n += c->svf_steps > 1 ? 1 : 0;               // cell maps of the last four steps, one launch (exits at once below one voxel)
     n += 1;                                      // warp
     n += c->data_term == IRS_DATA_LCC ? 2 : 1;   // LCC boxes / SSD residual
     n += gmm_walk_enabled(c) ? 1 : c->C * (c->virtual_decimation ? 2 : 1);   // mixture statistics + VD factor + Adam of all chains

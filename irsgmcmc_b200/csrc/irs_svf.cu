@@ -78,11 +78,20 @@ __device__ __forceinline__ float cells_region_max(const IrsCells& cm, int chain,
 
 // Cell map of one field, computed only when somebody needs it: the step's max |u| has reached one voxel (the adjoint then
 // picks its window per tile).  One block per cell; launched behind the last forward steps, exits at once otherwise.
+// blockIdx.z selects the step k = k_first + z: ONE launch behind the forward pass covers the (up to four) late steps that can
+// reach one voxel -- as four launches the early exits alone cost ~2.5 us each in every transition.
 __global__ void __launch_bounds__(256)
-svf_cells_kernel(const float* __restrict__ u_all, float scale, const float* __restrict__ maxabs, IrsCells cm, IrsDims d) {
+svf_cells_kernel(const float* __restrict__ v_all, const float* __restrict__ hist, float scale0, float* __restrict__ maxabs,
+                 int n_steps, int k_first, long long F, int C, IrsDims d) {
     irs_pdl_wait();
     irs_pdl_launch_dependents();
-    if ((int)floorf(__ldg(maxabs) + 1e-3f) + 1 < 2) return;   // = svf_gather_radius(max |u_k|) < 2: nobody reads the map
+    const int k = k_first + blockIdx.z;
+    if ((int)floorf(__ldg(maxabs + k) + 1e-3f) + 1 < 2) return;   // = svf_gather_radius(max |u_k|) < 2: nobody reads the map
+    IrsCells cm;
+    cm.nx = (d.W + CELL_X - 1) / CELL_X; cm.ny = (d.H + CELL_Y - 1) / CELL_Y; cm.nz = (d.D + CELL_Z - 1) / CELL_Z;
+    cm.p = maxabs + n_steps + (size_t)k * C * cm.nx * cm.ny * cm.nz;
+    const float* u_all = (k == 0) ? v_all : hist + (size_t)(k - 1) * F;
+    const float scale = (k == 0) ? scale0 : 1.0f;
     const int cx = blockIdx.x % cm.nx, cy = (blockIdx.x / cm.nx) % cm.ny, cz = blockIdx.x / (cm.nx * cm.ny), chain = blockIdx.y;
     const int V = (int)d.V();
     const float* u = u_all + (size_t)chain * 3 * V;
@@ -1492,11 +1501,14 @@ int irs_launch_svf_fwd(const float* v, float* hist, float* maxabs, int n_steps, 
     // Cell map of the input of step k (= the field the adjoint of step k gathers from).  Only the last four steps can reach one
     // voxel for |v| < 16 voxels (|u_k| <= |v| / 2^(n-k)); earlier steps keep the step-wide radius.  The kernel exits at once
     // unless max |u_k| >= 1, and with programmatic dependent launch it is invisible in graph replay.
-    auto launch_cells = [&](int k, const float* in, float in_scale) -> cudaError_t {
-        if (k < n_steps - 4 || k == 0) return cudaSuccess;
-        IrsCells cm = make_cells(maxabs, n_steps, k, C, d);
-        dim3 grid((unsigned)(cm.nx * cm.ny * cm.nz), C);
-        return irs_launch_pdl(svf_cells_kernel, grid, dim3(256), 0, st, in, in_scale, (const float*)(maxabs + k), cm, d);
+    // one launch behind the whole forward pass (the maps are read by the adjoint only)
+    auto launch_cells = [&]() -> cudaError_t {
+        const int k_first = n_steps > 4 ? n_steps - 4 : 1;
+        if (k_first >= n_steps) return cudaSuccess;
+        IrsCells cm = make_cells(maxabs, n_steps, k_first, C, d);
+        dim3 grid((unsigned)(cm.nx * cm.ny * cm.nz), C, n_steps - k_first);
+        return irs_launch_pdl(svf_cells_kernel, grid, dim3(256), 0, st, v, (const float*)hist, scale0, maxabs, n_steps, k_first,
+                              (long long)F, C, d);
     };
     constexpr int RF = 2;
     const int tiles = ((d.W + TILE_X - 1) / TILE_X) * ((d.H + TILE_Y - 1) / TILE_Y);
@@ -1542,9 +1554,9 @@ int irs_launch_svf_fwd(const float* v, float* hist, float* maxabs, int n_steps, 
             e = irs_launch_pdl(en ? kern_e : kern, tgrid, dim3(TILE_T), smem, st, map, in, k == 0 ? scale0 : 1.0f,
                                hist + (size_t)k * F, k == 0 ? nullptr : maxabs + k - 1, maxabs + k, seg_len, d, eo);
             if (e != cudaSuccess) return (int)e;
-            e = launch_cells(k, in, k == 0 ? scale0 : 1.0f);
-            if (e != cudaSuccess) return (int)e;
         }
+        e = launch_cells();
+        if (e != cudaSuccess) return (int)e;
         if (with_energy && energy_done) *energy_done = 1;
         return (int)cudaGetLastError();
     }
@@ -1567,9 +1579,9 @@ int irs_launch_svf_fwd(const float* v, float* hist, float* maxabs, int n_steps, 
         e = irs_launch_pdl(svf_step_fwd_tile_kernel<RF>, tgrid, dim3(TILE_T), svf_fwd_tile_smem(RF), st, in,
                            k == 0 ? scale0 : 1.0f, hist + (size_t)k * F, maxabs + k, seg_len, d);
         if (e != cudaSuccess) return (int)e;
-        e = launch_cells(k, in, k == 0 ? scale0 : 1.0f);
-        if (e != cudaSuccess) return (int)e;
     }
+    e = launch_cells();
+    if (e != cudaSuccess) return (int)e;
     return (int)cudaGetLastError();
 }
 
