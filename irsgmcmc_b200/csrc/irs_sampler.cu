@@ -158,7 +158,7 @@ extern "C" int irs_sgld_launches_per_step(const irs_sgld_config* c) {
     n += gmm_walk_enabled(c) ? 1 : c->C * (c->virtual_decimation ? 2 : 1);   // mixture statistics + VD factor + Adam of all chains
     n += 1;                                      // dL/dz
     n += c->data_term == IRS_DATA_LCC ? 2 : 0;   // LCC adjoint boxes
-    n += 1;                                      // warp grid gradient
+    n += c->data_term == IRS_DATA_LCC ? 0 : 1;   // warp adjoint: an epilogue of the last LCC adjoint box pass; SSD: warp_apply_grad
     n += 1;                                      // regulariser hyper step
     n += c->svf_steps + (c->svf_steps < 4 ? c->svf_steps : 4);   // SVF adjoint (gather; the last four steps carry the
                                                                  // early-exit large-displacement scatter companion)
