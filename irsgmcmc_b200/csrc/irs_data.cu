@@ -826,12 +826,17 @@ int irs_launch_gmm_chain_walk(const float* z, const unsigned char* mask, double*
     if (serial) {
         const int G = (int)(want < sms ? want : sms);           // all CTAs resident: they wait for each other
         if ((long long)G * IRS_SUM_COUNT > partials_stride) return IRS_ERR_WORKSPACE;
-        if (cfg.K <= 4)
-            gmm_chain_walk_kernel<true, 4><<<G, WALK_T, 0, st>>>(z, mask, hyper, 0, cfg, 0, partials, partials_stride, counters,
-                                                                 counters + C, stats, tables, C, d);
-        else
-            gmm_chain_walk_kernel<true, IRS_MAX_K><<<G, WALK_T, 0, st>>>(z, mask, hyper, 0, cfg, 0, partials, partials_stride,
-                                                                         counters, counters + C, stats, tables, C, d);
+        // Cooperative launch: the CTAs wait for each other (tickets), so they must all be resident together.  On an otherwise idle
+        // GPU a plain launch of <= one CTA per SM would do, but two samplers driving the same GPU from two streams could each get a
+        // part of the SMs and wait forever; a cooperative grid is scheduled as a whole or not at all (and is graph-capturable).
+        const int frozen0 = 0;
+        const long long hs0 = 0;
+        unsigned int* ticket = counters + C;
+        void* args[] = {(void*)&z, (void*)&mask, (void*)&hyper, (void*)&hs0, (void*)&cfg, (void*)&frozen0, (void*)&partials,
+                        (void*)&partials_stride, (void*)&counters, (void*)&ticket, (void*)&stats, (void*)&tables, (void*)&C, (void*)&d};
+        const void* fn = cfg.K <= 4 ? (const void*)gmm_chain_walk_kernel<true, 4> : (const void*)gmm_chain_walk_kernel<true, IRS_MAX_K>;
+        cudaError_t e = cudaLaunchCooperativeKernel(fn, dim3(G), dim3(WALK_T), args, 0, st);
+        if (e != cudaSuccess) return (int)e;
     } else {
         long long per_chain = (2LL * sms + C - 1) / C;          // about two waves of CTAs over all chains
         if (per_chain < 1) per_chain = 1;
