@@ -281,7 +281,14 @@ def run_config(tag, n, chains, data, world, rank, dev, peak, barrier, seg_dice=F
         dice = (2 * c[:, 2] / (c[:, 0] + c[:, 1]).clamp(min=1)).tolist()
         out['per_step_extras'] = 'transformation + nearest-neighbour int16 segmentation warp + Dice counts (15 structures)'
         out['dice_mean_last_sample'] = sum(dice) / len(dice)
-        out['asd'] = 'unavailable (SimpleITK contour distance, not on the GPU path)'
+        if rank == 0:   # ASD of the last sample on the host, outside the timed region (the reference computes it there too, with
+            try:        # SimpleITK: utils/util.py:171-176; here scipy's exact distance transform -- parity unpinned)
+                from irsgmcmc_b200.utils.util import calc_metrics
+                asd = calc_metrics(seg_f, sampler.warp_segmentation(), dict(enumerate(STRUCTURE_LABELS)), (1.0, 1.0, 1.0))[0][0]
+                out['asd_mean_last_sample_voxels'] = float(asd[asd < float('inf')].mean())
+                out['asd'] = 'host, scipy distance transform of the label contours, outside the timed region (parity unpinned)'
+            except Exception as exc:
+                out['asd'] = f'unavailable ({type(exc).__name__}: {exc})'[:200]
     if vi:
         # configs[0] says "VI warm start then 1 SGLD chain": the VI iteration of reference trainer.py:119-171 on the fused device
         # path (two antithetic samples through the step's operators + closed-form entropy + field-sized Adam), graph replays

@@ -445,10 +445,11 @@ class Trainer:
         return loss_terms, out, aux
 
     # -- the loop around it (reference trainer.py:358-476) -------------------------------------------------------------
-    def _run_MCMC(self, data_loss=None, reg_loss=None, speed_test_iters=100):
+    def _run_MCMC(self, data_loss=None, reg_loss=None, speed_test_iters=100, with_ASD=False):
         """burn-in + sampling; returns {'mean','std_dev', 'im_mean','im_std', 'n', 'DSC', 'ASD', 'no_non_diffeomorphic_voxels',
         'samples_per_sec'}; posterior statistics are over the kept samples of ALL ranks.  'ASD' (average surface distance,
-        reference utils/util.py:171-176 through SimpleITK on the host) is reported as unavailable: the string says why."""
+        reference utils/util.py:171-176 through SimpleITK on the host): with_ASD=True computes it per kept sample on the host with
+        scipy (utils.util.calc_ASD_host, parity unpinned); otherwise the entry is a string saying that it was not computed."""
         if self.SGLD_params is None:
             self._SGLD_init()
         s = self.sampler
@@ -458,7 +459,7 @@ class Trainer:
                 self._gmm_pushed = True
             else:
                 self._GMM_init()
-        dsc, folded = [], []
+        dsc, asd, folded = [], [], []
         total = self.no_iters_burn_in + self.no_samples_MCMC
         from ..utils.diff_op import GradientOperator
         diff_op = GradientOperator()
@@ -478,6 +479,9 @@ class Trainer:
                     seg_w = s.warp_segmentation(transformation=T)
                     seg_f = self.fixed['seg'].to(s.device).expand(self.no_chains, -1, -1, -1, -1)
                     dsc.append(calc_DSC_GPU(self.no_chains, seg_f, seg_w, self.structures_dict))
+                    if with_ASD:
+                        from ..utils.util import calc_metrics
+                        asd.append(calc_metrics(seg_f, seg_w, self.structures_dict, self.im_spacing, no_samples=self.no_chains)[0])
                 n_folded, log_det_J = calc_no_non_diffeomorphic_voxels(T, diff_op)
                 folded.append(n_folded)
                 if self.save_dir is not None:
@@ -496,8 +500,9 @@ class Trainer:
         mom = s.posterior_moments()
         result = {'mean': mom['displacement_mean'], 'std_dev': mom['displacement_std'], 'im_mean': mom['im_mean'],
                   'im_std': mom['im_std'], 'n': mom['n'], 'DSC': dsc, 'no_non_diffeomorphic_voxels': folded,
-                  'ASD': 'unavailable: SimpleITK LabelContour / SignedMaurerDistanceMap (reference utils/util.py:171-176) is a '
-                         'host-side dependency this package does not carry; Dice is computed on the GPU per kept sample'}
+                  'ASD': asd if with_ASD else 'unavailable: not requested (with_ASD=True computes the label-contour average '
+                                              'Hausdorff distance of reference utils/util.py:171-176 on the host with scipy instead of '
+                                              'SimpleITK; parity unpinned)'}
         if self.save_dir is not None and (not torch.distributed.is_initialized() or torch.distributed.get_rank() == 0):
             from ..logger import save_field_to_disk   # reference logger/logger.py:104-126 (mean / std of the displacement)
             import os

@@ -135,9 +135,57 @@ def calc_DSC_GPU(no_samples, seg_fixed, seg_moving, structures_dict):
     return (2.0 * cnt[..., 2] / (cnt[..., 0] + cnt[..., 1])).float().numpy()
 
 
-def calc_metrics(*args, **kwargs):
-    """The reference's calc_metrics (:151-206) adds the average surface distance per structure through SimpleITK's
-    LabelContour / SignedMaurerDistanceMap filters on the host.  SimpleITK is not a dependency of this package and the
-    surface distance is not on the GPU path: Dice is calc_DSC_GPU, ASD is reported as unavailable by the Trainer."""
-    raise NotImplementedError('ASD needs SimpleITK (host-side contour distance maps): unavailable in irsgmcmc_b200; '
-                              'use calc_DSC_GPU for the Dice scores')
+def _label_contour(mask):
+    """ITK LabelContourImageFilter with its defaults on a binary image: a foreground voxel belongs to the contour when one of its
+    six face neighbours is background (FullyConnectedOff); voxels on the image border count as touching background."""
+    from scipy import ndimage
+    return mask & ~ndimage.binary_erosion(mask, structure=ndimage.generate_binary_structure(3, 1), border_value=0)
+
+
+def calc_ASD_host(seg_fixed_structure, seg_moving_structure, spacing=(1.0, 1.0, 1.0)):
+    """
+    Average surface distance of two binary structures the way the reference computes it (utils/util.py:171-176):
+    sitk.LabelContour of both, then HausdorffDistanceImageFilter.GetAverageHausdorffDistance() = the mean of the two directed
+    average distances, each the mean over the contour voxels of one image of the Euclidean distance (image spacing applied) to
+    the nearest contour voxel of the other.  Host-side like the reference's (SimpleITK there, scipy's exact Euclidean distance
+    transform here).  PARITY UNPINNED: SimpleITK is absent from the build image, so this restates ITK's documented algorithm and is
+    checked against a brute-force evaluation of the same definition (tests/test_writers.py), not against SimpleITK itself.
+    Returns inf when a structure is empty (the reference's `except: ASD = inf`).
+    """
+    from scipy import ndimage
+    a, b = np.asarray(seg_fixed_structure).astype(bool), np.asarray(seg_moving_structure).astype(bool)
+    if not a.any() or not b.any():
+        return float('inf')
+    # crop to the bounding box of both structures (+ 1 voxel so that the contour sees their background): every contour voxel of
+    # either image lies inside it, so the distances are unchanged and the distance transforms stay small
+    idx = np.argwhere(a | b)
+    lo, hi = np.maximum(idx.min(0) - 1, 0), np.minimum(idx.max(0) + 2, a.shape)
+    box = tuple(slice(int(l), int(h)) for l, h in zip(lo, hi))
+    a, b = a[box], b[box]
+    ca, cb = _label_contour(a), _label_contour(b)
+    if not ca.any() or not cb.any():
+        return float('inf')
+    sp = [float(x) for x in np.asarray(spacing).reshape(-1)[:3]]
+    # array axes are (z, y, x) of an image whose spacing is given as (x, y, z): sitk.GetImageFromArray reverses the axes
+    sampling = sp[::-1]
+    d_to_b = ndimage.distance_transform_edt(~cb, sampling=sampling)
+    d_to_a = ndimage.distance_transform_edt(~ca, sampling=sampling)
+    return 0.5 * (float(d_to_b[ca].mean()) + float(d_to_a[cb].mean()))
+
+
+@torch.no_grad()
+def calc_metrics(seg_fixed, seg_moving, structures_dict, spacing, GPU=True, no_samples=1):
+    """(ASD, DSC) per sample and structure like the reference's calc_metrics (:151-206).  DSC: the counting kernel
+    (calc_DSC_GPU; `GPU=False` is not offered -- there is no host Dice).  ASD: calc_ASD_host per sample and structure on the
+    host, as in the reference (parity unpinned, see there); needs scipy."""
+    if not GPU:
+        raise NotImplementedError('calc_metrics(GPU=False): the Dice scores come from the CUDA counting kernel only')
+    DSC = calc_DSC_GPU(no_samples, seg_fixed, seg_moving, structures_dict)
+    a, b = seg_fixed[:no_samples].cpu().numpy(), seg_moving[:no_samples].cpu().numpy()
+    sp = spacing.numpy().tolist() if hasattr(spacing, 'numpy') else list(spacing)
+    ASD = np.zeros([no_samples, len(structures_dict)])
+    for idx in range(no_samples):
+        fa, mb = a[min(idx, a.shape[0] - 1)].squeeze(), b[idx].squeeze()
+        for j, label in enumerate(structures_dict.values()):
+            ASD[idx, j] = calc_ASD_host(fa == label, mb == label, sp)
+    return ASD, DSC

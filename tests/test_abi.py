@@ -115,7 +115,7 @@ def test_no_eager_torch_fallbacks_in_the_product():
     with pytest.raises(NotImplementedError):
         U.calc_no_non_diffeomorphic_voxels(torch.zeros(1, 3, 4, 4, 4), DifferentialOperator())
     with pytest.raises(NotImplementedError):
-        U.calc_metrics()
+        U.calc_metrics(seg, seg, {'a': 10}, (1, 1, 1), GPU=False)
     with pytest.raises(NotImplementedError):
         M.GMM(4, 2).log_pdf_VD(torch.zeros(3, 4))
     with pytest.raises(NotImplementedError):

@@ -42,3 +42,24 @@ def test_vtk_field_round_trip_and_sample_names(tmp_path):
     assert paths['displacement'].endswith('chain_3_sample_0000012_displacement.vtk')
     d, _ = load_field_from_disk(paths['displacement'])
     assert np.allclose(d, 2.0 * f)      # scaled by spacing[0] like the reference (logger/logger.py:223)
+
+
+def test_average_surface_distance_against_brute_force():
+    """calc_ASD_host (the reference's LabelContour + average Hausdorff distance, utils/util.py:171-176, restated with scipy) against a
+    brute-force evaluation of the same definition; parity with SimpleITK itself is unpinned (absent from the image)"""
+    from irsgmcmc_b200.utils.util import calc_ASD_host, _label_contour
+    rng = np.random.default_rng(3)
+    n = 14
+    zz, yy, xx = np.meshgrid(np.arange(n), np.arange(n), np.arange(n), indexing='ij')
+    a = (zz - 6.0) ** 2 + (yy - 7.0) ** 2 + (xx - 6.5) ** 2 <= 16.0
+    b = (zz - 7.0) ** 2 / 1.5 + (yy - 6.0) ** 2 + (xx - 7.5) ** 2 <= 14.0
+    spacing = (1.0, 1.5, 2.0)          # (x, y, z) like the reference's im_spacing
+    ca, cb = _label_contour(a), _label_contour(b)
+    assert ca.sum() < a.sum() and a[6, 7, 6] and not ca[6, 7, 6]      # the interior is not contour
+    pa = np.argwhere(ca) * np.array(spacing[::-1])
+    pb = np.argwhere(cb) * np.array(spacing[::-1])
+    dist = np.sqrt(((pa[:, None, :] - pb[None, :, :]) ** 2).sum(-1))
+    want = 0.5 * (dist.min(1).mean() + dist.min(0).mean())
+    assert abs(calc_ASD_host(a, b, spacing) - want) < 1e-9
+    assert calc_ASD_host(a, a, spacing) == 0.0
+    assert calc_ASD_host(a, np.zeros_like(a), spacing) == float('inf')
