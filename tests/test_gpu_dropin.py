@@ -305,6 +305,12 @@ def test_log_det_jacobian_and_dice_kernels(pkg):
     want = [[2.0 * float(((a[0] == l) & (b[c] == l)).sum()) / float((a == l).sum() + (b[c] == l).sum()) for l in labels]
             for c in range(C)]
     assert np.allclose(dsc, np.array(want), rtol=1e-6)
+    # calc_metrics = (ASD on the host, DSC from the kernel) with the reference's signature (utils/util.py:151-206)
+    structures = {f's{l}': l for l in labels}
+    ASD, DSC = U.calc_metrics(a.to(DEV).expand(C, -1, -1, -1, -1), b.to(DEV), structures, torch.tensor([1.0, 1.0, 1.0]), no_samples=C)
+    assert ASD.shape == DSC.shape == (C, len(labels)) and np.allclose(DSC, dsc) and np.isfinite(ASD).all() and (ASD > 0).all()
+    same, _ = U.calc_metrics(b.to(DEV), b.to(DEV), structures, (1.0, 1.0, 1.0), no_samples=C)
+    assert (same == 0).all()
 
 
 @pytest.mark.parametrize('reg_name', ['RegLoss_LogNormal', 'RegLoss_L2'])
