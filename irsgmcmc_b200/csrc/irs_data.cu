@@ -864,19 +864,21 @@ int irs_launch_vd_alpha(const float* z, const unsigned char* mask, double* hyper
 }
 
 // log_std <- linspace(log(sigma/100), log(5 sigma), K), sigma = moments[1]      (reference model/loss.py:61-65)
-__global__ void gmm_init_params_kernel(double* hyper, const double* moments, int K) {
+// ssd: the single Gaussian of the SSD data term starts at the residuals' own scale, log sigma (build-defined; the one-point
+// linspace would start at sigma / 100)
+__global__ void gmm_init_params_kernel(double* hyper, const double* moments, int K, int ssd) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     const double sigma = moments[1];
     const double lo = log(sigma / 100.0), hi = log(sigma * 5.0);
     for (int k = 0; k < K; ++k) {
         // torch.linspace in fp32
-        const double t = K > 1 ? lo + (hi - lo) * (double)k / (double)(K - 1) : lo;
+        const double t = ssd ? log(sigma) : (K > 1 ? lo + (hi - lo) * (double)k / (double)(K - 1) : lo);
         hyper[IRS_HYPER_LOG_STD + k] = irs_round_f32(t);
     }
 }
 
-int irs_launch_gmm_init_params(double* hyper, const double* moments, int K, cudaStream_t st) {
-    gmm_init_params_kernel<<<1, 32, 0, st>>>(hyper, moments, K);
+int irs_launch_gmm_init_params(double* hyper, const double* moments, int K, int ssd, cudaStream_t st) {
+    gmm_init_params_kernel<<<1, 32, 0, st>>>(hyper, moments, K, ssd);
     return (int)cudaGetLastError();
 }
 

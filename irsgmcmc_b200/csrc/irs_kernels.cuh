@@ -126,7 +126,7 @@ int irs_launch_gmm_chain_walk(const float* z, const unsigned char* mask, double*
                               unsigned int* counters, double* stats, float* tables, int C, IrsDims d, cudaStream_t st);
 int irs_launch_vd_alpha(const float* z, const unsigned char* mask, double* hyper, const IrsHyperCfg& cfg,
                         double* partials, unsigned int* counter, double* stats_row, IrsDims d, cudaStream_t st);
-int irs_launch_gmm_init_params(double* hyper, const double* moments, int K, cudaStream_t st);
+int irs_launch_gmm_init_params(double* hyper, const double* moments, int K, int ssd, cudaStream_t st);
 int irs_launch_masked_moments(const float* z, const unsigned char* mask, long long n, double* out, double* partials,
                               unsigned int* counter, cudaStream_t st);
 int irs_launch_gmm_grad(const float* z, const unsigned char* mask, const float* tables, int K, double* stats, float* g,

@@ -369,7 +369,7 @@ extern "C" int irs_sgld_gmm_init(const irs_sgld_config* cfg, const irs_sgld_buff
     }
     double* moments = b->stats + IRS_STAT_SIZE - 3;  // last three slots of chain 0's row, overwritten by the next step
     IRS_TRY(irs_launch_masked_moments(b->z, b->mask, V, moments, b->partials, b->counters, st));
-    IRS_TRY(irs_launch_gmm_init_params(b->hyper, moments, cfg->K, st));
+    IRS_TRY(irs_launch_gmm_init_params(b->hyper, moments, cfg->K, cfg->data_term == IRS_DATA_SSD, st));
     IRS_TRY(irs_launch_vd_alpha(b->z, b->mask, b->hyper, hc, b->partials, b->counters, b->stats, d, st));
     for (int it = 0; it < n_warmup; ++it)
         IRS_TRY(irs_launch_gmm_stats_step(b->z, b->mask, b->hyper, hc, b->partials, b->counters, b->stats, b->gmm_table,

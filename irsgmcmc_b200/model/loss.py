@@ -143,6 +143,13 @@ class SSD(GMM):
         super().__init__(1, 1)
         self.s = 0
 
+    @torch.no_grad()
+    def init_parameters(self, sigma):
+        """the single component starts at the residuals' own scale.  (GMM.init_parameters with one component would return the
+        first point of its linspace, sigma / 100: a precision of 1e4 / sigma^2 that throws a chain across the volume within
+        a few transitions -- measured max |u_11| = 5 voxels after six transitions at 64^3.)"""
+        self.log_std.data.fill_(math.log(float(sigma)))
+
     def map(self, im_fixed, im_moving):
         return im_fixed - im_moving
 

@@ -271,7 +271,10 @@ class SGLDSampler:
         then `warm_up` Adam steps.  `sigma_hat` given: only GMM.init_parameters (model/loss.py:61-65)."""
         K = self.cfg.no_components
         if sigma_hat is not None:
-            ls = torch.linspace(math.log(sigma_hat / 100.0), math.log(sigma_hat * 5.0), steps=K)
+            if self.cfg.data_loss == 'ssd':   # one Gaussian at the residuals' own scale (see SSD.init_parameters)
+                ls = torch.full((K,), math.log(sigma_hat))
+            else:
+                ls = torch.linspace(math.log(sigma_hat / 100.0), math.log(sigma_hat * 5.0), steps=K)
             self.hyper[..., _lib.HYPER_LOG_STD:_lib.HYPER_LOG_STD + K] = ls.double().to(self.device)
             return
         if v_sample is None:

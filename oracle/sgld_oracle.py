@@ -474,8 +474,13 @@ class State:
         self.taps = sobolev_taps(cfg.sobolev_s, cfg.sobolev_lambda).astype(np.float32)  # trainer.py:573 `.float()`
 
     def init_gmm(self, sigma_hat):
-        """reference model/loss.py:61-65"""
+        """reference model/loss.py:61-65.  SSD (build-defined, SURVEY surprise 1: the reference ships no SSD class): ONE Gaussian at
+        the residuals' own scale, log_std = log sigma_hat -- the mixture's linspace with a single point would start at
+        sigma_hat / 100, a precision of 1e4 / sigma_hat^2 that throws a chain across the volume within a few transitions."""
         K = self.log_std.numel()
+        if self.cfg.data == 'ssd':
+            self.log_std.fill_(math.log(sigma_hat))
+            return
         self.log_std.copy_(torch.linspace(math.log(sigma_hat / 100.0), math.log(sigma_hat * 5.0), steps=K))
 
 
