@@ -220,6 +220,36 @@ __device__ __forceinline__ float masked_vd_residual(const IrsGmm& g, const float
     return mask[i] ? irs_gmm_vd_residual(g, __ldg(z + i)) : 0.f;
 }
 
+// The scalar tail of a chain's mixture step, run by ONE WARP (call with the first 32 threads of the CTA that holds the reduced
+// sums): Adam with one lane per parameter, the table with one lane per component.  Bit-identical to the serial composition
+// irs_gmm_adam_step + irs_gmm_table (irs_hyper.cuh) -- this is the critical path between two chains, and as a loop on one thread
+// it cost 5-8 us of expf / logf / fp64 latency.
+__device__ __forceinline__ void gmm_finalize_warp(double* __restrict__ hyper, const IrsHyperCfg& cfg, const double* total,
+                                                  double alpha32, bool frozen, float* __restrict__ table_out,
+                                                  double* __restrict__ stats_row) {
+    const int lane = threadIdx.x & 31;
+    if (!frozen) {
+        IrsAdamCtx ctx;
+        irs_gmm_adam_context(hyper, cfg, total, ctx);
+        __syncwarp();
+        if (lane < 2 * cfg.K) irs_gmm_adam_param(hyper, cfg, total, alpha32, ctx, lane);
+        __syncwarp();
+        if (lane == 0) irs_gmm_adam_advance(hyper, cfg);
+        __syncwarp();
+    }
+    float logpi[IRS_MAX_K];
+    irs_log_proportions(hyper + IRS_HYPER_LOGITS, cfg.K, logpi);
+    if (lane < IRS_MAX_K) {   // irs_gmm_table, one lane per component
+        const float lsk = lane < cfg.K ? (float)hyper[IRS_HYPER_LOG_STD + lane] : 0.f;
+        table_out[lane] = lane < cfg.K ? logpi[lane] - lsk : -INFINITY;
+        table_out[IRS_MAX_K + lane] = lane < cfg.K ? expf(-2.0f * lsk) : 0.f;
+    }
+    if (lane == 0) {
+        stats_row[IRS_STAT_ALPHA] = alpha32;
+        stats_row[IRS_STAT_NLL_PRE] = total[IRS_SUM_NLL];
+    }
+}
+
 // mode 0: fused path (parameters from `hyper`, Adam step + table/alpha outputs; alpha_fixed != null reuses a stored
 //         factor instead of recomputing it -- the 25 warm-up steps of trainer.py:544-547)
 // mode 1: op-level VD factor only (mixture passed by value)
@@ -354,14 +384,9 @@ gmm_stats_a_kernel(const float* __restrict__ z, const unsigned char* __restrict_
         if (threadIdx.x < IRS_SUM_COUNT) totals_out[threadIdx.x] = total[threadIdx.x];
         return;
     }
-    if (threadIdx.x != 0) return;
+    if (threadIdx.x >= 32) return;
     const double alpha32 = irs_round_f32(alpha_fixed != nullptr ? *alpha_fixed : 1.0);
-    irs_gmm_adam_step(hyper, cfg, total, alpha32);
-    IrsGmm up;
-    irs_gmm_table(hyper + IRS_HYPER_LOG_STD, hyper + IRS_HYPER_LOGITS, cfg.K, up);
-    for (int k = 0; k < IRS_MAX_K; ++k) { table_out[k] = up.lw[k]; table_out[IRS_MAX_K + k] = up.prec[k]; }
-    stats_row[IRS_STAT_ALPHA] = alpha32;
-    stats_row[IRS_STAT_NLL_PRE] = total[IRS_SUM_NLL];
+    gmm_finalize_warp(hyper, cfg, total, alpha32, false, table_out, stats_row);
 }
 
 // pass B: lag-1 products of r along D, H, W; the last block combines them with pass A's sums: VD factor, Adam step
@@ -402,15 +427,11 @@ gmm_stats_b_kernel(const float* __restrict__ r, double* __restrict__ hyper, IrsH
     double blk[3];
     irs_block_sum<3>(acc, blk, sh);
     if (!irs_grid_sum<3>(blk, partials, counter, total)) return;
-    if (threadIdx.x != 0) return;
-    totals[IRS_SUM_RD] = total[0]; totals[IRS_SUM_RH] = total[1]; totals[IRS_SUM_RW] = total[2];
+    if (threadIdx.x >= 32) return;
+    if (threadIdx.x == 0) { totals[IRS_SUM_RD] = total[0]; totals[IRS_SUM_RH] = total[1]; totals[IRS_SUM_RW] = total[2]; }
+    __syncwarp();
     const double alpha32 = irs_round_f32(irs_vd_alpha(totals, cfg.n_mask));
-    irs_gmm_adam_step(hyper, cfg, totals, alpha32);
-    IrsGmm up;
-    irs_gmm_table(hyper + IRS_HYPER_LOG_STD, hyper + IRS_HYPER_LOGITS, cfg.K, up);
-    for (int k = 0; k < IRS_MAX_K; ++k) { table_out[k] = up.lw[k]; table_out[IRS_MAX_K + k] = up.prec[k]; }
-    stats_row[IRS_STAT_ALPHA] = alpha32;
-    stats_row[IRS_STAT_NLL_PRE] = totals[IRS_SUM_NLL];
+    gmm_finalize_warp(hyper, cfg, totals, alpha32, false, table_out, stats_row);
 }
 
 // ---- all chains in ONE launch ----------------------------------------------------------------------------------------------
@@ -583,28 +604,8 @@ gmm_chain_walk_kernel(const float* __restrict__ z_all, const unsigned char* __re
             if (threadIdx.x < 32) {
                 const int lane = threadIdx.x;
                 const double alpha32 = irs_round_f32(cfg.virtual_decimation ? irs_vd_alpha(total, cfg.n_mask) : 1.0);
-                if (!frozen) {
-                    IrsAdamCtx ctx;
-                    irs_gmm_adam_context(hyper, cfg, total, ctx);
-                    __syncwarp();
-                    if (lane < 2 * cfg.K) irs_gmm_adam_param(hyper, cfg, total, alpha32, ctx, lane);
-                    __syncwarp();
-                    if (lane == 0) irs_gmm_adam_advance(hyper, cfg);
-                    __syncwarp();
-                }
-                float logpi[IRS_MAX_K];
-                irs_log_proportions(hyper + IRS_HYPER_LOGITS, cfg.K, logpi);
-                float* table_out = tables_all + (size_t)c * 16;
-                if (lane < IRS_MAX_K) {   // irs_gmm_table, one lane per component
-                    const float lsk = lane < cfg.K ? (float)hyper[IRS_HYPER_LOG_STD + lane] : 0.f;
-                    table_out[lane] = lane < cfg.K ? logpi[lane] - lsk : -INFINITY;
-                    table_out[IRS_MAX_K + lane] = lane < cfg.K ? expf(-2.0f * lsk) : 0.f;
-                }
-                if (lane == 0) {
-                    double* stats_row = stats_all + (size_t)c * IRS_STAT_SIZE;
-                    stats_row[IRS_STAT_ALPHA] = alpha32;
-                    stats_row[IRS_STAT_NLL_PRE] = total[IRS_SUM_NLL];
-                }
+                gmm_finalize_warp(hyper, cfg, total, alpha32, frozen != 0, tables_all + (size_t)c * 16,
+                                  stats_all + (size_t)c * IRS_STAT_SIZE);
                 if (SERIAL) {
                     __threadfence();
                     __syncwarp();
