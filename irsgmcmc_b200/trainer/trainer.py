@@ -55,6 +55,12 @@ def sampler_config_from_json(config):
     if tm['type'] not in ('SVF_3D', 'SVFFD_3D'):
         raise NotImplementedError(tm['type'])
     kw['transformation'] = tm['type']
+    # not a key of the reference: "trainer": {"hyper_mode": "reference" | "frozen" | "per_chain"} selects how the mixture / regulariser
+    # hyper-parameters are stepped over the chains (SGLDConfig); the Trainer mirrors ONE parameter set into the drop-in modules, so
+    # 'per_chain' is for the sampler API only
+    kw['hyper_mode'] = tr.get('hyper_mode', 'reference')
+    if kw['hyper_mode'] == 'per_chain':
+        raise NotImplementedError("Trainer mirrors one shared parameter set: use SGLDSampler(SGLDConfig(hyper_mode='per_chain')) directly")
     if tm['type'] == 'SVFFD_3D':
         kw['cps'] = tm.get('args', {}).get('cps')
     return SGLDConfig(**kw)

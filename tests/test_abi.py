@@ -168,7 +168,13 @@ def test_config_from_reference_json():
                        'uniform_noise': {'enabled': True, 'magnitude': 0.1}}}
     c = sampler_config_from_json(cfg)
     assert (c.data_loss, c.no_components, c.s, c.reg_loss, c.w_reg, c.tau) == ('lcc', 4, 2, 'RegLoss_LogNormal', 1.6, 0.4)
-    assert c.transformation == 'SVF_3D' and c.cps is None
+    assert c.transformation == 'SVF_3D' and c.cps is None and c.hyper_mode == 'reference'
+    cfg['trainer']['hyper_mode'] = 'frozen'
+    assert sampler_config_from_json(cfg).hyper_mode == 'frozen'
+    cfg['trainer']['hyper_mode'] = 'per_chain'
+    with pytest.raises(NotImplementedError):
+        sampler_config_from_json(cfg)
+    del cfg['trainer']['hyper_mode']
     cfg['transformation_module'] = {'type': 'SVFFD_3D', 'args': {'cps': [4, 4, 4]}}   # configs/experiment5/config_SVFFD_4.json
     c = sampler_config_from_json(cfg)
     assert c.transformation == 'SVFFD_3D' and c.cps == (4, 4, 4)
