@@ -4,6 +4,7 @@
 // One call enqueues the whole iteration for all chains of this GPU on one stream; every scalar (virtual decimation
 // factors, mixture / regulariser hyper-parameters and their Adam state, the Philox offset) stays in device memory, so
 // the sequence has no host synchronisation and can be captured in a CUDA graph and replayed.
+#include <cstdint>
 #include <cstdlib>
 
 #include "irs_kernels.cuh"
@@ -60,6 +61,31 @@ welford_kernel(const float* __restrict__ sample, int n_new, long long n, double 
     }
     mean[i] = m;
     m2[i] = s;
+}
+
+// the same recurrence on four elements per thread (128-bit accesses, the next sample's load in flight while this one is folded
+// in): the update of 64 chains at 128^3 reads 2 GB -- as the scalar kernel it ran at 2 TB/s
+__global__ void __launch_bounds__(256)
+welford_vec_kernel(const float* __restrict__ sample, int n_new, long long n, double count, float* __restrict__ mean,
+                   float* __restrict__ m2) {
+    const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i >= n) return;
+    float4 m = *reinterpret_cast<const float4*>(mean + i), s = *reinterpret_cast<const float4*>(m2 + i);
+    float cnt = (float)count;
+    float4 x = __ldg(reinterpret_cast<const float4*>(sample + i));
+    for (int j = 0; j < n_new; ++j) {
+        float4 nx = x;
+        if (j + 1 < n_new) nx = __ldg(reinterpret_cast<const float4*>(sample + (size_t)(j + 1) * n + i));
+        cnt += 1.f;
+        float d;
+        d = x.x - m.x; m.x += d / cnt; s.x += d * (x.x - m.x);
+        d = x.y - m.y; m.y += d / cnt; s.y += d * (x.y - m.y);
+        d = x.z - m.z; m.z += d / cnt; s.z += d * (x.z - m.z);
+        d = x.w - m.w; m.w += d / cnt; s.w += d * (x.w - m.w);
+        x = nx;
+    }
+    *reinterpret_cast<float4*>(mean + i) = m;
+    *reinterpret_cast<float4*>(m2 + i) = s;
 }
 
 __global__ void __launch_bounds__(256)
@@ -380,7 +406,10 @@ extern "C" int irs_sgld_gmm_init(const irs_sgld_config* cfg, const irs_sgld_buff
 extern "C" int irs_welford_update(const float* sample, int n_new, long long n, double count_before, float* mean,
                                   float* m2, void* stream) {
     if (!sample || !mean || !m2 || n_new < 1 || n < 1 || count_before < 0) return IRS_ERR_BAD_ARG;
-    welford_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(sample, n_new, n, count_before, mean, m2);
+    const bool vec = (n % 4) == 0 && ((reinterpret_cast<uintptr_t>(sample) | reinterpret_cast<uintptr_t>(mean) |
+                                       reinterpret_cast<uintptr_t>(m2)) & 15) == 0;
+    if (vec) welford_vec_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(sample, n_new, n, count_before, mean, m2);
+    else welford_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(sample, n_new, n, count_before, mean, m2);
     return (int)cudaGetLastError();
 }
 
