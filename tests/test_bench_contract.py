@@ -30,3 +30,35 @@ def test_other_ranks_of_the_reference_arm_exit_without_work():
     res = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--gpus', '2'],
                          capture_output=True, text=True, timeout=120, cwd=ROOT, env={**os.environ, 'RANK': '1'})
     assert res.returncode == 0 and res.stdout.strip() == ''
+
+
+def test_graph_length_and_core_pinning_helpers():
+    """the timed region is K transitions in K / g graph replays with g | K wherever a divisor in [10, 40] exists; ranks get disjoint,
+    equal shares of the cores"""
+    sys.path.insert(0, ROOT)
+    import bench
+    assert bench.graph_length(20) == 20 and bench.graph_length(1) == 1 and bench.graph_length(40) == 40
+    assert bench.graph_length(200) == 40 and bench.graph_length(100) == 25 and bench.graph_length(50) == 25
+    assert bench.graph_length(97) == 10           # prime: ten-transition replays and an eager remainder
+    for k in (20, 60, 200, 1000):
+        assert k % bench.graph_length(k) == 0
+    before = os.sched_getaffinity(0)
+    try:
+        per = bench.pin_rank_to_cores(0, 1)       # a single rank keeps every core
+        assert per is None and os.sched_getaffinity(0) == before
+        if len(before) >= 2:
+            per = bench.pin_rank_to_cores(1, 2)
+            mine = os.sched_getaffinity(0)
+            assert per == len(before) // 2 and len(mine) == per and mine == set(sorted(before)[per:2 * per])
+    finally:
+        os.sched_setaffinity(0, before)
+
+
+def test_own_arm_fails_loudly_without_a_gpu():
+    """no CPU path: without CUDA the own arm raises instead of measuring anything"""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('needs a machine without a GPU')
+    res = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--steps', '1'], capture_output=True, text=True,
+                         timeout=300, cwd=ROOT)
+    assert res.returncode != 0 and 'no CPU path' in res.stderr
