@@ -130,3 +130,32 @@ def save_sample(save_dir, spacing, sample_no, im_moving_warped_batch, displaceme
         paths['log_det_J'] = os.path.join(save_dir, prefix + '_log_det_J.nii.gz')
         save_im_to_disk(_to_numpy(log_det_J_batch)[0], paths['log_det_J'], sp)
     return paths
+
+
+def save_displacement_mean_and_std_dev(save_dir, spacing, displacement_mean, displacement_std_dev, mask, model):
+    """sample mean / standard deviation of the displacement (3, D, H, W), scaled by spacing[0], with and without the moving mask
+    (1, 1, D, H, W): <model>_sample_mean.vtk, _mean_masked.vtk, _std_dev.vtk, _std_dev_masked.vtk -- the reference's four files
+    (logger/logger.py:110-131)"""
+    os.makedirs(save_dir, exist_ok=True)
+    sp = [float(s) for s in _to_numpy(spacing).reshape(-1)[:3]]
+    m = None if mask is None else _to_numpy(mask)[0].astype(np.float32)
+    paths = {}
+    for tag, field in (('mean', displacement_mean), ('std_dev', displacement_std_dev)):
+        f = _to_numpy(field).astype(np.float32) * np.float32(sp[0])
+        paths[tag] = os.path.join(save_dir, f'{model}_sample_{tag}.vtk')
+        save_field_to_disk(f, paths[tag], sp)
+        if m is not None:
+            paths[tag + '_masked'] = os.path.join(save_dir, f'{model}_sample_{tag}_masked.vtk')
+            save_field_to_disk(f * m, paths[tag + '_masked'], sp)
+    return paths
+
+
+def save_variational_posterior_mean(save_dir, spacing, im_moving_warped, displacement):
+    """registration at the mean of q(v): im_moving_warped_mu.nii.gz and displacement_mu.vtk (reference logger/logger.py:198-208)"""
+    os.makedirs(save_dir, exist_ok=True)
+    sp = [float(s) for s in _to_numpy(spacing).reshape(-1)[:3]]
+    paths = {'im_moving_warped_mu': os.path.join(save_dir, 'im_moving_warped_mu.nii.gz'),
+             'displacement_mu': os.path.join(save_dir, 'displacement_mu.vtk')}
+    save_im_to_disk(_to_numpy(im_moving_warped)[0, 0], paths['im_moving_warped_mu'], sp)
+    save_field_to_disk(_to_numpy(displacement)[0] * sp[0], paths['displacement_mu'], sp)
+    return paths

@@ -400,6 +400,75 @@ class Trainer:
         self._gmm_pushed = False   # the next transition pushes the parameters AND the optimiser state VI left behind
         return self.var_params_q_v, m, history
 
+    @torch.no_grad()
+    def _test_VI(self, var_params_q_v=None, no_samples=None, modules=None, speed_test_samples=100, with_ASD=True):
+        """
+        evaluation of the fitted q(v) (reference trainer.py:226-289): `no_samples_VI_test` draws from q(v) -> Sobolev smoothing ->
+        transformation -> number of folded voxels + log det J, warped image and segmentation, ASD / DSC per structure, the sample on
+        disk; then the registration at the posterior mean, the sample mean / standard deviation of the displacement, and the
+        sampling speed test (draw + transformation + image and segmentation warps).  The reference keeps every displacement in a
+        host buffer for torch.std; here they are folded into Welford moments on the device (same unbiased result).
+        Returns {'no_non_diffeomorphic_voxels': [S], 'DSC': (S, structures), 'ASD': (S, structures) | str, 'mean', 'std_dev' (3,D,H,W),
+        'displacement_mu', 'im_moving_warped_mu', 'samples_per_sec'}.
+        """
+        from .. import ops
+        from ..utils import SobolevGrad, calc_metrics
+        from ..utils.sampler import sample_q_v
+        tr = self.config['trainer']
+        S = int(tr.get('no_samples_VI_test', 0)) if no_samples is None else int(no_samples)
+        m = modules or getattr(self, '_vi_modules', None) or self._build_VI_modules()
+        dev = self.device
+        vp = {k: v.detach().to(dev, torch.float32) for k, v in (var_params_q_v or self.var_params_q_v).items()}
+        moving = {k: v.to(dev) for k, v in self.moving.items()}
+        seg_fixed = self.fixed['seg'].to(dev) if 'seg' in self.fixed else None
+        with_seg = bool(self.structures_dict) and seg_fixed is not None and 'seg' in moving
+        transformation_module, registration_module, diff_op = m['transformation_module'], m['registration_module'], m['reg_loss'].diff_op
+
+        def register(v):
+            v_smoothed = SobolevGrad.apply(v, m['S'], m['padding']) if 'S' in m else v
+            transformation, displacement = transformation_module(v_smoothed)
+            return transformation, displacement, registration_module(moving['im'], transformation)
+
+        mean, m2, count = torch.zeros((3, *self.dims), device=dev), torch.zeros((3, *self.dims), device=dev), 0
+        folded, dsc, asd = [], [], []
+        for test_sample_no in range(1, S + 1):
+            transformation, displacement, im_moving_warped = register(sample_q_v(vp, no_samples=1))
+            count = ops.welford_update(displacement.contiguous(), count, mean, m2)
+            n_folded, log_det_J = calc_no_non_diffeomorphic_voxels(transformation, diff_op)
+            folded.append(int(n_folded[0]))
+            if with_seg:
+                seg_moving_warped = registration_module(moving['seg'], transformation)
+                if with_ASD:
+                    ASD, DSC = calc_metrics(seg_fixed, seg_moving_warped, self.structures_dict, self.im_spacing)
+                    asd.append(ASD[0])
+                else:
+                    DSC = calc_DSC_GPU(1, seg_fixed, seg_moving_warped, self.structures_dict)
+                dsc.append(DSC[0])
+            if self.save_dir is not None:
+                from ..logger import save_sample
+                save_sample(self.save_dir, self.im_spacing, test_sample_no, im_moving_warped, displacement, log_det_J, model='VI')
+        # the registration at the mean of the approximate posterior (reference trainer.py:257-262)
+        _, displacement_mu, im_moving_warped_mu = register(vp['mu'])
+        std_dev = ops.welford_std(m2, count) if count > 1 else torch.full_like(m2, float('nan'))   # torch.std of one sample is NaN
+        if self.save_dir is not None:
+            from ..logger import save_displacement_mean_and_std_dev, save_variational_posterior_mean
+            save_variational_posterior_mean(self.save_dir, self.im_spacing, im_moving_warped_mu, displacement_mu)
+            if count > 0:
+                save_displacement_mean_and_std_dev(self.save_dir, self.im_spacing, mean, std_dev, moving.get('mask'), 'VI')
+        result = {'no_non_diffeomorphic_voxels': folded, 'DSC': np.asarray(dsc), 'mean': mean, 'std_dev': std_dev,
+                  'ASD': np.asarray(asd) if (with_seg and with_ASD) else 'unavailable: no segmentations / structures, or with_ASD=False',
+                  'displacement_mu': displacement_mu, 'im_moving_warped_mu': im_moving_warped_mu, 'n': count}
+        if speed_test_samples:   # reference trainer.py:275-289
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(speed_test_samples):
+                transformation, _, _ = register(sample_q_v(vp, no_samples=1))
+                if 'seg' in moving:
+                    registration_module(moving['seg'], transformation)
+            torch.cuda.synchronize()
+            result['samples_per_sec'] = speed_test_samples / (time.perf_counter() - t0)
+        return result
+
     def _run_model(self, VI=None, MCMC=None, speed_test_iters=0):
         """the reference's Trainer._run_model (trainer.py:478-504): mixture initialisation (25 Adam steps), VI warm start,
         then SGLD -- with the mixture / regulariser parameters and their Adam state handed from stage to stage"""
@@ -413,6 +482,8 @@ class Trainer:
         result = {'modules': m}
         if VI:
             result['var_params_q_v'], _, result['VI_history'] = self._run_VI(modules=m)
+            if int(tr.get('no_samples_VI_test', 0)) > 0:   # reference trainer.py:488-498: fit q(v), then sample from it
+                result['VI_test'] = self._test_VI(modules=m, speed_test_samples=speed_test_iters)
         if MCMC:
             self._SGLD_init()
             self._gmm_pushed = False
@@ -510,11 +581,10 @@ class Trainer:
                                               'Hausdorff distance of reference utils/util.py:171-176 on the host with scipy instead of '
                                               'SimpleITK; parity unpinned)'}
         if self.save_dir is not None and (not torch.distributed.is_initialized() or torch.distributed.get_rank() == 0):
-            from ..logger import save_field_to_disk   # reference logger/logger.py:104-126 (mean / std of the displacement)
-            import os
-            os.makedirs(self.save_dir, exist_ok=True)
-            save_field_to_disk(mom['displacement_mean'] * self.im_spacing[0], os.path.join(self.save_dir, 'displacement_mean.vtk'), self.im_spacing)
-            save_field_to_disk(mom['displacement_std'] * self.im_spacing[0], os.path.join(self.save_dir, 'displacement_std_dev.vtk'), self.im_spacing)
+            # MCMC_sample_{mean,std_dev}[_masked].vtk like the reference (trainer.py:457-460, logger/logger.py:110-131)
+            from ..logger import save_displacement_mean_and_std_dev
+            save_displacement_mean_and_std_dev(self.save_dir, self.im_spacing, mom['displacement_mean'], mom['displacement_std'],
+                                               self.moving.get('mask'), 'MCMC')
         if speed_test_iters:  # the reference's built-in speed test: transitions + one segmentation warp each (:467-476)
             torch.cuda.synchronize()
             t0 = time.perf_counter()

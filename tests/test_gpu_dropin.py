@@ -273,9 +273,11 @@ def test_trainer_facade(pkg):
     from irsgmcmc_b200.logger import load_field_from_disk, load_im_from_disk
     names = sorted(os.listdir(save_dir))
     assert 'chain_0_sample_0000008_displacement.vtk' in names and 'chain_1_sample_0000016_im_moving_warped.nii.gz' in names
-    assert 'chain_1_sample_0000012_log_det_J.nii.gz' in names and len(names) == 3 * C * 3 + 2
-    mean, sp = load_field_from_disk(os.path.join(save_dir, 'displacement_mean.vtk'))
+    assert 'chain_1_sample_0000012_log_det_J.nii.gz' in names and len(names) == 3 * C * 3 + 4
+    mean, sp = load_field_from_disk(os.path.join(save_dir, 'MCMC_sample_mean.vtk'))   # reference logger/logger.py:110-131
     assert np.allclose(mean, 2.0 * res['mean'].cpu().numpy(), atol=1e-6) and sp == [2.0, 2.0, 2.0]
+    std_masked, _ = load_field_from_disk(os.path.join(save_dir, 'MCMC_sample_std_dev_masked.vtk'))
+    assert np.allclose(std_masked, 2.0 * (res['std_dev'] * moving['mask'][0].to(res['std_dev'].device)).cpu().numpy(), atol=1e-6)
     im, _ = load_im_from_disk(os.path.join(save_dir, 'chain_0_sample_0000016_im_moving_warped.nii.gz'))
     assert im.shape == (n, n, n) and np.isfinite(im).all()
 
@@ -376,6 +378,66 @@ def test_run_VI_then_MCMC(pkg):
     t._SGLD_init(vp)
     res = t._run_MCMC(m['data_loss'], m['reg_loss'], speed_test_iters=0)
     assert res['n'] == 3 * C and torch.isfinite(res['mean']).all()
+
+
+def test_test_VI(pkg):
+    """Trainer._test_VI (reference trainer.py:226-289): samples of q(v) -> folding count, Dice / ASD, files, sample statistics --
+    against the same quantities composed by hand from the drop-in modules with the same random numbers"""
+    import os
+    import tempfile
+    U, M, _ = pkg
+    from irsgmcmc_b200.trainer import Trainer
+    from irsgmcmc_b200.data_loader.synthetic import make_pair, STRUCTURE_LABELS
+    from irsgmcmc_b200.logger import load_field_from_disk, load_im_from_disk
+    n, S = 16, 3
+    torch.manual_seed(11)
+    fixed, moving, vp0 = make_pair(n)
+    structures = {f's{l}': l for l in STRUCTURE_LABELS}
+    cfg = _reference_style_config(1)
+    cfg['trainer'].update(no_iters_VI=2, no_samples_VI_test=S)
+    save_dir = tempfile.mkdtemp()
+    t = Trainer(cfg, fixed, moving, vp0, structures_dict=structures, device=torch.device(DEV), save_dir=save_dir,
+                im_spacing=(1.5, 1.5, 1.5))
+    vp, m, _ = t._run_VI()
+    torch.manual_seed(77)
+    res = t._test_VI(speed_test_samples=2)
+    assert res['n'] == S and len(res['no_non_diffeomorphic_voxels']) == S and res['samples_per_sec'] > 0
+    assert res['DSC'].shape == (S, len(structures)) and res['ASD'].shape == (S, len(structures))
+    ok = np.isfinite(res['DSC'])   # a structure that is empty in both segmentations at this size gives 0 / 0
+    assert ok.any() and (res['DSC'][ok] >= 0).all() and (res['DSC'][ok] <= 1).all()
+
+    # the same draws by hand (same generator state, same order of random numbers: randn_like(sigma), randn(1) per sample)
+    torch.manual_seed(77)
+    vpd = {k: v.to(DEV) for k, v in vp.items()}
+    disp, dsc = [], []
+    for _ in range(S):
+        v = U.SobolevGrad.apply(U.sample_q_v(vpd), m['S'], m['padding'])
+        T, d = m['transformation_module'](v)
+        disp.append(d[0])
+        seg_w = m['registration_module'](moving['seg'].to(DEV), T)
+        dsc.append(U.calc_DSC_GPU(1, fixed['seg'].to(DEV), seg_w, structures)[0])
+    disp = torch.stack(disp)
+    assert rel(res['mean'], disp.mean(0)) < 1e-6 and rel(res['std_dev'], disp.std(0)) < 1e-5   # unbiased, like torch.std
+    assert np.array_equal(res['DSC'], np.asarray(dsc), equal_nan=True)
+    T_mu, d_mu = m['transformation_module'](U.SobolevGrad.apply(vpd['mu'], m['S'], m['padding']))
+    assert torch.equal(res['displacement_mu'], d_mu)
+
+    names = sorted(os.listdir(save_dir))
+    expect = [f'sample_{i:07}_{k}' for i in range(1, S + 1) for k in ('displacement.vtk', 'im_moving_warped.nii.gz', 'log_det_J.nii.gz')]
+    expect += ['VI_sample_mean.vtk', 'VI_sample_mean_masked.vtk', 'VI_sample_std_dev.vtk', 'VI_sample_std_dev_masked.vtk',
+               'displacement_mu.vtk', 'im_moving_warped_mu.nii.gz']
+    assert names == sorted(expect)
+    f, sp = load_field_from_disk(os.path.join(save_dir, 'displacement_mu.vtk'))
+    assert np.allclose(f, 1.5 * d_mu[0].cpu().numpy(), atol=1e-6) and sp == [1.5, 1.5, 1.5]
+    f, _ = load_field_from_disk(os.path.join(save_dir, 'sample_0000002_displacement.vtk'))
+    assert np.allclose(f, 1.5 * disp[1].cpu().numpy(), atol=1e-6)
+    im, _ = load_im_from_disk(os.path.join(save_dir, 'im_moving_warped_mu.nii.gz'))
+    assert np.allclose(im, res['im_moving_warped_mu'][0, 0].cpu().numpy(), atol=1e-7)
+
+    # _run_model runs it after VI when the config asks for test samples (reference trainer.py:488-498)
+    t2 = Trainer(cfg, fixed, moving, vp0, structures_dict=structures, device=torch.device(DEV))
+    out = t2._run_model(VI=True, MCMC=False)
+    assert out['VI_test']['n'] == S and 'samples_per_sec' not in out['VI_test']
 
 
 def test_run_VI_then_MCMC_svffd(pkg):

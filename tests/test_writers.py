@@ -44,6 +44,30 @@ def test_vtk_field_round_trip_and_sample_names(tmp_path):
     assert np.allclose(d, 2.0 * f)      # scaled by spacing[0] like the reference (logger/logger.py:223)
 
 
+def test_statistics_and_posterior_mean_files(tmp_path):
+    """the reference's file names for the sample statistics and the posterior-mean registration (logger/logger.py:110-131,198-208)"""
+    from irsgmcmc_b200.logger import (load_field_from_disk, load_im_from_disk, save_displacement_mean_and_std_dev,
+                                      save_variational_posterior_mean)
+    rng = np.random.default_rng(2)
+    mean, std = (rng.standard_normal((3, 4, 5, 6)).astype(np.float32) for _ in range(2))
+    mask = torch.from_numpy(rng.random((1, 1, 4, 5, 6)) > 0.5)
+    paths = save_displacement_mean_and_std_dev(str(tmp_path), (2.0, 2.0, 2.0), torch.from_numpy(mean), torch.from_numpy(std), mask, 'VI')
+    assert sorted(p.name for p in tmp_path.iterdir()) == ['VI_sample_mean.vtk', 'VI_sample_mean_masked.vtk', 'VI_sample_std_dev.vtk',
+                                                           'VI_sample_std_dev_masked.vtk']
+    back, sp = load_field_from_disk(paths['mean'])
+    assert np.allclose(back, 2.0 * mean) and sp == [2.0, 2.0, 2.0]
+    back, _ = load_field_from_disk(paths['std_dev_masked'])
+    assert np.allclose(back, 2.0 * std * mask[0].numpy())
+    assert set(save_displacement_mean_and_std_dev(str(tmp_path / 'nomask'), (1, 1, 1), mean, std, None, 'MCMC')) == {'mean', 'std_dev'}
+    im, d = rng.random((1, 1, 4, 5, 6)).astype(np.float32), rng.standard_normal((1, 3, 4, 5, 6)).astype(np.float32)
+    paths = save_variational_posterior_mean(str(tmp_path / 'mu'), torch.tensor([1.5, 1.5, 1.5]), torch.from_numpy(im), torch.from_numpy(d))
+    assert paths['im_moving_warped_mu'].endswith('im_moving_warped_mu.nii.gz') and paths['displacement_mu'].endswith('displacement_mu.vtk')
+    back, _ = load_im_from_disk(paths['im_moving_warped_mu'])
+    assert np.array_equal(back, im[0, 0])
+    back, _ = load_field_from_disk(paths['displacement_mu'])
+    assert np.allclose(back, 1.5 * d[0])
+
+
 def test_average_surface_distance_against_brute_force():
     """calc_ASD_host (the reference's LabelContour + average Hausdorff distance, utils/util.py:171-176, restated with scipy) against a
     brute-force evaluation of the same definition; parity with SimpleITK itself is unpinned (absent from the image)"""
