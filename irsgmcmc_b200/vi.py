@@ -92,6 +92,31 @@ class VIWarmStart:
         self.iteration += n
         self.sampler.iteration += n
 
+    # -- checkpoint / resume (the reference has none: a VI run of 1024 iterations that dies starts over) -------------------------
+    @torch.no_grad()
+    def state_dict(self):
+        """variational parameters, their Adam moments, the step counter / bias-correction products (`vi_state`) and the shared
+        mixture / regulariser state with its Philox offset (`hyper`), as host tensors.  The noise of an iteration is a function of
+        (seed, iteration counter on the device), so a warm start restored from it continues bit-identically."""
+        return {'shape': tuple(self.mu.shape), 'seed': self.sampler.cfg.seed, 'iteration': self.iteration,
+                'mu': self.mu.cpu(), 'log_var': self.log_var.cpu(), 'u': self.u.cpu(),
+                'adam_m': [t.cpu() for t in self._m], 'adam_v': [t.cpu() for t in self._v],
+                'vi_state': self.vi_state.cpu(), 'hyper': self.sampler.hyper.cpu()}
+
+    @torch.no_grad()
+    def load_state_dict(self, sd):
+        """in place: device pointers (and with them a captured graph) stay valid"""
+        if tuple(sd['shape']) != tuple(self.mu.shape) or sd['seed'] != self.sampler.cfg.seed:
+            raise ValueError(f"checkpoint does not match this warm start: shape {tuple(sd['shape'])}, seed {sd['seed']} "
+                             f"(here {tuple(self.mu.shape)}, {self.sampler.cfg.seed})")
+        for name in ('mu', 'log_var', 'u', 'vi_state'):
+            getattr(self, name).copy_(sd[name])
+        for k in range(3):
+            self._m[k].copy_(sd['adam_m'][k])
+            self._v[k].copy_(sd['adam_v'][k])
+        self.sampler.hyper.copy_(sd['hyper'])
+        self.iteration = self.sampler.iteration = int(sd['iteration'])
+
     # -- results -------------------------------------------------------------------------------------------------------------
     def var_params(self):
         return {'mu': self.mu, 'log_var': self.log_var, 'u': self.u}

@@ -97,6 +97,38 @@ def test_fused_vi_runs_in_a_graph_and_is_deterministic(built):
     assert not torch.equal(res[0][0].cpu(), vp0['mu'])
 
 
+def test_fused_vi_checkpoint_resume_is_bit_identical(built):
+    """5 iterations in one go == 3 iterations, state_dict -> a fresh VIWarmStart -> 2 more (own Philox noise, graph replays)"""
+    from irsgmcmc_b200.vi import VIWarmStart
+    n = 16
+    torch.manual_seed(2)
+    t, vp0 = _trainer(n, 'RegLoss_LogNormal', True)
+
+    def fresh():
+        vi = VIWarmStart(t.fixed, t.moving, vp0, t.sampler.cfg, device=DEV)
+        vi.sampler.init_gmm(sigma_hat=0.7)
+        return vi
+
+    a = fresh()
+    a.step(5)
+    b = fresh()
+    b.step(3)
+    sd = b.state_dict()
+    assert sd['iteration'] == 3 and all(not v.is_cuda for v in (sd['mu'], sd['hyper'], sd['vi_state'], *sd['adam_m']))
+    c = fresh()
+    c.step(1)                      # its own history (and a captured graph) must not matter
+    c.load_state_dict(sd)
+    c.step(2)
+    torch.cuda.synchronize()
+    for x, y in ((a.mu, c.mu), (a.log_var, c.log_var), (a.u, c.u), (a.vi_state, c.vi_state), (a.sampler.hyper, c.sampler.hyper),
+                 (a._m[1], c._m[1]), (a._v[2], c._v[2])):
+        assert torch.equal(x, y)
+    assert c.iteration == 5
+    sd['seed'] += 1
+    with pytest.raises(ValueError):
+        c.load_state_dict(sd)
+
+
 @pytest.mark.parametrize('reg_key', ['lognormal', 'l2'])
 def test_fused_vi_iteration_vs_oracle(built, reg_key):
     """one fused VI iteration against the oracle's restatement of reference trainer/trainer.py:130-171 (oracle.vi_iteration,
