@@ -43,7 +43,8 @@ const char* irs_error_string(int code);
 int irs_warp3d_fwd(const float* img, long long img_chain_stride, const float* T, const float* jitter_unit, float alpha,
                    float* out, int C, int D, int H, int W, void* stream);
 
-/* gradient of the above w.r.t. T (the autograd of F.grid_sample w.r.t. its grid): g_T (C,3,D,H,W) */
+/* gradient of the above w.r.t. T (the autograd of F.grid_sample w.r.t. its grid, reference utils/registration.py:29-30 inside
+ * loss.backward(), trainer/trainer.py:349): g_T (C,3,D,H,W) */
 int irs_warp3d_bwd_grid(const float* img, long long img_chain_stride, const float* T, const float* jitter_unit,
                         float alpha, const float* g_out, float* g_T, int C, int D, int H, int W, void* stream);
 
@@ -74,7 +75,8 @@ int irs_svf_exp_fwd(const float* v, float* hist, float* maxabs, int n_steps, int
 int irs_svf_outputs(const float* u, const float* lin_x, const float* lin_y, const float* lin_z, float* T, float* disp,
                     int C, int D, int H, int W, void* stream);
 
-/* adjoint: g_u (C,3,D,H,W) = dL/du_n  ->  g_v = dL/dv.  g_u is used as scratch and DESTROYED; g_work: C*3*D*H*W floats.
+/* adjoint (what autograd does for reference utils/transformation.py:63-76 inside loss.backward(), trainer/trainer.py:349):
+ * g_u (C,3,D,H,W) = dL/du_n  ->  g_v = dL/dv.  g_u is used as scratch and DESTROYED; g_work: C*3*D*H*W floats.
  * The interpolation transpose is computed as a GATHER over a window of radius floor(maxabs)+1 (no atomics); steps whose
  * radius exceeds gather_radius_max use an exact atomic scatter kernel instead. */
 int irs_svf_exp_bwd(const float* v, const float* hist, const float* maxabs, float* g_u, float* g_work, float* g_v,
@@ -142,13 +144,16 @@ int irs_lcc_normalise(const float* im, int s, float* a, float* rs, float* zn, in
 int irs_lcc_normalise_bwd(const float* g_zn, const float* a, const float* rs, int s, float* work, float* g_im,
                           int C, int D, int H, int W, void* stream);
 
-/* per-voxel mixture log-density and its derivatives.  gmm_host: K log_std then K logits (host floats).
+/* per-voxel mixture log-density and its derivatives (reference GMM.log_pdf / forward, model/loss.py:87-93,113-114, with
+ * log_proportions = log_softmax(logits + 1e-2), :67-69).  gmm_host: K log_std then K logits (host floats).
  *   logp[i] = log sum_k pi_k N(z_i; 0, sigma_k);  optional outputs: dz[i] = d logp_i / d z_i,
  *   g_params (2K doubles, device) = sum_i w_i d logp_i / d (log_std, logits), w = weights or 1 */
 int irs_gmm_log_pdf(const float* z, long long n, const float* gmm_host, int K, float* logp, float* dz,
                     const float* weights, double* g_params, double* partials, unsigned int* counter, void* stream);
 
-/* virtual decimation factor of one chain: residual z (D,H,W), mask (D,H,W) bytes, mixture as above -> alpha (1 double) */
+/* virtual decimation factor of one chain (reference rescale_residuals + calc_VD_factor, utils/util.py:330-347,446-485, called
+ * from Trainer.__get_VD_factor, trainer/trainer.py:507-514): residual z (D,H,W), mask (D,H,W) bytes, mixture as above ->
+ * alpha (1 double) */
 int irs_vd_factor(const float* z, const unsigned char* mask, const float* gmm_host, int K, double* alpha,
                   double* partials, unsigned int* counter, int D, int H, int W, void* stream);
 
@@ -293,8 +298,9 @@ typedef struct irs_sgld_buffers {
 
 size_t irs_sgld_partials_doubles(const irs_sgld_config* cfg);
 
-/* enqueue one transition on `stream` (about 46 kernel launches for any number of chains, 7 more with the FFD; capturable
- * in a CUDA graph) */
+/* enqueue one transition of all chains on `stream` = Trainer._SGLD_transition (reference trainer/trainer.py:291-356):
+ * irs_sgld_launches_per_step(cfg) kernel launches (41 at 128^3 with one chain; 7 more with the FFD), no host synchronisation,
+ * capturable in a CUDA graph */
 int irs_sgld_step(const irs_sgld_config* cfg, const irs_sgld_buffers* buf, void* stream);
 
 /* Profiling aid: one eager transition with a CUDA event between stages; synchronises the stream and writes the
