@@ -244,3 +244,66 @@ def test_chain_initialisation_matches_reference(ref, init):
         torch.manual_seed(5)
         b = sample_q_v(vp, no_samples=k)
         assert all(torch.equal(x, y) for x, y in zip(a if k == 2 else (a,), b if k == 2 else (b,)))
+
+
+@pytest.mark.parametrize('reg_name,reg_type', [('lognormal', 'RegLoss_LogNormal'), ('l2', 'RegLoss_L2')])
+def test_vi_iterations_match_reference_run_VI(ref, reg_name, reg_type, monkeypatch):
+    """
+    The unmodified Trainer._run_VI of the reference (trainer/trainer.py:119-223) for three iterations -- its own sample_q_v
+    draws, both antithetic sample losses, hyper-priors, the entropy terms, loss.backward(), the reference's Adam on
+    (mu, log_var, u) and on the regulariser's hyper-parameters, the mixture stepped twice per iteration -- against the oracle's
+    vi_iteration + AdamState fed the same random numbers.  Only I/O is stubbed (file writers, TensorBoard, SimpleITK metrics).
+    """
+    import types
+    import numpy as np
+    import trainer.trainer as ref_trainer_module
+    from irsgmcmc_b200.data_loader.synthetic import make_pair
+    n, iters, lr = 12, 3, 0.01
+    torch.manual_seed(123)
+    fixed, moving, vp0 = make_pair(n)
+    shape = (1, 3, n, n, n)
+    vp0 = {'mu': 0.2 * torch.randn(shape), 'log_var': vp0['log_var'] + 0.1 * torch.randn(shape), 'u': vp0['u'] + 0.05 * torch.randn(shape)}
+    jitters = [torch.rand(shape) for _ in range(2 * iters + 2)]
+
+    t = ref_import.make_trainer(ref, (n, n, n), 1, reg_type=reg_type, w_reg=1.6, uniform_noise=0.1)
+    t.losses['entropy'] = ref.loss.EntropyMultivariateNormal()
+    gmm, reg = t.losses['data']['loss'], t.losses['reg']['loss']
+    gmm.init_parameters(torch.tensor(1.0))
+    Adam = ref.optim.Adam
+    t.config = types.SimpleNamespace(init_optimizer_q_v=lambda vp: Adam(
+        [{'params': [vp['mu']], 'lr': lr}, {'params': [vp['log_var']], 'lr': lr}, {'params': [vp['u']], 'lr': lr}], lr_decay=1e-3))
+    t.start_iter_VI, t.no_iters_VI, t.log_period_VI = 1, iters, 10 ** 9
+    t.save_dirs, t.im_spacing, t.structures_dict = None, (1.0, 1.0, 1.0), {}
+    t.writer = types.SimpleNamespace(set_step=lambda *a, **k: None)
+    t.metrics = types.SimpleNamespace(update=lambda *a, **k: None)
+    for name in ('save_fixed_im', 'save_fixed_mask', 'save_moving_im', 'save_moving_mask', 'log_hist_res', 'log_images', 'log_fields'):
+        monkeypatch.setattr(ref_trainer_module, name, lambda *a, **k: None)
+    monkeypatch.setattr(ref_trainer_module, 'calc_metrics', lambda *a, **k: (np.zeros((1, 0)), np.zeros((1, 0))))
+    it_j = iter(jitters)
+    monkeypatch.setattr(ref.util, 'get_noise_uniform', lambda shape, device, alpha: -2.0 * alpha * next(it_j) + alpha)
+
+    vp_ref = {k: v.clone() for k, v in vp0.items()}
+    torch.manual_seed(77)
+    t._run_VI(fixed, moving, vp_ref)
+
+    # the oracle with the same numbers: per iteration randn_like(sigma), randn(1) (utils/sampler.py:14-15), two jitter fields
+    torch.manual_seed(77)
+    st = O.State(O.Config(reg=reg_name, w_reg=1.6), torch.zeros(shape), torch.ones(shape), (n, n, n))
+    st.init_gmm(1.0)
+    vp = {k: v.clone() for k, v in vp0.items()}
+    adam = O.AdamState([vp['mu'], vp['log_var'], vp['u']], [lr, lr, lr], 1e-3)
+    for i in range(iters):
+        eps, x = torch.randn(shape), torch.randn(1)
+        terms, grads = O.vi_iteration(st, fixed, moving, vp, eps, x, jitters[2 * i], jitters[2 * i + 1])
+        adam.step([grads['mu'], grads['log_var'], grads['u']])
+    # Adam's first steps have size lr whatever the gradient: compare the UPDATES, not the parameters
+    for k in ('mu', 'log_var', 'u'):
+        d_ref, d_or = vp_ref[k].detach() - vp0[k], vp[k] - vp0[k]
+        assert float(d_ref.abs().max()) > 0.5 * lr
+        assert rel(d_or, d_ref) < 1e-4, (k, rel(d_or, d_ref))   # measured 1.0e-5 ... 1.2e-5 (fp32, three iterations)
+    assert rel(st.log_std, gmm.log_std.detach()) < 1e-4 and rel(st.logits, gmm.logits.detach()) < 1e-3
+    if reg_name == 'lognormal':
+        assert abs(float(st.loc) - float(reg.loc)) < 1e-6 * abs(float(reg.loc)) and abs(float(st.log_scale) - float(reg.log_scale)) < 1e-6
+    else:
+        assert abs(float(st.log_w_reg) - float(reg.log_w_reg)) < 1e-6
+    assert t.optimizer_q_v.state[vp_ref['mu']]['step'] == iters == adam.step_no
