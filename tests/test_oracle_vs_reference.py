@@ -307,3 +307,100 @@ def test_vi_iterations_match_reference_run_VI(ref, reg_name, reg_type, monkeypat
     else:
         assert abs(float(st.log_w_reg) - float(reg.log_w_reg)) < 1e-6
     assert t.optimizer_q_v.state[vp_ref['mu']]['step'] == iters == adam.step_no
+
+
+@pytest.mark.parametrize('dtype', [torch.float64, torch.float32])
+def test_run_MCMC_loop_matches_reference(ref, monkeypatch, dtype):
+    """
+    The unmodified Trainer._run_MCMC of the reference (trainer/trainer.py:358-476): chain initialisation from q(v), burn-in, the
+    kept-sample rule, the host buffer of displacement samples and calc_posterior_statistics -- with its OWN random draws
+    (sample_q_v per chain, randn_like for the Langevin noise, rand for the jitter) -- against the oracle loop fed the same
+    generator: sgld_transition per iteration, kept samples by the same rule, posterior_statistics.  Only I/O is stubbed.
+    fp64 (the reference run under torch.set_default_dtype(float64)): the two loops must agree to rounding.  fp32: eight chained
+    transitions compound the isolated cell-face flips of the interpolation gradients (SURVEY surprise 9), so the
+    bound there only says "same random numbers, same loop" (a wrong draw order or kept-sample rule gives O(1)).
+    """
+    import types
+    import numpy as np
+    import trainer.trainer as ref_trainer_module
+    from irsgmcmc_b200.data_loader.synthetic import make_pair
+    n, C, burn_in, no_samples, period, tau = 12, 2, 2, 6, 2, 0.4
+    torch.manual_seed(123)
+    fixed, moving, vp0 = make_pair(n)
+    shape = (1, 3, n, n, n)
+    vp0 = {'mu': 0.2 * torch.randn(shape), 'log_var': vp0['log_var'] + 0.1 * torch.randn(shape), 'u': vp0['u'] + 0.05 * torch.randn(shape)}
+    cast = lambda d: {k: (v.to(dtype) if v.is_floating_point() else v) for k, v in d.items()}
+    fixed, moving, vp0 = cast(fixed), cast(moving), cast(vp0)
+    old_default = torch.get_default_dtype()
+    torch.set_default_dtype(dtype)      # the reference allocates its state and draws its noise in the default dtype
+    try:
+        t = ref_import.make_trainer(ref, (n, n, n), C, reg_type='RegLoss_LogNormal', w_reg=1.6, uniform_noise=0.1, tau=tau,
+                                    dtype=dtype if dtype == torch.float64 else None)
+        if dtype == torch.float64:  # RegistrationModule rejects fp64 (reference utils/registration.py:13-15,32)
+            t.registration_module = lambda im, T: F.grid_sample(
+                im if im.is_floating_point() else im.to(dtype), T.permute(0, 2, 3, 4, 1), mode='bilinear' if im.is_floating_point() else 'nearest',
+                padding_mode='border', align_corners=True)
+        gmm, reg = t.losses['data']['loss'], t.losses['reg']['loss']
+        gmm.init_parameters(torch.tensor(1.0))
+
+        class _Config(dict):
+            def init_obj(self, name, module, *args, **kwargs):      # parse_config.py:251-266
+                return getattr(module, self[name]['type'])(*args, **self[name]['args'], **kwargs)
+
+        t.config = _Config(optimizer_SG_MCMC={'type': 'SGD', 'args': {'lr': tau}})
+        t.MCMC_init, t.no_iters_burn_in, t.no_samples_MCMC, t.log_period_MCMC = 'VI', burn_in, no_samples, period
+        t.dims, t.no_voxels = (n, n, n), n ** 3
+        t.save_dirs, t.im_spacing, t.structures_dict = None, (1.0, 1.0, 1.0), {}
+        t.writer = types.SimpleNamespace(set_step=lambda *a, **k: None)
+        t.metrics = types.SimpleNamespace(update=lambda *a, **k: None)
+        t.logger = types.SimpleNamespace(info=lambda *a, **k: None)
+        for name in ('log_sample', 'log_hist_res', 'save_sample', 'log_displacement_mean_and_std_dev'):
+            monkeypatch.setattr(ref_trainer_module, name, lambda *a, **k: None)
+        monkeypatch.setattr(ref_trainer_module, 'calc_metrics', lambda *a, **k: (np.zeros((C, 0)), np.zeros((C, 0))))
+        # utils/util.py:114-120 defaults to device='cuda:0': the reference's own function, called with its own `device` argument
+        real_stats = ref_trainer_module.calc_posterior_statistics
+        monkeypatch.setattr(ref_trainer_module, 'calc_posterior_statistics', lambda samples: real_stats(samples, device='cpu'))
+        got = {}
+        monkeypatch.setattr(ref_trainer_module, 'save_displacement_mean_and_std_dev',
+                            lambda logger, dirs, spacing, mean, std, mask, model: got.update(mean=mean.clone(), std=std.clone()))
+        # the built-in speed test (100 more transitions, :467-476) runs after the statistics: stop it at its first transition
+        calls = {'n': 0}
+        real_transition = t._SGLD_transition
+
+        class _Stop(Exception):
+            pass
+
+        def counted(*a, **k):
+            calls['n'] += 1
+            if calls['n'] > burn_in + no_samples:
+                raise _Stop()
+            return real_transition(*a, **k)
+
+        t._SGLD_transition = counted
+        torch.manual_seed(77)
+        with pytest.raises(_Stop):
+            t._run_MCMC(fixed, moving, {k: v.clone() for k, v in vp0.items()})
+        assert calls['n'] == burn_in + no_samples + 1 and 'mean' in got
+
+        # the oracle loop with the same generator: per chain randn_like(sigma), randn(1); per transition randn, rand of (C,3,...)
+        torch.manual_seed(77)
+        sigma1 = torch.exp(0.5 * vp0['log_var'])
+        v0 = torch.cat([vp0['mu'] + torch.randn(shape) * sigma1 + torch.randn(1) * vp0['u'] for _ in range(C)], 0)
+        st = O.State(O.Config(reg='lognormal', w_reg=1.6, tau=tau, exact_grid=dtype == torch.float64), v0,
+                     sigma1.expand(C, -1, -1, -1, -1), (n, n, n), dtype)
+        st.init_gmm(1.0)
+        kept = []
+        for sample_no in range(1, burn_in + no_samples + 1):
+            eps, ju = torch.randn(C, 3, n, n, n), torch.rand(C, 3, n, n, n)
+            _, out, _, _ = O.sgld_transition(st, fixed, moving, eps, ju)
+            if sample_no > burn_in and (sample_no % period == 0 or sample_no == no_samples):     # trainer.py:414-415
+                kept.extend(out['displacement'][c] for c in range(C))
+    finally:
+        torch.set_default_dtype(old_default)
+    assert len(kept) == C * no_samples // period       # the reference's buffer size (:365-366): every row is filled
+    mean, std = O.posterior_statistics(torch.stack(kept))
+    e_v, e_mean, e_std = rel(st.v, t.v_curr_state.detach()), rel(mean, got['mean']), rel(std, got['std'])
+    e_gmm = rel(st.log_std, gmm.log_std.detach())
+    # measured: fp64 1.4e-13 / 7.5e-14 / 5.0e-14 / 1.5e-13; fp32 8.6e-3 / 7.4e-4 / 2.6e-4 / 3.5e-4
+    tol_v, tol = (1e-10, 1e-10) if dtype == torch.float64 else (5e-2, 1e-2)
+    assert e_v < tol_v and e_mean < tol and e_std < tol and e_gmm < tol, (e_v, e_mean, e_std, e_gmm)
