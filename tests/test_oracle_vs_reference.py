@@ -410,3 +410,27 @@ def test_run_MCMC_loop_matches_reference(ref, monkeypatch, dtype):
     # measured: fp64 1.4e-13 / 7.5e-14 / 5.0e-14 / 1.5e-13; fp32 8.6e-3 / 7.4e-4 / 2.6e-4 / 3.5e-4
     tol_v, tol = (1e-10, 1e-10) if dtype == torch.float64 else (5e-2, 1e-2)
     assert e_v < tol_v and e_mean < tol and e_std < tol and e_gmm < tol, (e_v, e_mean, e_std, e_gmm)
+
+
+def test_GMM_init_matches_reference(ref):
+    """Trainer.__GMM_init of the reference (trainer/trainer.py:529-547: one q(v) draw -> residuals -> sigma_hat -> linspace
+    initialisation -> VD factor -> 25 Adam steps on the mixture) against the oracle's gmm_init on the same draw"""
+    from irsgmcmc_b200.data_loader.synthetic import make_pair
+    n = 14
+    torch.manual_seed(123)
+    fixed, moving, vp0 = make_pair(n)
+    t = ref_import.make_trainer(ref, (n, n, n), 1, reg_type='RegLoss_LogNormal', w_reg=1.6)
+    gmm = t.losses['data']['loss']
+    torch.manual_seed(5)
+    t._Trainer__GMM_init(fixed, moving, {k: v.clone() for k, v in vp0.items()})
+    torch.manual_seed(5)
+    v_sample = vp0['mu'] + torch.randn_like(vp0['log_var']) * torch.exp(0.5 * vp0['log_var']) + torch.randn(1) * vp0['u']
+    st = O.State(O.Config(reg='lognormal', w_reg=1.6), torch.zeros(1, 3, n, n, n), torch.ones(1, 3, n, n, n), (n, n, n))
+    O.gmm_init(st, fixed, moving, v_sample)
+    # fp32, 25 chained Adam steps: measured 1.7e-5 / 5.1e-7
+    assert rel(st.log_std, gmm.log_std.detach()) < 1e-4 and rel(st.logits, gmm.logits.detach()) < 1e-4, \
+        (rel(st.log_std, gmm.log_std.detach()), rel(st.logits, gmm.logits.detach()))
+    assert t.optimizer_GMM.state[gmm.log_std]['step'] == 25 == st.adam_gmm.step_no
+    for mine, theirs in zip(st.adam_gmm.m + st.adam_gmm.v, [t.optimizer_GMM.state[q][k] for k in ('exp_avg', 'exp_avg_sq')
+                                                            for q in (gmm.log_std, gmm.logits)]):
+        assert rel(mine, theirs) < 1e-3
