@@ -400,6 +400,30 @@ def det_jacobian(nabla):
         - a[:, 2] * b[:, 1] * c[:, 0] - b[:, 2] * c[:, 1] * a[:, 0] - c[:, 2] * a[:, 1] * b[:, 0]
 
 
+def no_non_diffeomorphic_voxels(T):
+    """reference utils/util.py:209-212: log det J of the forward-difference Jacobian of a transformation; a voxel counts as
+    folded when the logarithm is NaN (det J < 0).  Returns (counts per sample, log det J)"""
+    log_det = det_jacobian(forward_differences(T, transformation=True)).log()
+    return torch.isnan(log_det).sum(dim=(1, 2, 3)), log_det
+
+
+def dice_scores(seg_fixed, seg_moving, labels):
+    """reference utils/util.py:123-148 (calc_DSC_GPU): per sample and structure 2 |A & B| / (|A| + |B|); 0 / 0 is NaN there
+    too (tensor division does not raise, so the `except` branch never runs)"""
+    out = torch.zeros(seg_moving.shape[0], len(labels))
+    for i in range(seg_moving.shape[0]):
+        a = seg_fixed[min(i, seg_fixed.shape[0] - 1)]
+        for j, label in enumerate(labels):
+            fa, mb = a == label, seg_moving[i] == label
+            out[i, j] = 2.0 * (fa & mb).sum() / (fa.sum() + mb.sum())
+    return out
+
+
+def field_norm(field):
+    """reference utils/util.py:215-225 (calc_norm): voxel-wise Euclidean norm, (N,1,D,H,W)"""
+    return torch.linalg.vector_norm(field, ord=2, dim=1, keepdim=True)
+
+
 def expgamma_log_pdf(x, shape, rate):
     """reference model/distributions.py:111-112,167-168"""
     return shape * math.log(rate) + (shape - 1) * x - rate * torch.exp(x) - math.lgamma(shape) + x

@@ -236,14 +236,42 @@ def ffd_vectors(ref):
     print('wrote ffd')
 
 
+def eval_vectors(ref):
+    """per-sample evaluation functions of the reference: calc_DSC_GPU (utils/util.py:123-148, runs on
+    CPU tensors as well), calc_no_non_diffeomorphic_voxels (:209-212) on a transformation that folds, calc_norm (:215-225)"""
+    out = {}
+    torch.manual_seed(21)
+    n, C = 24, 3
+    fixed, moving, _ = make_pair(n)
+    svf = ref.transformation.SVF_3D((n, n, n))
+    regm = ref.registration.RegistrationModule()
+    v = smooth_field((C, 3, n, n, n), 2.5, 9)
+    v[2] *= 6.0                                   # a deformation large enough to fold
+    T, disp = svf(v)
+    seg_w = regm(moving['seg'].expand(C, -1, -1, -1, -1).contiguous(), T)
+    labels = sorted(int(x) for x in torch.unique(fixed['seg']) if int(x) != 0)
+    structures = {f's{l}': l for l in labels}
+    out['labels'] = np.array(labels, dtype=np.int64)
+    out['seg_fixed'], out['seg_moving_warped'] = np32(fixed['seg']), np32(seg_w)
+    out['DSC'] = ref.util.calc_DSC_GPU(C, fixed['seg'].expand(C, -1, -1, -1, -1), seg_w, structures)
+    counts, log_det_J = ref.util.calc_no_non_diffeomorphic_voxels(T, ref.diff_op.GradientOperator())
+    assert counts[2] > 0 and counts[0] == 0, counts
+    out['T'], out['no_non_diffeomorphic_voxels'], out['log_det_J'] = np32(T), np.asarray(counts), np32(log_det_J)
+    out['disp'], out['disp_norm'] = np32(disp), np32(ref.util.calc_norm(disp))
+    np.savez_compressed(os.path.join(HERE, 'eval.npz'), **out)
+    print('wrote eval', counts, out['DSC'].shape)
+
+
 if __name__ == '__main__':
     ref = ref_import.load()
-    which = sys.argv[1:] or ['ops', 'transitions', 'ffd']
+    which = sys.argv[1:] or ['ops', 'transitions', 'ffd', 'eval']
     if 'ops' in which:
         op_vectors(ref)
     if 'transitions' in which:
         transition_vectors(ref, 12, 2, 'RegLoss_LogNormal', True, 1.6, 'lcc_lognormal')
         transition_vectors(ref, 12, 2, 'RegLoss_L2', True, 1.4, 'lcc_l2')
+    if 'eval' in which:
+        eval_vectors(ref)
     if 'ffd' in which:
         ffd_vectors(ref)
         transition_vectors(ref, 16, 2, 'RegLoss_LogNormal', True, 1.6, 'svffd_lognormal', cps=(4, 4, 4))

@@ -90,6 +90,20 @@ def test_oracle_diff_op_and_det_j(ops_gold):
     assert rel(O.det_jacobian(nab), ops_gold['det_J']) < 1e-5
 
 
+def test_oracle_evaluation_functions():
+    """per-sample evaluation: Dice, folded-voxel count / log det J on a transformation that folds, norms --
+    vectors from the reference's calc_DSC_GPU, calc_no_non_diffeomorphic_voxels, calc_norm (make_golden.py eval)"""
+    g = load('eval.npz')
+    labels = [int(x) for x in g['labels']]
+    assert torch.equal(O.dice_scores(g['seg_fixed'], g['seg_moving_warped'], labels), g['DSC'])
+    counts, log_det = O.no_non_diffeomorphic_voxels(g['T'])
+    assert counts.tolist() == g['no_non_diffeomorphic_voxels'].tolist() and counts[2] > 0
+    assert torch.equal(torch.isnan(log_det), torch.isnan(g['log_det_J']))
+    ok = ~torch.isnan(log_det)
+    assert rel(log_det[ok].exp(), g['log_det_J'][ok].exp()) < 1e-6
+    assert rel(O.field_norm(g['disp']), g['disp_norm']) < 1e-7
+
+
 def test_oracle_data_term(ops_gold):
     for s in (1, 2):
         z = O.lcc_map(ops_gold[f'lcc_s{s}_F'], ops_gold[f'lcc_s{s}_M'], s)
@@ -337,3 +351,26 @@ def test_cuda_svffd_transition_vs_reference_golden(built):
     O.gmm_init(st, fixed, moving, v_sample)
     ls, lg = r.gmm_parameters()
     assert rel(ls, st.log_std) < 1e-4 and rel(lg, st.logits) < 1e-3
+
+
+@pytest.mark.gpu
+def test_cuda_evaluation_kernels_vs_reference_golden(built):
+    """calc_DSC_GPU / calc_no_non_diffeomorphic_voxels / calc_norm of the drop-in package (CUDA kernels) against the vectors of
+    the reference's functions of the same names (utils/util.py:123-148,209-225)"""
+    import irsgmcmc_b200.utils as U
+    dev = 'cuda:0'
+    g = load('eval.npz')
+    labels = [int(x) for x in g['labels']]
+    C = g['seg_moving_warped'].shape[0]
+    structures = {f's{l}': l for l in labels}
+    dsc = U.calc_DSC_GPU(C, g['seg_fixed'].to(dev).expand(C, -1, -1, -1, -1), g['seg_moving_warped'].to(dev), structures)
+    assert np.allclose(dsc, g['DSC'].numpy(), rtol=1e-6, atol=0, equal_nan=True)
+    counts, log_det = U.calc_no_non_diffeomorphic_voxels(g['T'].to(dev), U.GradientOperator())
+    want = g['no_non_diffeomorphic_voxels'].numpy()
+    assert counts[0] == 0 and counts[1] == 0 and abs(int(counts[2]) - int(want[2])) <= 1, (counts, want)
+    nan_new, nan_ref = torch.isnan(log_det.cpu()), torch.isnan(g['log_det_J'])
+    assert int((nan_new != nan_ref).sum()) <= 1        # a determinant within rounding of zero may change sign
+    ok = ~(nan_new | nan_ref)
+    # fp32 determinants of a folding deformation: six products of O(10) cancel to O(1) (measured 3.5e-5; the oracle on the CPU: < 1e-6)
+    assert rel(log_det.cpu()[ok].exp(), g['log_det_J'][ok].exp()) < 2e-4
+    assert rel(U.calc_norm(g['disp'].to(dev)), g['disp_norm']) < 1e-5
